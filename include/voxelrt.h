@@ -1,0 +1,149 @@
+/*
+ * libvoxelrt — C-ABI of the B200-native rendering hot path for voxel-rt2.
+ *
+ * The reference has no FFI: its hot path sits behind the Python object `Scene.renderer`
+ * (renderer/pathtracer.py `class Renderer`) plus Taichi fields poked directly from scene.py.
+ * Each entry point below names the reference interface it replaces (file:line under the
+ * reference tree). The Python host (`voxel_rt2_b200/renderer.py`) mirrors `Renderer`'s method
+ * names on top of these calls, and `scene.py` keeps the reference's Scene API unchanged.
+ *
+ * Conventions: plain pointers and sizes only; every host pointer is caller-allocated and
+ * borrowed for the duration of the call; every function returns 0 on success or a negative
+ * vrt_status; the message for the last failure is vrt_last_error(ctx) (ctx may be NULL for
+ * creation failures). No C++ exceptions cross the boundary. A context is driven by one host
+ * thread; several contexts may coexist (one per GPU / per process).
+ */
+#ifndef VOXELRT_H
+#define VOXELRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vrt_status {
+  VRT_OK = 0,
+  VRT_ERR_CUDA = -1,
+  VRT_ERR_BAD_ARG = -2,
+  VRT_ERR_NOT_PREPARED = -3,
+  VRT_ERR_NO_DEVICE = -4,
+  VRT_ERR_OOM = -5
+} vrt_status;
+
+typedef struct vrt_ctx vrt_ctx;
+
+/* Construction parameters. Replaces the constants baked into the reference:
+ * SCREEN_RES / VOXEL_DX (scene.py:11-12), voxel_grid_res = 128 (pathtracer.py:83),
+ * MAX_RAY_DEPTH = 4 (pathtracer.py:17), skybox_res = 3840 (atmos.py:66-67),
+ * Renderer(dx, image_res, up, voxel_edges, exposure) (pathtracer.py:28). */
+typedef struct vrt_config {
+  int32_t width;        /* multiple of 8 */
+  int32_t height;       /* multiple of 4 */
+  int32_t grid_res;     /* R: power of two, 8..512 */
+  float voxel_dx;       /* world size of one voxel (1/64 at R=128) */
+  float voxel_edges;    /* Scene(voxel_edges=0.06) */
+  float exposure;       /* Scene(exposure=3) */
+  int32_t max_depth;    /* 1..8, reference 4 */
+  int32_t sky_res;      /* sky table resolution, reference 3840 */
+  int32_t cloud_passes; /* reference 32 (scene.py:199) */
+  int32_t device;       /* CUDA device ordinal */
+  uint32_t seed;
+  int32_t jitter_mode;  /* 0 = no TAA jitter, 1 = per-sample Halton(2,3) jitter (pathtracer.py:264-265) */
+  int32_t reserved[4];
+} vrt_config;
+
+/* One record of the primary-hit dump (north_star: "voxel id, face normal, hit t"). 32 bytes. */
+typedef struct vrt_hit {
+  float t;          /* world-space distance along the primary ray; +inf on miss */
+  int32_t cell[3];  /* grid cell [0,R)^3 for voxel hits, (-1,-1,-1) otherwise */
+  float normal[3];  /* raytracer.py:152-155 normal (components in {-1,0,1}; floor: (0,+-1,0)) */
+  uint32_t flags;   /* bits 0-7 kind (0 miss, 1 floor, 2 voxel); 8-15 shadow (0 lit, 1 occluded,
+                       2 back-facing: no ray, 3 n/a); 16-23 material id; 24-31 is_light */
+} vrt_hit;
+
+/* Counters of the last vrt_accumulate with stats enabled. */
+typedef struct vrt_stats {
+  uint64_t paths, rays, steps, queries, hits, sky_escapes, nee_visible, vertices;
+  float last_render_ms;   /* device time of the path kernel(s) in the last vrt_accumulate */
+  float last_resolve_ms;  /* device time of the last tonemap pass */
+  float sky_precompute_ms;
+  uint32_t kernel_launches; /* kernels launched by the last vrt_accumulate */
+} vrt_stats;
+
+/* Renderer.__init__ (pathtracer.py:28-136) */
+int vrt_create(const vrt_config* cfg, vrt_ctx** out);
+void vrt_destroy(vrt_ctx* ctx);
+const char* vrt_last_error(const vrt_ctx* ctx);
+
+/* Use a caller-owned CUDA stream (cudaStream_t as void*) for all work; NULL = library stream. */
+int vrt_set_stream(vrt_ctx* ctx, void* cuda_stream);
+
+/* Renderer.set_voxel/get_voxel storage (pathtracer.py:1325-1334, voxel_world.py:6-25):
+ * material int8 [R][R][R] and colour uint8 [R][R][R][3], C order, index = ijk + R/2. */
+int vrt_upload_voxels(vrt_ctx* ctx, const int8_t* material, const uint8_t* rgb);
+
+/* scene.py:233-237 -> Renderer.set_proj_mat / set_view_mat / set_camera_pos
+ * (pathtracer.py:246-281). Row-major 4x4 view and projection (GL convention). */
+int vrt_set_camera(vrt_ctx* ctx, const float pos[3], const float view[16], const float proj[16]);
+
+/* Renderer.set_directional_light (pathtracer.py:139-144): direction is normalised here,
+ * cos_theta_max = cos(cone_angle/2), radiance = 3 * rgb. */
+int vrt_set_light(vrt_ctx* ctx, const float direction[3], float cone_angle, const float rgb[3]);
+
+/* Scene.set_floor (scene.py:148-151) */
+int vrt_set_floor(vrt_ctx* ctx, float height, const float rgb[3], int32_t material);
+/* Scene.set_background_color (scene.py:156-157) */
+int vrt_set_background(vrt_ctx* ctx, const float rgb[3]);
+/* Scene.set_use_physical_sky / set_use_clouds (scene.py:159-169) */
+int vrt_set_sky(vrt_ctx* ctx, int32_t physical, int32_t clouds);
+/* MaterialList (materials.py:47-112): 128 rows x 14 floats (base_col rgb + 11 scalars). */
+int vrt_set_materials(vrt_ctx* ctx, const float* table128x14);
+/* Atmos.load_textures (atmos.py:85-90): uint8 [256][256][3] indexed [x][y] (imread layout). */
+int vrt_set_cloud_texture(vrt_ctx* ctx, const uint8_t* tex256x256x3);
+
+/* Renderer.prepare_data (pathtracer.py:314-323) + the sky start-up frames of Scene.finish
+ * (scene.py:243-253): bricks + occupancy mips + colour SoA; if the physical sky is on,
+ * transmittance LUT, cloud passes and the two sky tables. */
+int vrt_prepare(vrt_ctx* ctx);
+
+/* Sky tables as float3 [sky_res][sky_res] (atmos.py:68-69). get: copy out after vrt_prepare;
+ * set: install externally computed tables (skips the precompute in vrt_prepare). */
+int vrt_get_sky_tables(vrt_ctx* ctx, float* scattering, float* transmittance);
+int vrt_set_sky_tables(vrt_ctx* ctx, const float* scattering, const float* transmittance);
+/* Atmos.trans_LUT (atmos.py:63): binary16 bits [256][128][3] */
+int vrt_get_trans_lut(vrt_ctx* ctx, uint16_t* lut);
+
+/* Primary-hit dump (config 1): next_hit for the camera ray (pathtracer.py:218-244) and the
+ * sun shadow ray along the cone axis (pathtracer.py:435-450). out has width*height records,
+ * row-major with v (y) slowest: out[v*width + u]. */
+int vrt_trace_primary(vrt_ctx* ctx, vrt_hit* out);
+
+/* Renderer.accumulate (pathtracer.py:1310-1319) for sample indices first, first+stride, ...
+ * (n_samples of them). stats != 0 also fills the counters. */
+int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_t stride, int32_t stats);
+
+/* Only pixels in 8x4 tiles with tile_id % n == rank are rendered (tile sharding). Default 0,1. */
+int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n);
+
+/* Renderer.reset_framebuffer (pathtracer.py:664-668) */
+int vrt_reset(vrt_ctx* ctx);
+
+/* Device pointer of the float4 [height][width] accumulation buffer (rgb sums, w = samples),
+ * for device-side collectives (NCCL all-reduce through torch.distributed). */
+int vrt_accum_device_ptr(vrt_ctx* ctx, void** ptr, uint64_t* bytes);
+
+/* Renderer.color_buffer after accumulate: mean linear radiance, float4 [height][width]. */
+int vrt_fetch_hdr(vrt_ctx* ctx, float* rgba);
+/* Renderer.fetch_image / _render_to_image (pathtracer.py:634-662,1321-1323) */
+int vrt_fetch_ldr(vrt_ctx* ctx, float* rgba);
+/* Same pass, result left on the device (no copy): returns the device pointer. */
+int vrt_resolve_ldr_device(vrt_ctx* ctx, void** ptr);
+
+int vrt_get_stats(vrt_ctx* ctx, vrt_stats* out);
+int vrt_synchronize(vrt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXELRT_H */

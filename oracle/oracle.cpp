@@ -1,0 +1,560 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (never on the product path; the product fails loudly
+// without its CUDA library). CPU restatement (C++17 + OpenMP, float32, -ffp-contract=off) of
+// voxel-rt2's rendering hot path, exported with a flat C interface for ctypes:
+//   render            renderer/pathtracer.py:331-632 (non-ReSTIR estimator)
+//   accumulation      renderer/pathtracer.py:1185-1230,1242-1303 (static camera: running mean)
+//   NaN scrub         renderer/pathtracer.py:1068-1075
+//   tonemap           renderer/pathtracer.py:634-662, renderer/math_utils.py:160-186
+//   materials         renderer/materials.py:49-112 (table supplied by the host)
+// Traversal, BSDF and sky live in otrace.h / obsdf.h / osky.h.
+//
+// PARITY UNPINNED: the reference ships no golden vectors / tests and Taichi cannot be installed
+// here, so this restatement is pinned only by hand-derived known-answer tests (tests/) and a
+// brute-force traversal twin, not by outputs of the reference itself.
+#include <omp.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include "../include/voxelrt.h"
+#include "obsdf.h"
+#include "osky.h"
+#include "otrace.h"
+
+using namespace orc;
+
+namespace {
+
+struct Ctx {
+  Scene scene;
+  Sky sky;
+  std::vector<Mat> mats;  // 128
+  int max_depth = 4;
+  float exposure = 3.0f;
+  uint32_t seed = 0;
+  int jitter_mode = 0;
+  int cloud_passes = 32;
+  std::vector<float> hist_d, hist_s;  // vec4 per pixel (history_buffer / history_buffer_specular)
+  Counters counters;
+  double last_ms = 0;
+  int tile_rank = 0, tile_n = 1;
+};
+
+static const float RADIANCE_CLAMP = 300.0f;  // pathtracer.py:20
+static inline V3 firefly_filter(V3 v) { return clamp3(v, 0.0f, RADIANCE_CLAMP); }  // :22-24
+static inline float power_heuristic(float a, float b) {                              // :349-353
+  float a_sqr = a * a;
+  float p_sum = fmaxf_(a_sqr + b * b, 1e-4f);
+  return a_sqr / p_sum;
+}
+// math_utils.py:231-236
+static inline uint32_t encode_material(int mat_id, V3 albedo) {
+  uint32_t d0 = (uint32_t)mat_id, d1 = (uint32_t)(albedo.x * 255.0f), d2 = (uint32_t)(albedo.y * 255.0f),
+           d3 = (uint32_t)(albedo.z * 255.0f);
+  return d0 | (d1 << 8) | (d2 << 16) | (d3 << 24);
+}
+
+static inline const Mat& mat_at(const Ctx& c, int id) { return c.mats[id < 0 ? 0 : (id > 127 ? 127 : id)]; }
+
+struct PathOut {
+  V3 diffuse, specular;
+};
+
+// pathtracer.py:355-632 for one pixel sample, USE_RESTIR_PT = False, static camera.
+static void trace_path(const Ctx& c, int u, int v, uint32_t sample, Counters* cnt, PathOut& out) {
+  const Scene& s = c.scene;
+  const uint32_t key = path_key((uint32_t)(v * s.W + u), sample, c.seed);
+  V3 d = get_cast_dir(s, (float)u, (float)v);
+  V3 pos = s.cam_pos;
+  V3 contrib{0, 0, 0}, throughput{1, 1, 1};
+  uint32_t primary_mat_info = 0;
+  int first_bounce_lobe_id = 0;
+  float first_bounce_invpdf = 1.0f;
+  V3 first_NEE_d{0, 0, 0}, first_NEE_s{0, 0, 0};
+  float first_light_sample_bsdf_pdf = 1.0f;
+  bool is_sky_ray = false;
+  if (cnt) cnt->paths++;
+
+  for (int depth = 0; depth < c.max_depth; depth++) {
+    const uint32_t base = 8u * (uint32_t)depth;
+    Hit h = next_hit(s, pos, d, kInf, false, cnt);
+    Mat hit_mat = mat_at(c, h.mat_id);
+    V3 hit_pos = pos + h.closest * d;
+    if (depth == 0) primary_mat_info = encode_material(h.mat_id, h.albedo);
+
+    if (!h.hit_light && h.closest < kInf) {
+      if (cnt) cnt->vertices++;
+      V3 normal = h.normal;
+      pos = hit_pos + normal * kEps;
+      hit_mat.base_col = h.albedo;
+      V3 view = -d;
+      V3 tang, bitang;
+      make_orthonormal_basis(normal, tang, bitang);
+      float NEE_visible = 0.0f;
+      {
+        V3 light_dir = sample_cone_oriented(s.light_cos_max, s.light_dir, rnd(key, base + 0), rnd(key, base + 1));
+        float ndl = dot(light_dir, normal);
+        float light_sample_bsdf_pdf = pdf_disney(hit_mat, view, normal, light_dir, tang, bitang);
+        if (depth == 0) first_light_sample_bsdf_pdf = light_sample_bsdf_pdf;
+        if (ndl > 0.0f) {
+          Hit sh = next_hit(s, pos, light_dir, kInf, true, cnt);
+          if (sh.closest >= kInf) {
+            NEE_visible = 1.0f;
+            float mis = 1.0f;
+            if (depth > 0) mis = power_heuristic(cone_sample_pdf(s.light_cos_max, 1.0f), light_sample_bsdf_pdf);
+            V3 bd, bs;
+            disney_evaluate_split(hit_mat, view, normal, light_dir, tang, bitang, bd, bs);
+            V3 skyT{1, 1, 1};
+            if (s.use_physical_sky == 1) {
+              skyT = sample_skybox_transmittance(s.sky_trans, s.sky_res, light_dir);
+              if (cnt) cnt->N++;
+            }
+            V3 nee_d = mis * bd * skyT * s.light_weight * s.light_color * ndl;
+            V3 nee_s = mis * bs * skyT * s.light_weight * s.light_color * ndl;
+            if (depth == 0) {
+              first_NEE_d += firefly_filter(throughput * nee_d);
+              first_NEE_s += firefly_filter(throughput * nee_s);
+            } else {
+              contrib += firefly_filter(throughput * (nee_d + nee_s));
+            }
+          }
+        }
+      }
+      V3 bsdf;
+      float pdf;
+      int lobe_id;
+      d = sample_disney(hit_mat, view, normal, tang, bitang, rnd(key, base + 2), rnd(key, base + 3), rnd(key, base + 4), bsdf,
+                        pdf, lobe_id);
+      V3 bounce_weight = bsdf * saturate(dot(d, normal));
+      if (depth == 0) {
+        first_bounce_invpdf = 1.0f / pdf;
+        first_bounce_lobe_id = lobe_id;
+      } else {
+        bounce_weight = bounce_weight / pdf;
+        float bsdf_sample_light_pdf = cone_sample_pdf(s.light_cos_max, dot(s.light_dir, d));
+        bounce_weight *= power_heuristic(pdf, NEE_visible * bsdf_sample_light_pdf);
+      }
+      throughput *= bounce_weight;
+    } else {
+      if (h.closest == kInf) {
+        float hit_sun = dot(s.light_dir, d) >= s.light_cos_max ? 1.0f : 0.0f;
+        V3 sky_scattering = s.background;
+        V3 sky_T{1, 1, 1};
+        if (s.use_physical_sky == 1) {
+          sample_skybox(s.sky_scatter, s.sky_trans, s.sky_res, d, rnd(key, base + 5), rnd(key, base + 6), rnd(key, base + 7),
+                        sky_scattering, sky_T);
+          if (cnt) cnt->E++;
+        }
+        V3 sky_emission = firefly_filter(sky_scattering + sky_T * s.light_weight * s.light_color * hit_sun);
+        contrib += throughput * sky_emission;
+        if (depth == 0) is_sky_ray = true;
+      } else {
+        if (depth > 0) contrib += throughput * h.albedo;
+      }
+      break;
+    }
+  }
+
+  // primary-vertex MIS weight of the NEE sample (:556-579, non-ReSTIR branch)
+  if (!is_sky_ray) {
+    float light_sample_light_pdf = cone_sample_pdf(s.light_cos_max, 1.0f);
+    float w = power_heuristic(light_sample_light_pdf, first_light_sample_bsdf_pdf);
+    first_NEE_d *= w;
+    first_NEE_s *= w;
+  }
+  // :609-619
+  uint32_t pm = primary_mat_info & 255u;
+  V3 emission{0, 0, 0};
+  if (pm == 2u)
+    emission = V3{(float)((primary_mat_info >> 8) & 255u) / 255.0f, (float)((primary_mat_info >> 16) & 255u) / 255.0f,
+                  (float)((primary_mat_info >> 24) & 255u) / 255.0f};
+  V3 diffuse{0, 0, 0}, specular{0, 0, 0};
+  if (first_bounce_lobe_id == LOBE_DIFFUSE) diffuse += contrib * first_bounce_invpdf + emission;
+  if (first_bounce_lobe_id == LOBE_SPEC_REFL) specular += contrib * first_bounce_invpdf;
+  diffuse += first_NEE_d;
+  specular += first_NEE_s;
+  out.diffuse = diffuse;
+  out.specular = specular;
+}
+
+static inline bool bad3(V3 c) {  // pathtracer.py:1068-1075
+  return isbad(c.x) || isbad(c.y) || isbad(c.z) || c.x < 0.0f || c.y < 0.0f || c.z < 0.0f;
+}
+
+static double halton(uint32_t i, uint32_t b) {
+  double f = 1.0, r = 0.0;
+  while (i > 0) {
+    f /= (double)b;
+    r += f * (double)(i % b);
+    i /= b;
+  }
+  return r;
+}
+static void set_jitter(Ctx& c, uint32_t sample) {
+  // pathtracer.py:264-265: (rand*2-1) * inv_image_res, one draw per frame shared by all pixels.
+  if (c.jitter_mode == 1) {
+    c.scene.jitter[0] = (float)((halton(sample + 1, 2) * 2.0 - 1.0) / (double)c.scene.W);
+    c.scene.jitter[1] = (float)((halton(sample + 1, 3) * 2.0 - 1.0) / (double)c.scene.H);
+  } else {
+    c.scene.jitter[0] = c.scene.jitter[1] = 0.0f;
+  }
+}
+
+// math_utils.py:160-186 (all locals are f32 in the Taichi func)
+static inline V3 uchimura(V3 x) {
+  const float P = 1.0f, a = 1.0f, m = 0.22f, l = 0.4f, cc = 1.33f, b = 0.0f;
+  const float l0 = ((P - m) * l) / a;
+  const float S0 = m + l0;
+  const float S1 = m + a * l0;
+  const float C2 = (a * P) / (P - S1);
+  const float CP = -C2 / P;
+  V3 r;
+  for (int i = 0; i < 3; i++) {
+    float xi = x[i];
+    float t = clampf((xi - 0.0f) / (m - 0.0f), 0.0f, 1.0f);
+    float w0 = 1.0f - t * t * (3.0f - 2.0f * t);
+    float w2 = xi < m + l0 ? 0.0f : 1.0f;
+    float w1 = 1.0f - w0 - w2;
+    float T = m * std::pow(xi / m, cc) + b;
+    float S = P - (P - S1) * std::exp(CP * (xi - S0));
+    float L = m + a * (xi - m);
+    r.at(i) = T * w0 + L * w1 + S * w2;
+  }
+  return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* orc_create(int W, int H, int R, float voxel_dx, float voxel_edges, float exposure, int max_depth, uint32_t seed,
+                 int jitter_mode, int cloud_passes) {
+  Ctx* c = new Ctx();
+  c->scene.W = W, c->scene.H = H, c->scene.R = R;
+  c->scene.voxel_size = voxel_dx;
+  c->scene.voxel_inv_size = (float)(1.0 / (double)voxel_dx);  // voxel_world.py:11 (python float)
+  c->scene.voxel_edges = voxel_edges;
+  c->exposure = exposure, c->max_depth = max_depth, c->seed = seed, c->jitter_mode = jitter_mode;
+  c->cloud_passes = cloud_passes;
+  c->sky.seed = seed;
+  c->scene.material.assign((size_t)R * R * R, 0);
+  c->scene.color.assign((size_t)R * R * R * 3, 0);
+  c->mats.assign(128, Mat{V3{1, 1, 1}, 0.0f, 0.0f, 0.04f, 0.0f, 0.9f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f});
+  c->hist_d.assign((size_t)W * H * 4, 0.0f);
+  c->hist_s.assign((size_t)W * H * 4, 0.0f);
+  build_occupancy(c->scene);
+  // defaults: scene.py:127, pathtracer.py:91-93
+  double n = std::sqrt(3.0);
+  c->scene.light_dir = V3{(float)(1 / n), (float)(1 / n), (float)(1 / n)};
+  c->scene.light_cos_max = (float)std::cos(0.1 * 0.5);
+  return c;
+}
+void orc_destroy(void* p) { delete (Ctx*)p; }
+
+void orc_upload_voxels(void* p, const int8_t* mat, const uint8_t* rgb) {
+  Ctx* c = (Ctx*)p;
+  size_t n = (size_t)c->scene.R * c->scene.R * c->scene.R;
+  std::copy(mat, mat + n, c->scene.material.begin());
+  std::copy(rgb, rgb + 3 * n, c->scene.color.begin());
+  build_occupancy(c->scene);
+}
+// Inverses are formed here, in float64 Gauss-Jordan with partial pivoting, then rounded to
+// float32 (the reference inverts in-kernel with Taichi's inverse(), pathtracer.py:273,281).
+static bool invert4(const double m[16], double inv[16]) {
+  double a[4][8];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) a[i][j] = m[i * 4 + j], a[i][4 + j] = i == j ? 1.0 : 0.0;
+  for (int c = 0; c < 4; c++) {
+    int p = c;
+    for (int r = c + 1; r < 4; r++)
+      if (std::fabs(a[r][c]) > std::fabs(a[p][c])) p = r;
+    if (std::fabs(a[p][c]) < 1e-300) return false;
+    if (p != c)
+      for (int j = 0; j < 8; j++) std::swap(a[p][j], a[c][j]);
+    double d = a[c][c];
+    for (int j = 0; j < 8; j++) a[c][j] /= d;
+    for (int r = 0; r < 4; r++)
+      if (r != c) {
+        double f = a[r][c];
+        for (int j = 0; j < 8; j++) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) inv[i * 4 + j] = a[i][4 + j];
+  return true;
+}
+int orc_set_camera(void* p, const float* pos, const float* view, const float* proj) {
+  Ctx* c = (Ctx*)p;
+  double v[16], pr[16], vi[16], pi[16];
+  for (int i = 0; i < 16; i++) v[i] = view[i], pr[i] = proj[i];
+  if (!invert4(v, vi) || !invert4(pr, pi)) return -1;
+  c->scene.cam_pos = V3{pos[0], pos[1], pos[2]};
+  for (int i = 0; i < 16; i++) {
+    c->scene.view[i] = view[i], c->scene.proj[i] = proj[i];
+    c->scene.inv_view[i] = (float)vi[i], c->scene.inv_proj[i] = (float)pi[i];
+  }
+  return 0;
+}
+void orc_set_light(void* p, const float* dir, float cone_angle, const float* rgb) {
+  Ctx* c = (Ctx*)p;
+  double x = dir[0], y = dir[1], z = dir[2];
+  double n = std::sqrt(x * x + y * y + z * z);
+  c->scene.light_dir = V3{(float)(x / n), (float)(y / n), (float)(z / n)};
+  c->scene.light_cos_max = (float)std::cos((double)cone_angle * 0.5);
+  c->scene.light_color = V3{rgb[0], rgb[1], rgb[2]};
+  c->scene.light_weight = 3.0f;
+}
+void orc_set_floor(void* p, float h, const float* rgb, int mat) {
+  Ctx* c = (Ctx*)p;
+  c->scene.floor_height = h;
+  c->scene.floor_color = V3{rgb[0], rgb[1], rgb[2]};
+  c->scene.floor_material = mat;
+}
+void orc_set_background(void* p, const float* rgb) { ((Ctx*)p)->scene.background = V3{rgb[0], rgb[1], rgb[2]}; }
+void orc_set_sky(void* p, int physical, int clouds) {
+  Ctx* c = (Ctx*)p;
+  c->scene.use_physical_sky = physical ? 1 : 0;
+  c->sky.use_clouds = clouds ? 1 : 0;
+}
+void orc_set_materials(void* p, const float* t) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < 128; i++) {
+    const float* r = t + i * 14;
+    c->mats[i] = Mat{V3{r[0], r[1], r[2]}, r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13]};
+  }
+}
+void orc_set_cloud_texture(void* p, const uint8_t* tex) {
+  Ctx* c = (Ctx*)p;
+  c->sky.cloud_tex.assign(tex, tex + 256 * 256 * 3);
+}
+static void bind_sky(Ctx* c) {
+  c->scene.sky_res = c->sky.S;
+  c->scene.sky_scatter = c->sky.scatter.data();
+  c->scene.sky_trans = c->sky.trans.data();
+}
+void orc_precompute_sky(void* p, int sky_res) {
+  Ctx* c = (Ctx*)p;
+  if (c->sky.cloud_tex.empty()) c->sky.cloud_tex.assign(256 * 256 * 3, 0);
+  V3 sun_col = c->scene.light_color * c->scene.light_weight;  // pathtracer.py:320,326,329
+  precompute_sky(c->sky, sky_res, c->scene.light_dir, sun_col, c->scene.light_cos_max, c->cloud_passes);
+  bind_sky(c);
+}
+void orc_set_sky_tables(void* p, int S, const float* scat, const float* trans) {
+  Ctx* c = (Ctx*)p;
+  c->sky.S = S;
+  c->sky.scatter.assign(scat, scat + (size_t)S * S * 3);
+  c->sky.trans.assign(trans, trans + (size_t)S * S * 3);
+  bind_sky(c);
+}
+void orc_get_sky_tables(void* p, float* scat, float* trans) {
+  Ctx* c = (Ctx*)p;
+  std::copy(c->sky.scatter.begin(), c->sky.scatter.end(), scat);
+  std::copy(c->sky.trans.begin(), c->sky.trans.end(), trans);
+}
+void orc_get_trans_lut(void* p, uint16_t* lut) {
+  Ctx* c = (Ctx*)p;
+  if (c->sky.trans_lut.empty()) generate_transmittance_lut(c->sky);
+  std::copy(c->sky.trans_lut.begin(), c->sky.trans_lut.end(), lut);
+}
+void orc_get_cloud_ambient(void* p, float* out) {
+  Ctx* c = (Ctx*)p;
+  out[0] = c->sky.cloud_ambient.x, out[1] = c->sky.cloud_ambient.y, out[2] = c->sky.cloud_ambient.z;
+}
+void orc_set_tile_shard(void* p, int rank, int n) {
+  Ctx* c = (Ctx*)p;
+  c->tile_rank = rank, c->tile_n = n;
+}
+
+// Primary-hit dump, same record layout as vrt_trace_primary.
+void orc_trace_primary(void* p, vrt_hit* out) {
+  Ctx* c = (Ctx*)p;
+  Scene& s = c->scene;
+  s.jitter[0] = s.jitter[1] = 0.0f;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int v = 0; v < s.H; v++)
+    for (int u = 0; u < s.W; u++) {
+      V3 d = get_cast_dir(s, (float)u, (float)v);
+      Hit h = next_hit(s, s.cam_pos, d, kInf, false, nullptr);
+      vrt_hit& o = out[(size_t)v * s.W + u];
+      o.t = h.closest;
+      int kind = h.closest < kInf ? h.kind : 0;
+      o.cell[0] = kind == 2 ? h.cell.x : -1, o.cell[1] = kind == 2 ? h.cell.y : -1, o.cell[2] = kind == 2 ? h.cell.z : -1;
+      o.normal[0] = h.normal.x, o.normal[1] = h.normal.y, o.normal[2] = h.normal.z;
+      uint32_t shadow = 3;
+      if (!h.hit_light && h.closest < kInf) {
+        V3 hit_pos = s.cam_pos + h.closest * d;
+        V3 pos = hit_pos + h.normal * kEps;
+        float ndl = dot(s.light_dir, h.normal);
+        if (ndl > 0.0f) {
+          Hit sh = next_hit(s, pos, s.light_dir, kInf, true, nullptr);
+          shadow = sh.closest >= kInf ? 0u : 1u;
+        } else {
+          shadow = 2u;
+        }
+      }
+      o.flags = (uint32_t)kind | (shadow << 8) | (((uint32_t)h.mat_id & 255u) << 16) | ((uint32_t)(h.hit_light ? 1 : 0) << 24);
+    }
+}
+
+// accumulate(): render + static-camera temporal filters, one frame per sample index.
+void orc_accumulate(void* p, int first_sample, int n_samples, int stride, int stats, int n_threads) {
+  Ctx* c = (Ctx*)p;
+  Scene& s = c->scene;
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+  double t0 = omp_get_wtime();
+  const float max_accum = 999999999.0f;  // scene.py:210
+  const int tiles_x = s.W / 8;
+  for (int k = 0; k < n_samples; k++) {
+    uint32_t sample = (uint32_t)(first_sample + k * stride);
+    set_jitter(*c, sample);
+    Counters total;
+#pragma omp parallel
+    {
+      Counters local;
+#pragma omp for schedule(dynamic, 2)
+      for (int v = 0; v < s.H; v++)
+        for (int u = 0; u < s.W; u++) {
+          if (c->tile_n > 1) {
+            int tile = (v / 4) * tiles_x + (u / 8);
+            if (tile % c->tile_n != c->tile_rank) continue;
+          }
+          PathOut o;
+          trace_path(*c, u, v, sample, stats ? &local : nullptr, o);
+          if (bad3(o.diffuse)) o.diffuse = V3{0, 0, 0};
+          if (bad3(o.specular)) o.specular = V3{0, 0, 0};
+          float* hd = &c->hist_d[((size_t)v * s.W + u) * 4];
+          float* hs = &c->hist_s[((size_t)v * s.W + u) * 4];
+          hd[3] = fminf_(hd[3] + 1.0f, max_accum);
+          float wd = 1.0f / hd[3];
+          hd[0] = mixf(hd[0], o.diffuse.x, wd), hd[1] = mixf(hd[1], o.diffuse.y, wd), hd[2] = mixf(hd[2], o.diffuse.z, wd);
+          hs[3] = fminf_(hs[3] + 1.0f, max_accum);
+          float ws = 1.0f / hs[3];
+          hs[0] = mixf(hs[0], o.specular.x, ws), hs[1] = mixf(hs[1], o.specular.y, ws), hs[2] = mixf(hs[2], o.specular.z, ws);
+        }
+#pragma omp critical
+      total.add(local);
+    }
+    c->counters.add(total);
+  }
+  c->last_ms = (omp_get_wtime() - t0) * 1e3;
+}
+double orc_last_ms(void* p) { return ((Ctx*)p)->last_ms; }
+void orc_reset(void* p) {
+  Ctx* c = (Ctx*)p;
+  std::fill(c->hist_d.begin(), c->hist_d.end(), 0.0f);
+  std::fill(c->hist_s.begin(), c->hist_s.end(), 0.0f);
+  c->counters = Counters();
+}
+void orc_get_counters(void* p, uint64_t* out) {
+  const Counters& k = ((Ctx*)p)->counters;
+  out[0] = k.paths, out[1] = k.rays, out[2] = k.steps, out[3] = k.Q, out[4] = k.H, out[5] = k.E, out[6] = k.N,
+  out[7] = k.vertices;
+}
+// color_buffer = diffuse history + specular history (pathtracer.py:1230,1295); w = sample count
+void orc_fetch_hdr(void* p, float* rgba) {
+  Ctx* c = (Ctx*)p;
+  size_t n = (size_t)c->scene.W * c->scene.H;
+  for (size_t i = 0; i < n; i++) {
+    rgba[i * 4 + 0] = c->hist_d[i * 4 + 0] + c->hist_s[i * 4 + 0];
+    rgba[i * 4 + 1] = c->hist_d[i * 4 + 1] + c->hist_s[i * 4 + 1];
+    rgba[i * 4 + 2] = c->hist_d[i * 4 + 2] + c->hist_s[i * 4 + 2];
+    rgba[i * 4 + 3] = c->hist_d[i * 4 + 3];
+  }
+}
+// _render_to_image (pathtracer.py:634-662) applied to an arbitrary HDR buffer
+void orc_tonemap(void* p, const float* hdr_rgba, float* ldr_rgba) {
+  Ctx* c = (Ctx*)p;
+  int W = c->scene.W, H = c->scene.H;
+  for (int j = 0; j < H; j++)
+    for (int i = 0; i < W; i++) {
+      size_t k = ((size_t)j * W + i) * 4;
+      float uvx = (float)i / (float)W, uvy = (float)j / (float)H;
+      float dx = uvx - 0.5f, dy = uvy - 0.5f;
+      float dist = std::sqrt(dx * dx + dy * dy);
+      float darken = 1.0f - 0.9f * fmaxf_(dist - 0.0f, 0.0f);
+      V3 hdr{hdr_rgba[k], hdr_rgba[k + 1], hdr_rgba[k + 2]};
+      V3 tm = uchimura(hdr * darken * c->exposure);
+      ldr_rgba[k + 0] = saturate(std::pow(tm.x, 1.0f / 2.2f));
+      ldr_rgba[k + 1] = saturate(std::pow(tm.y, 1.0f / 2.2f));
+      ldr_rgba[k + 2] = saturate(std::pow(tm.z, 1.0f / 2.2f));
+      ldr_rgba[k + 3] = 1.0f;
+    }
+}
+void orc_fetch_ldr(void* p, float* rgba) {
+  Ctx* c = (Ctx*)p;
+  std::vector<float> hdr((size_t)c->scene.W * c->scene.H * 4);
+  orc_fetch_hdr(p, hdr.data());
+  orc_tonemap(p, hdr.data(), rgba);
+}
+
+// ------------------------------------------------------------------ unit probes for tests
+// raytrace() in voxel space for n rays (raytracer.py:72-155)
+void orc_raytrace(void* p, int n, const float* o, const float* d, float* t, int* cell, float* normal, int* iters) {
+  Ctx* c = (Ctx*)p;
+#pragma omp parallel for
+  for (int i = 0; i < n; i++) {
+    RayHit h = raytrace(c->scene, V3{o[3 * i], o[3 * i + 1], o[3 * i + 2]}, V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]}, kEps, kInf,
+                        nullptr);
+    t[i] = h.t;
+    cell[3 * i] = h.cell.x, cell[3 * i + 1] = h.cell.y, cell[3 * i + 2] = h.cell.z;
+    normal[3 * i] = h.normal.x, normal[3 * i + 1] = h.normal.y, normal[3 * i + 2] = h.normal.z;
+    iters[i] = h.iters;
+  }
+}
+// occupancy bit of (x,y,z) at lod
+int orc_occupancy(void* p, int x, int y, int z, int lod) {
+  Ctx* c = (Ctx*)p;
+  if (lod < 0 || lod >= c->scene.n_lods) return -1;
+  return c->scene.occ_bit(x, y, z, lod) ? 1 : 0;
+}
+// BSDF probes: for n (mat_id, albedo, v, n, l, u3) tuples return
+// out[n][12] = {eval_d rgb, eval_s rgb, pdf_disney, sample_dir xyz, sample_pdf, lobe} + brdf rgb -> 15 floats
+void orc_bsdf_probe(void* p, int n, const int* mat_id, const float* albedo, const float* v, const float* nrm, const float* l,
+                    const float* u3, float* out) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < n; i++) {
+    Mat m = mat_at(*c, mat_id[i]);
+    m.base_col = V3{albedo[3 * i], albedo[3 * i + 1], albedo[3 * i + 2]};
+    V3 vv{v[3 * i], v[3 * i + 1], v[3 * i + 2]}, nn{nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]},
+        ll{l[3 * i], l[3 * i + 1], l[3 * i + 2]};
+    V3 tang, bitang;
+    make_orthonormal_basis(nn, tang, bitang);
+    V3 bd, bs;
+    disney_evaluate_split(m, vv, nn, ll, tang, bitang, bd, bs);
+    float pdf = pdf_disney(m, vv, nn, ll, tang, bitang);
+    V3 brdf;
+    float spdf;
+    int lobe;
+    V3 dir = sample_disney(m, vv, nn, tang, bitang, u3[3 * i], u3[3 * i + 1], u3[3 * i + 2], brdf, spdf, lobe);
+    float* o = out + 15 * i;
+    o[0] = bd.x, o[1] = bd.y, o[2] = bd.z, o[3] = bs.x, o[4] = bs.y, o[5] = bs.z, o[6] = pdf;
+    o[7] = dir.x, o[8] = dir.y, o[9] = dir.z, o[10] = spdf, o[11] = (float)lobe, o[12] = brdf.x, o[13] = brdf.y, o[14] = brdf.z;
+  }
+}
+// sky probes: project/unproject and table lookups for n directions
+void orc_project_sky(int n, int S, const float* d, float* uv) {
+  for (int i = 0; i < n; i++) {
+    V2 t = project_sky(V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]}, 1.0f / (float)S);
+    uv[2 * i] = t.x, uv[2 * i + 1] = t.y;
+  }
+}
+void orc_unproject_sky(int n, int S, const float* uv, float* d) {
+  for (int i = 0; i < n; i++) {
+    V3 r = unproject_sky(V2{uv[2 * i], uv[2 * i + 1]}, 1.0f / (float)S);
+    d[3 * i] = r.x, d[3 * i + 1] = r.y, d[3 * i + 2] = r.z;
+  }
+}
+void orc_sample_sky_trans(void* p, int n, const float* d, float* out) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < n; i++) {
+    V3 r = sample_skybox_transmittance(c->scene.sky_trans, c->scene.sky_res, V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]});
+    out[3 * i] = r.x, out[3 * i + 1] = r.y, out[3 * i + 2] = r.z;
+  }
+}
+float orc_rnd(uint32_t pixel, uint32_t sample, uint32_t seed, uint32_t dim) { return rnd(path_key(pixel, sample, seed), dim); }
+uint16_t orc_f32_to_f16(float f) { return f32_to_f16_bits(f); }
+float orc_f16_to_f32(uint16_t h) { return f16_bits_to_f32(h); }
+int orc_num_threads() { return omp_get_max_threads(); }
+
+}  // extern "C"

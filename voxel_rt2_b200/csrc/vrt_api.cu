@@ -1,0 +1,614 @@
+// C-ABI of libvoxelrt (see include/voxelrt.h for the reference interfaces each call replaces).
+// Host side only: context, device memory, parameter marshalling, launches. No CPU fallback: if
+// there is no CUDA device, vrt_create fails with VRT_ERR_NO_DEVICE.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vrt_internal.h"
+
+struct vrt_ctx {
+  vrt_config cfg;
+  int device = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // voxel world
+  int8_t* d_mat = nullptr;
+  uint8_t* d_rgb = nullptr;
+  unsigned long long* d_bricks = nullptr;
+  uint32_t* d_color = nullptr;
+  uint32_t* d_upper = nullptr;
+  uint32_t upper_off[8] = {0};
+  int n_lods = 0, upper_words = 0;
+  bool voxels_uploaded = false, prepared = false;
+
+  // uniforms
+  float cam_pos[3] = {0.4f, 0.5f, 2.0f};
+  float inv_proj[16], inv_view[16];
+  bool camera_set = false;
+  float light_dir[3], light_cos_max, light_color[3] = {0, 0, 0};
+  float floor_height = 0.0f, floor_color[3] = {1, 1, 1};
+  int floor_material = 1;
+  float background[3] = {0, 0, 0};
+  int use_sky = 0, use_clouds = 0;
+
+  // tables
+  float4* d_mats = nullptr;
+  float4* d_sky_scatter = nullptr;
+  float4* d_sky_trans = nullptr;
+  __half* d_trans_lut = nullptr;
+  uint8_t* d_cloud_tex = nullptr;
+  float* d_cloud_ambient = nullptr;
+  bool sky_valid = false, cloud_tex_set = false;
+
+  // frame buffers
+  float4* d_accum = nullptr;
+  float4* d_out = nullptr;  // resolve target (hdr or ldr)
+  vrt_hit* d_hits = nullptr;
+  float2* d_jitter = nullptr;
+  int jitter_cap = 0;
+  unsigned int* d_work = nullptr;
+  unsigned long long* d_stats = nullptr;
+
+  int tile_rank = 0, tile_n = 1;
+  vrt_stats stats;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      char buf_[512];                                                                  \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = buf_;                                                                 \
+      return e_ == cudaErrorMemoryAllocation ? VRT_ERR_OOM : VRT_ERR_CUDA;              \
+    }                                                                                  \
+  } while (0)
+
+#define REQUIRE(cond, msg)      \
+  do {                          \
+    if (!(cond)) {              \
+      ctx->err = msg;           \
+      return VRT_ERR_BAD_ARG;   \
+    }                           \
+  } while (0)
+
+static bool invert4(const double m[16], double inv[16]) {
+  double a[4][8];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) a[i][j] = m[i * 4 + j], a[i][4 + j] = i == j ? 1.0 : 0.0;
+  for (int c = 0; c < 4; c++) {
+    int p = c;
+    for (int r = c + 1; r < 4; r++)
+      if (std::fabs(a[r][c]) > std::fabs(a[p][c])) p = r;
+    if (std::fabs(a[p][c]) < 1e-300) return false;
+    if (p != c)
+      for (int j = 0; j < 8; j++) std::swap(a[p][j], a[c][j]);
+    double d = a[c][c];
+    for (int j = 0; j < 8; j++) a[c][j] /= d;
+    for (int r = 0; r < 4; r++)
+      if (r != c) {
+        double f = a[r][c];
+        for (int j = 0; j < 8; j++) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) inv[i * 4 + j] = a[i][4 + j];
+  return true;
+}
+
+static double halton(uint32_t i, uint32_t b) {
+  double f = 1.0, r = 0.0;
+  while (i > 0) {
+    f /= (double)b;
+    r += f * (double)(i % b);
+    i /= b;
+  }
+  return r;
+}
+
+static void default_materials(float* t) {  // materials.py:50-63
+  for (int i = 0; i < 128; i++) {
+    float* r = t + i * 16;
+    memset(r, 0, 16 * sizeof(float));
+    r[0] = r[1] = r[2] = 1.0f;
+    r[5] = 0.04f;  // specular
+    r[7] = 0.9f;   // roughness
+  }
+}
+
+static int n_local_tiles(const vrt_ctx* ctx) {
+  int total = (ctx->cfg.width / 8) * (ctx->cfg.height / 4);
+  if (ctx->tile_rank >= total) return 0;
+  return (total - ctx->tile_rank + ctx->tile_n - 1) / ctx->tile_n;
+}
+
+static void fill_params(const vrt_ctx* ctx, Params& P) {
+  memset(&P, 0, sizeof P);
+  const vrt_config& c = ctx->cfg;
+  P.bricks = ctx->d_bricks, P.upper = ctx->d_upper, P.color = ctx->d_color;
+  P.R = c.grid_res, P.n_lods = ctx->n_lods, P.brick_res = c.grid_res / 4, P.upper_words = ctx->upper_words;
+  for (int i = 0; i < 8; i++) P.upper_off[i] = ctx->upper_off[i];
+  P.voxel_size = c.voxel_dx;
+  P.voxel_inv_size = (float)(1.0 / (double)c.voxel_dx);  // voxel_world.py:11
+  P.voxel_edges = c.voxel_edges;
+  P.grid_half = (float)(c.grid_res / 2);
+  P.floor_height = ctx->floor_height;
+  P.floor_color = f3{ctx->floor_color[0], ctx->floor_color[1], ctx->floor_color[2]};
+  P.floor_material = ctx->floor_material;
+  P.light_dir = f3{ctx->light_dir[0], ctx->light_dir[1], ctx->light_dir[2]};
+  P.light_cos_max = ctx->light_cos_max;
+  P.light_color = f3{ctx->light_color[0], ctx->light_color[1], ctx->light_color[2]};
+  P.light_weight = 3.0f;  // pathtracer.py:144
+  P.background = f3{ctx->background[0], ctx->background[1], ctx->background[2]};
+  P.use_sky = ctx->use_sky && ctx->sky_valid;
+  P.cam_pos = f3{ctx->cam_pos[0], ctx->cam_pos[1], ctx->cam_pos[2]};
+  memcpy(P.inv_proj, ctx->inv_proj, sizeof P.inv_proj);
+  memcpy(P.inv_view, ctx->inv_view, sizeof P.inv_view);
+  P.W = c.width, P.H = c.height;
+  P.sky_scatter = ctx->d_sky_scatter, P.sky_trans = ctx->d_sky_trans, P.sky_res = c.sky_res;
+  P.mats = ctx->d_mats;
+  P.accum = ctx->d_accum;
+  P.seed = c.seed;
+  P.max_depth = c.max_depth;
+  P.tile_rank = ctx->tile_rank, P.tile_n = ctx->tile_n;
+  P.tiles_x = c.width / 8;
+  P.n_tiles = n_local_tiles(ctx);
+  P.work_counter = ctx->d_work;
+  P.stats = nullptr;
+  P.jitter = ctx->d_jitter;
+}
+
+extern "C" {
+
+const char* vrt_last_error(const vrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+void vrt_destroy(vrt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_mat), cudaFree(ctx->d_rgb), cudaFree(ctx->d_bricks), cudaFree(ctx->d_color), cudaFree(ctx->d_upper);
+  cudaFree(ctx->d_mats), cudaFree(ctx->d_sky_scatter), cudaFree(ctx->d_sky_trans), cudaFree(ctx->d_trans_lut);
+  cudaFree(ctx->d_cloud_tex), cudaFree(ctx->d_cloud_ambient), cudaFree(ctx->d_accum), cudaFree(ctx->d_out), cudaFree(ctx->d_hits);
+  cudaFree(ctx->d_jitter), cudaFree(ctx->d_work), cudaFree(ctx->d_stats);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int vrt_create(const vrt_config* cfg, vrt_ctx** out) {
+  if (!cfg || !out) {
+    g_create_err = "vrt_create: null argument";
+    return VRT_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  const int R = cfg->grid_res;
+  if (cfg->width <= 0 || cfg->height <= 0 || cfg->width % 8 || cfg->height % 4) {
+    g_create_err = "vrt_create: width must be a positive multiple of 8 and height of 4";
+    return VRT_ERR_BAD_ARG;
+  }
+  if (R < 8 || R > 512 || (R & (R - 1))) {
+    g_create_err = "vrt_create: grid_res must be a power of two in [8, 512]";
+    return VRT_ERR_BAD_ARG;
+  }
+  if (cfg->max_depth < 1 || cfg->max_depth > 8 || !(cfg->voxel_dx > 0.0f) || cfg->sky_res < 0 || cfg->sky_res > 8192 ||
+      cfg->cloud_passes < 0) {
+    g_create_err = "vrt_create: bad max_depth / voxel_dx / sky_res / cloud_passes";
+    return VRT_ERR_BAD_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("vrt_create: no CUDA device (") + cudaGetErrorString(e) + "); libvoxelrt has no CPU path";
+    return VRT_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_err = "vrt_create: device ordinal out of range";
+    return VRT_ERR_BAD_ARG;
+  }
+  vrt_ctx* ctx = new vrt_ctx();
+  ctx->cfg = *cfg;
+  ctx->device = cfg->device;
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  auto fail = [&](int code) {
+    g_create_err = ctx->err;
+    vrt_destroy(ctx);
+    return code;
+  };
+#define CKC(call)                                                                         \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ctx->err = std::string(#call " failed: ") + cudaGetErrorString(e_);                 \
+      return fail(e_ == cudaErrorMemoryAllocation ? VRT_ERR_OOM : VRT_ERR_CUDA);           \
+    }                                                                                     \
+  } while (0)
+  CKC(cudaSetDevice(ctx->device));
+  CKC(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+  CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = true;
+  CKC(cudaEventCreate(&ctx->ev0));
+  CKC(cudaEventCreate(&ctx->ev1));
+
+  const size_t nvox = (size_t)R * R * R;
+  ctx->n_lods = 0;
+  while ((1 << ctx->n_lods) < R) ctx->n_lods++;
+  ctx->upper_words = 0;
+  for (int l = 3; l < ctx->n_lods; l++) {
+    size_t r = (size_t)(R >> l);
+    ctx->upper_off[l - 3] = (uint32_t)ctx->upper_words;
+    ctx->upper_words += (int)((r * r * r + 31) / 32);
+  }
+  CKC(cudaMalloc(&ctx->d_mat, nvox));
+  CKC(cudaMalloc(&ctx->d_rgb, nvox * 3));
+  CKC(cudaMalloc(&ctx->d_bricks, nvox / 64 * sizeof(unsigned long long)));
+  CKC(cudaMalloc(&ctx->d_color, nvox * 4));
+  CKC(cudaMalloc(&ctx->d_upper, (size_t)(ctx->upper_words > 0 ? ctx->upper_words : 1) * 4));
+  CKC(cudaMalloc(&ctx->d_mats, 128 * 16 * sizeof(float)));
+  const size_t npx = (size_t)cfg->width * cfg->height;
+  CKC(cudaMalloc(&ctx->d_accum, npx * sizeof(float4)));
+  CKC(cudaMalloc(&ctx->d_out, npx * sizeof(float4)));
+  CKC(cudaMemsetAsync(ctx->d_accum, 0, npx * sizeof(float4), ctx->stream));
+  CKC(cudaMalloc(&ctx->d_work, sizeof(unsigned int)));
+  CKC(cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)));
+  CKC(cudaMalloc(&ctx->d_cloud_ambient, 3 * sizeof(float)));
+  CKC(cudaMalloc(&ctx->d_cloud_tex, 256 * 256 * 3));
+  CKC(cudaMemsetAsync(ctx->d_cloud_tex, 0, 256 * 256 * 3, ctx->stream));
+  if (cfg->sky_res > 0) {
+    const size_t ns = (size_t)cfg->sky_res * cfg->sky_res;
+    CKC(cudaMalloc(&ctx->d_sky_scatter, ns * sizeof(float4)));
+    CKC(cudaMalloc(&ctx->d_sky_trans, ns * sizeof(float4)));
+    CKC(cudaMalloc(&ctx->d_trans_lut, 256 * 128 * 3 * sizeof(__half)));
+  }
+  {
+    std::vector<float> t(128 * 16);
+    default_materials(t.data());
+    CKC(cudaMemcpyAsync(ctx->d_mats, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+  }
+  // defaults: light ((1,1,1), 0.1, black) scene.py:127; identity-free camera must be set by the caller
+  const float dir[3] = {1, 1, 1}, rgb[3] = {0, 0, 0};
+  vrt_set_light(ctx, dir, 0.1f, rgb);
+#undef CKC
+  *out = ctx;
+  return VRT_OK;
+}
+
+int vrt_set_stream(vrt_ctx* ctx, void* s) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) {
+    cudaStreamDestroy(ctx->stream);
+    ctx->own_stream = false;
+  }
+  if (s) {
+    ctx->stream = (cudaStream_t)s;
+  } else {
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return VRT_OK;
+}
+
+int vrt_upload_voxels(vrt_ctx* ctx, const int8_t* material, const uint8_t* rgb) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(material && rgb, "vrt_upload_voxels: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  const size_t nvox = (size_t)ctx->cfg.grid_res * ctx->cfg.grid_res * ctx->cfg.grid_res;
+  CK(cudaMemcpyAsync(ctx->d_mat, material, nvox, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_rgb, rgb, nvox * 3, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->voxels_uploaded = true;
+  ctx->prepared = false;
+  return VRT_OK;
+}
+
+int vrt_set_camera(vrt_ctx* ctx, const float pos[3], const float view[16], const float proj[16]) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(pos && view && proj, "vrt_set_camera: null pointer");
+  double v[16], p[16], vi[16], pi[16];
+  for (int i = 0; i < 16; i++) v[i] = view[i], p[i] = proj[i];
+  REQUIRE(invert4(v, vi) && invert4(p, pi), "vrt_set_camera: singular matrix");
+  for (int i = 0; i < 16; i++) ctx->inv_view[i] = (float)vi[i], ctx->inv_proj[i] = (float)pi[i];
+  memcpy(ctx->cam_pos, pos, sizeof ctx->cam_pos);
+  ctx->camera_set = true;
+  return VRT_OK;
+}
+
+int vrt_set_light(vrt_ctx* ctx, const float direction[3], float cone_angle, const float rgb[3]) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(direction && rgb, "vrt_set_light: null pointer");
+  double x = direction[0], y = direction[1], z = direction[2];
+  double n = std::sqrt(x * x + y * y + z * z);
+  REQUIRE(n > 0.0, "vrt_set_light: zero direction");
+  ctx->light_dir[0] = (float)(x / n), ctx->light_dir[1] = (float)(y / n), ctx->light_dir[2] = (float)(z / n);
+  ctx->light_cos_max = (float)std::cos((double)cone_angle * 0.5);
+  memcpy(ctx->light_color, rgb, sizeof ctx->light_color);
+  ctx->sky_valid = false;  // the sky tables depend on the sun
+  return VRT_OK;
+}
+
+int vrt_set_floor(vrt_ctx* ctx, float height, const float rgb[3], int32_t material) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(rgb, "vrt_set_floor: null pointer");
+  ctx->floor_height = height;
+  memcpy(ctx->floor_color, rgb, sizeof ctx->floor_color);
+  ctx->floor_material = material;
+  return VRT_OK;
+}
+
+int vrt_set_background(vrt_ctx* ctx, const float rgb[3]) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(rgb, "vrt_set_background: null pointer");
+  memcpy(ctx->background, rgb, sizeof ctx->background);
+  return VRT_OK;
+}
+
+int vrt_set_sky(vrt_ctx* ctx, int32_t physical, int32_t clouds) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(!physical || ctx->cfg.sky_res > 0, "vrt_set_sky: context was created with sky_res = 0");
+  if ((clouds != 0) != (ctx->use_clouds != 0)) ctx->sky_valid = false;
+  ctx->use_sky = physical ? 1 : 0;
+  ctx->use_clouds = clouds ? 1 : 0;
+  return VRT_OK;
+}
+
+int vrt_set_materials(vrt_ctx* ctx, const float* t) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(t, "vrt_set_materials: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<float> rows(128 * 16, 0.0f);
+  for (int i = 0; i < 128; i++)
+    for (int j = 0; j < 14; j++) rows[i * 16 + j] = t[i * 14 + j];
+  CK(cudaMemcpyAsync(ctx->d_mats, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRT_OK;
+}
+
+int vrt_set_cloud_texture(vrt_ctx* ctx, const uint8_t* tex) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(tex, "vrt_set_cloud_texture: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_cloud_tex, tex, 256 * 256 * 3, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->cloud_tex_set = true;
+  ctx->sky_valid = false;
+  return VRT_OK;
+}
+
+int vrt_prepare(vrt_ctx* ctx) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  if (!ctx->voxels_uploaded) {
+    ctx->err = "vrt_prepare: vrt_upload_voxels has not been called";
+    return VRT_ERR_NOT_PREPARED;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(vrt_launch_build(ctx->d_mat, ctx->d_rgb, ctx->cfg.grid_res, ctx->d_bricks, ctx->d_color, ctx->d_upper, ctx->upper_off, ctx->n_lods,
+                      ctx->upper_words, ctx->stream));
+  if (ctx->use_sky && !ctx->sky_valid) {
+    SkyBuild B;
+    B.S = ctx->cfg.sky_res;
+    B.scatter = ctx->d_sky_scatter, B.trans = ctx->d_sky_trans, B.trans_lut = ctx->d_trans_lut;
+    B.cloud_tex = ctx->d_cloud_tex, B.cloud_ambient = ctx->d_cloud_ambient;
+    B.sun_dir = f3{ctx->light_dir[0], ctx->light_dir[1], ctx->light_dir[2]};
+    // sun_col = light_color * light_weight (pathtracer.py:320,326,329)
+    B.sun_col = f3{ctx->light_color[0] * 3.0f, ctx->light_color[1] * 3.0f, ctx->light_color[2] * 3.0f};
+    B.cosmax = ctx->light_cos_max;
+    B.use_clouds = ctx->use_clouds;
+    B.cloud_passes = ctx->cfg.cloud_passes > 0 ? ctx->cfg.cloud_passes : 1;
+    B.seed = ctx->cfg.seed;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(vrt_launch_sky_precompute(B, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->stats.sky_precompute_ms, ctx->ev0, ctx->ev1));
+    ctx->sky_valid = true;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->prepared = true;
+  return VRT_OK;
+}
+
+int vrt_get_sky_tables(vrt_ctx* ctx, float* scattering, float* transmittance) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(scattering && transmittance, "vrt_get_sky_tables: null pointer");
+  if (!ctx->sky_valid) {
+    ctx->err = "vrt_get_sky_tables: sky tables have not been computed";
+    return VRT_ERR_NOT_PREPARED;
+  }
+  CK(cudaSetDevice(ctx->device));
+  const size_t ns = (size_t)ctx->cfg.sky_res * ctx->cfg.sky_res;
+  std::vector<float4> tmp(ns);
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMemcpyAsync(tmp.data(), k == 0 ? ctx->d_sky_scatter : ctx->d_sky_trans, ns * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float* dst = k == 0 ? scattering : transmittance;
+    for (size_t i = 0; i < ns; i++) dst[3 * i] = tmp[i].x, dst[3 * i + 1] = tmp[i].y, dst[3 * i + 2] = tmp[i].z;
+  }
+  return VRT_OK;
+}
+
+int vrt_set_sky_tables(vrt_ctx* ctx, const float* scattering, const float* transmittance) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(scattering && transmittance, "vrt_set_sky_tables: null pointer");
+  REQUIRE(ctx->cfg.sky_res > 0, "vrt_set_sky_tables: context was created with sky_res = 0");
+  CK(cudaSetDevice(ctx->device));
+  const size_t ns = (size_t)ctx->cfg.sky_res * ctx->cfg.sky_res;
+  std::vector<float4> tmp(ns);
+  for (int k = 0; k < 2; k++) {
+    const float* src = k == 0 ? scattering : transmittance;
+    for (size_t i = 0; i < ns; i++) tmp[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.0f);
+    CK(cudaMemcpyAsync(k == 0 ? ctx->d_sky_scatter : ctx->d_sky_trans, tmp.data(), ns * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->sky_valid = true;
+  return VRT_OK;
+}
+
+int vrt_get_trans_lut(vrt_ctx* ctx, uint16_t* lut) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(lut, "vrt_get_trans_lut: null pointer");
+  if (!ctx->d_trans_lut || !ctx->sky_valid) {
+    ctx->err = "vrt_get_trans_lut: sky has not been computed";
+    return VRT_ERR_NOT_PREPARED;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(lut, ctx->d_trans_lut, 256 * 128 * 3 * sizeof(__half), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRT_OK;
+}
+
+static int check_ready(vrt_ctx* ctx, const char* who) {
+  if (!ctx->prepared || !ctx->camera_set) {
+    ctx->err = std::string(who) + ": call vrt_prepare and vrt_set_camera first";
+    return VRT_ERR_NOT_PREPARED;
+  }
+  if (ctx->use_sky && !ctx->sky_valid) {
+    ctx->err = std::string(who) + ": physical sky enabled but tables are stale; call vrt_prepare";
+    return VRT_ERR_NOT_PREPARED;
+  }
+  return VRT_OK;
+}
+
+int vrt_trace_primary(vrt_ctx* ctx, vrt_hit* out) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(out, "vrt_trace_primary: null pointer");
+  int rc = check_ready(ctx, "vrt_trace_primary");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t npx = (size_t)ctx->cfg.width * ctx->cfg.height;
+  if (!ctx->d_hits) CK(cudaMalloc(&ctx->d_hits, npx * sizeof(vrt_hit)));
+  Params P;
+  fill_params(ctx, P);
+  P.tile_rank = 0, P.tile_n = 1;
+  P.n_tiles = (ctx->cfg.width / 8) * (ctx->cfg.height / 4);
+  CK(vrt_launch_primary(P, ctx->d_hits, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->d_hits, npx * sizeof(vrt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRT_OK;
+}
+
+int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_t stride, int32_t stats) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(n_samples > 0 && stride > 0 && first_sample >= 0, "vrt_accumulate: bad sample range");
+  int rc = check_ready(ctx, "vrt_accumulate");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (n_samples > ctx->jitter_cap) {
+    if (ctx->d_jitter) cudaFree(ctx->d_jitter);
+    ctx->d_jitter = nullptr;
+    CK(cudaMalloc(&ctx->d_jitter, (size_t)n_samples * sizeof(float2)));
+    ctx->jitter_cap = n_samples;
+  }
+  // pathtracer.py:264-265: taa_jitter = (rand*2-1) * inv_image_res, one value per frame. Ours
+  // is a Halton(2,3) point per sample index so the pixel footprint is stratified.
+  std::vector<float2> jit((size_t)n_samples);
+  for (int k = 0; k < n_samples; k++) {
+    uint32_t s = (uint32_t)(first_sample + k * stride);
+    if (ctx->cfg.jitter_mode == 1)
+      jit[k] = make_float2((float)((halton(s + 1, 2) * 2.0 - 1.0) / (double)ctx->cfg.width),
+                           (float)((halton(s + 1, 3) * 2.0 - 1.0) / (double)ctx->cfg.height));
+    else
+      jit[k] = make_float2(0.0f, 0.0f);
+  }
+  CK(cudaMemcpyAsync(ctx->d_jitter, jit.data(), jit.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
+  if (stats) CK(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  Params P;
+  fill_params(ctx, P);
+  P.first_sample = first_sample, P.n_samples = n_samples, P.stride = stride;
+  P.stats = stats ? ctx->d_stats : nullptr;
+  if (P.n_tiles <= 0) return VRT_OK;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(vrt_launch_path(P, stats != 0, ctx->sm_count, ctx->stream, nullptr));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->stats.kernel_launches = 1;
+  // the jitter vector is read by the async copy above: wait before it goes out of scope
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->stats.last_render_ms, ctx->ev0, ctx->ev1));
+  if (stats) {
+    unsigned long long h[8];
+    CK(cudaMemcpyAsync(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.paths = h[0], ctx->stats.rays = h[1], ctx->stats.steps = h[2], ctx->stats.queries = h[3], ctx->stats.hits = h[4];
+    ctx->stats.sky_escapes = h[5], ctx->stats.nee_visible = h[6], ctx->stats.vertices = h[7];
+  }
+  return VRT_OK;
+}
+
+int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(n >= 1 && rank >= 0 && rank < n, "vrt_set_tile_shard: need 0 <= rank < n");
+  ctx->tile_rank = rank, ctx->tile_n = n;
+  return VRT_OK;
+}
+
+int vrt_reset(vrt_ctx* ctx) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemsetAsync(ctx->d_accum, 0, (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4), ctx->stream));
+  return VRT_OK;
+}
+
+int vrt_accum_device_ptr(vrt_ctx* ctx, void** ptr, uint64_t* bytes) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(ptr, "vrt_accum_device_ptr: null pointer");
+  *ptr = ctx->d_accum;
+  if (bytes) *bytes = (uint64_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4);
+  return VRT_OK;
+}
+
+static int resolve(vrt_ctx* ctx, bool ldr, float* host) {
+  CK(cudaSetDevice(ctx->device));
+  const int W = ctx->cfg.width, H = ctx->cfg.height;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(vrt_launch_resolve(ctx->d_accum, ldr ? nullptr : ctx->d_out, ldr ? ctx->d_out : nullptr, W, H, ctx->cfg.exposure, ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (host) CK(cudaMemcpyAsync(host, ctx->d_out, (size_t)W * H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->stats.last_resolve_ms, ctx->ev0, ctx->ev1));
+  return VRT_OK;
+}
+
+int vrt_fetch_hdr(vrt_ctx* ctx, float* rgba) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(rgba, "vrt_fetch_hdr: null pointer");
+  return resolve(ctx, false, rgba);
+}
+int vrt_fetch_ldr(vrt_ctx* ctx, float* rgba) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(rgba, "vrt_fetch_ldr: null pointer");
+  return resolve(ctx, true, rgba);
+}
+int vrt_resolve_ldr_device(vrt_ctx* ctx, void** ptr) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(ptr, "vrt_resolve_ldr_device: null pointer");
+  int rc = resolve(ctx, true, nullptr);
+  *ptr = ctx->d_out;
+  return rc;
+}
+
+int vrt_get_stats(vrt_ctx* ctx, vrt_stats* out) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(out, "vrt_get_stats: null pointer");
+  *out = ctx->stats;
+  return VRT_OK;
+}
+
+int vrt_synchronize(vrt_ctx* ctx) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// Internal launcher interface between the translation units of libvoxelrt.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/voxelrt.h"
+#include "vrt_common.cuh"
+
+// vrt_render.cu
+cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st);
+cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out);
+cudaError_t vrt_launch_resolve(const float4* accum, float4* hdr, float4* ldr, int W, int H, float exposure, cudaStream_t st);
+
+// vrt_build.cu — voxel arrays ([x][y][z], z fastest) -> bricks, colour SoA, upper pyramid
+cudaError_t vrt_launch_build(const int8_t* d_mat, const uint8_t* d_rgb, int R, unsigned long long* bricks, uint32_t* color,
+                             uint32_t* upper, const uint32_t* upper_off_host, int n_lods, int upper_words, cudaStream_t st);
+
+// vrt_sky_precompute.cu
+struct SkyBuild {
+  int S;
+  float4* scatter;  // [S][S]
+  float4* trans;
+  __half* trans_lut;          // [256][128][3]
+  const uint8_t* cloud_tex;   // [256][256][3]
+  float* cloud_ambient;       // 3 floats (device)
+  f3 sun_dir, sun_col;
+  float cosmax;
+  int use_clouds;
+  int cloud_passes;
+  uint32_t seed;
+};
+cudaError_t vrt_launch_sky_precompute(const SkyBuild& B, cudaStream_t st);

@@ -1,0 +1,376 @@
+// Render kernels of libvoxelrt (sm_100a):
+//   k_primary  primary-hit dump: next_hit for the camera ray + sun shadow ray on the cone axis
+//              (renderer/pathtracer.py:218-244, :435-450)
+//   k_path     fused bounce / shade / NEE path kernel: persistent warps, per-lane path
+//              regeneration from a warp-local tile queue, segment and shadow rays of different
+//              lanes traced by one shared traversal loop (renderer/pathtracer.py:355-632,
+//              non-ReSTIR estimator, static camera; accumulation :1185-1303 reduced to a sum)
+//   k_resolve  mean + vignette + exposure + Uchimura + gamma (renderer/pathtracer.py:634-662,
+//              renderer/math_utils.py:160-186), float4 in / float4 out
+#include "vrt_bsdf.cuh"
+#include "vrt_internal.h"
+#include "vrt_sky.cuh"
+#include "vrt_trace.cuh"
+
+#define RADIANCE_CLAMP 300.0f  // pathtracer.py:20
+HD f3 firefly_filter(f3 v) { return clamp3(v, 0.0f, RADIANCE_CLAMP); }
+HD float power_heuristic(float a, float b) {  // pathtracer.py:349-353
+  float a_sqr = a * a;
+  return a_sqr / fmaxf(a_sqr + b * b, 1e-4f);
+}
+HD uint32_t encode_material(int mat_id, f3 albedo) {  // math_utils.py:231-236
+  return (uint32_t)mat_id | ((uint32_t)(albedo.x * 255.0f) << 8) | ((uint32_t)(albedo.y * 255.0f) << 16) |
+         ((uint32_t)(albedo.z * 255.0f) << 24);
+}
+HD bool bad3(f3 c) { return isbad(c.x) || isbad(c.y) || isbad(c.z) || c.x < 0.0f || c.y < 0.0f || c.z < 0.0f; }
+
+#define SMEM_MAT_WORDS 2048  // 128 materials x 16 floats
+
+// Stage the material table and (when it fits) the upper occupancy pyramid in shared memory.
+HD const uint32_t* stage_shared(const Params& P, uint32_t* smem, int upper_in_smem) {
+  float4* s_mats = reinterpret_cast<float4*>(smem);
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_mats[i] = P.mats[i];
+  const uint32_t* upper = P.upper;
+  if (upper_in_smem) {
+    uint32_t* s_upper = smem + SMEM_MAT_WORDS;
+    for (int i = threadIdx.x; i < P.upper_words; i += blockDim.x) s_upper[i] = P.upper[i];
+    upper = s_upper;
+  }
+  __syncthreads();
+  return upper;
+}
+
+// ------------------------------------------------------------------------------- k_primary
+__global__ void __launch_bounds__(128) k_primary(const __grid_constant__ Params P, vrt_hit* __restrict__ out, int upper_in_smem) {
+  extern __shared__ uint32_t smem[];
+  const uint32_t* upper = stage_shared(P, smem, upper_in_smem);
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P.n_tiles) return;
+  const int tile = P.tile_rank + P.tile_n * warp;
+  const int u = (tile % P.tiles_x) * 8 + (lane & 7), v = (tile / P.tiles_x) * 4 + (lane >> 3);
+  f3 d = get_cast_dir(P, (float)u, (float)v, 0.0f, 0.0f);
+  Hit h = next_hit<false>(P, upper, P.cam_pos, d, false, nullptr, nullptr);
+  uint32_t shadow = 3u;
+  const int kind = h.closest < VRT_INF ? h.kind : 0;
+  if (!h.hit_light && h.closest < VRT_INF) {
+    f3 n{h.nx, h.ny, h.nz};
+    f3 pos{xadd(xadd(P.cam_pos.x, xmul(h.closest, d.x)), xmul(n.x, VRT_EPS)), xadd(xadd(P.cam_pos.y, xmul(h.closest, d.y)), xmul(n.y, VRT_EPS)),
+           xadd(xadd(P.cam_pos.z, xmul(h.closest, d.z)), xmul(n.z, VRT_EPS))};
+    float ndl = xdot(P.light_dir, n);
+    if (ndl > 0.0f) {
+      Hit sh = next_hit<false>(P, upper, pos, P.light_dir, true, nullptr, nullptr);
+      shadow = sh.closest >= VRT_INF ? 0u : 1u;
+    } else {
+      shadow = 2u;
+    }
+  }
+  vrt_hit o;
+  o.t = h.closest;
+  o.cell[0] = kind == 2 ? h.cx : -1, o.cell[1] = kind == 2 ? h.cy : -1, o.cell[2] = kind == 2 ? h.cz : -1;
+  o.normal[0] = h.nx, o.normal[1] = h.ny, o.normal[2] = h.nz;
+  o.flags = (uint32_t)kind | (shadow << 8) | (((uint32_t)h.mat_id & 255u) << 16) | ((uint32_t)(h.hit_light ? 1 : 0) << 24);
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)v * P.W + u);
+  const float4* src = reinterpret_cast<const float4*>(&o);
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+
+// ---------------------------------------------------------------------------------- k_path
+enum { ST_SEGMENT = 0, ST_SHADOW = 1 };
+enum { PIX_IDLE = -1, PIX_DONE = -2 };
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, int upper_in_smem) {
+  extern __shared__ uint32_t smem[];
+  const uint32_t* upper = stage_shared(P, smem, upper_in_smem);
+  const float4* s_mats = reinterpret_cast<const float4*>(smem);
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // per-launch constants
+  f3 sun_bx, sun_by;
+  make_orthonormal_basis(P.light_dir, sun_bx, sun_by);
+  const float light_pdf_axis = cone_sample_pdf(P.light_cos_max, 1.0f);
+  const f3 sun_rad = P.light_weight * P.light_color;
+  const float sky_fres = 1.0f / (float)P.sky_res;
+
+  // warp-local work queue: one tile (32 pixels) per global atomic
+  int chunk_base = 0, chunk_rem = 0;
+
+  // lane state
+  int pix = PIX_IDLE;
+  int s_i = 0, depth = 0, state = ST_SEGMENT, f_lobe = 0;
+  bool sky_ray = false;
+  uint32_t key = 0, pm_info = 0;
+  f3 pos = mk3(0.0f), d = mk3(0.0f), thr = mk3(1.0f), contrib = mk3(0.0f), acc = mk3(0.0f);
+  f3 fnee_d = mk3(0.0f), fnee_s = mk3(0.0f);
+  float f_invpdf = 1.0f;
+  // surface stash while the shadow ray is in flight
+  f3 s_n = mk3(0.0f), s_alb = mk3(0.0f), s_view = mk3(0.0f);
+  int s_mat = 0;
+  TraceCounters tc{0, 0, 0};
+  uint32_t c_hits = 0, c_escapes = 0, c_nee = 0, c_vertices = 0, c_paths = 0;
+
+  auto start_path = [&]() {
+    const int tile = P.tile_rank + P.tile_n * (pix >> 5);
+    const int u = (tile % P.tiles_x) * 8 + (pix & 7), v = (tile / P.tiles_x) * 4 + ((pix >> 3) & 3);
+    const uint32_t sample = (uint32_t)(P.first_sample + s_i * P.stride);
+    key = path_key((uint32_t)(v * P.W + u), sample, P.seed);
+    const float2 j = P.jitter[s_i];
+    d = get_cast_dir(P, (float)u, (float)v, j.x, j.y);
+    pos = P.cam_pos;
+    thr = mk3(1.0f), contrib = mk3(0.0f), fnee_d = mk3(0.0f), fnee_s = mk3(0.0f);
+    f_invpdf = 1.0f, f_lobe = 0, pm_info = 0, sky_ray = false, depth = 0, state = ST_SEGMENT;
+    if (STATS) c_paths++;
+  };
+  // pathtracer.py:609-619 + NaN scrub :1068-1075, then either the next sample of this pixel or
+  // the single read-modify-write of the accumulation texel.
+  auto finish_path = [&]() {
+    f3 emission = mk3(0.0f);
+    if ((pm_info & 255u) == 2u)
+      emission = f3{(float)((pm_info >> 8) & 255u) / 255.0f, (float)((pm_info >> 16) & 255u) / 255.0f, (float)((pm_info >> 24) & 255u) / 255.0f};
+    f3 diffuse = fnee_d, specular = fnee_s;
+    if (f_lobe == LOBE_DIFFUSE) diffuse += contrib * f_invpdf + emission;
+    if (f_lobe == LOBE_SPEC_REFL) specular += contrib * f_invpdf;
+    if (bad3(diffuse)) diffuse = mk3(0.0f);
+    if (bad3(specular)) specular = mk3(0.0f);
+    acc += diffuse + specular;
+    s_i++;
+    if (s_i < P.n_samples) {
+      start_path();
+    } else {
+      const int tile = P.tile_rank + P.tile_n * (pix >> 5);
+      const int u = (tile % P.tiles_x) * 8 + (pix & 7), v = (tile / P.tiles_x) * 4 + ((pix >> 3) & 3);
+      float4* dst = P.accum + (size_t)v * P.W + u;
+      float4 a = *dst;
+      a.x += acc.x, a.y += acc.y, a.z += acc.z, a.w += (float)P.n_samples;
+      *dst = a;
+      pix = PIX_IDLE;
+    }
+  };
+
+  for (;;) {
+    // ---- (1) refill idle lanes from the warp's tile queue
+    for (;;) {
+      const unsigned need = __ballot_sync(FULL, pix == PIX_IDLE);
+      if (need == 0u) break;
+      if (chunk_rem == 0) {
+        unsigned c = 0;
+        if (lane == 0) c = atomicAdd(P.work_counter, 1u);
+        c = __shfl_sync(FULL, c, 0);
+        if (c >= (unsigned)P.n_tiles) {
+          if (pix == PIX_IDLE) pix = PIX_DONE;
+          break;
+        }
+        chunk_base = (int)c * 32;
+        chunk_rem = 32;
+      }
+      const int rank = __popc(need & lt_mask);
+      if (pix == PIX_IDLE && rank < chunk_rem) {
+        pix = chunk_base + (32 - chunk_rem) + rank;
+        s_i = 0;
+        acc = mk3(0.0f);
+        start_path();
+      }
+      chunk_rem -= min(__popc(need), chunk_rem);
+    }
+    if (__all_sync(FULL, pix == PIX_DONE)) break;
+    const bool active = pix >= 0;
+
+    // ---- (2) trace the lane's current ray (path segment or sun shadow ray)
+    Hit h;
+    h.closest = VRT_INF, h.hit_light = 0, h.mat_id = 0, h.kind = 0, h.nx = h.ny = h.nz = 0.0f, h.albedo = mk3(1.0f);
+    if (active) h = next_hit<STATS>(P, upper, pos, d, state == ST_SHADOW, &tc, &c_hits);
+
+    // ---- (3) classify
+    bool do_shade = false;
+    float visible = 0.0f;
+    f3 light_dir = d;
+    if (active) {
+      if (state == ST_SEGMENT) {
+        const uint32_t base = 8u * (uint32_t)depth;
+        if (h.closest == VRT_INF) {
+          // escaped: background or sky tables + sun disk (pathtracer.py:499-511)
+          const float hit_sun = dot(P.light_dir, d) >= P.light_cos_max ? 1.0f : 0.0f;
+          f3 sky_scattering = P.background, sky_T = mk3(1.0f);
+          if (P.use_sky) {
+            f3 dj = normalize(d + f3{rnd(key, base + 5), rnd(key, base + 6), rnd(key, base + 7)} * 0.0015f);
+            SkyTap t = sky_tap(P.sky_res, project_sky(dj, sky_fres));
+            sky_scattering = sky_fetch(P.sky_scatter, t);
+            sky_T = sky_fetch(P.sky_trans, t);
+            if (STATS) c_escapes++;
+          }
+          f3 sky_emission = firefly_filter(sky_scattering + sky_T * sun_rad * hit_sun);
+          contrib += thr * sky_emission;
+          if (depth == 0) sky_ray = true;
+          finish_path();
+        } else if (h.hit_light) {
+          // emissive voxel / floor terminates the path (pathtracer.py:519-525)
+          if (depth > 0) contrib += thr * h.albedo;
+          if (depth == 0) pm_info = encode_material(h.mat_id, h.albedo);
+          finish_path();
+        } else {
+          if (STATS) c_vertices++;
+          s_n = f3{h.nx, h.ny, h.nz};
+          s_alb = h.albedo;
+          s_mat = h.mat_id;
+          s_view = -d;
+          pos = (pos + h.closest * d) + s_n * VRT_EPS;
+          light_dir = sample_cone_oriented(P.light_cos_max, P.light_dir, sun_bx, sun_by, rnd(key, base + 0), rnd(key, base + 1));
+          if (dot(light_dir, s_n) > 0.0f) {
+            d = light_dir;
+            state = ST_SHADOW;
+          } else {
+            do_shade = true;
+          }
+        }
+      } else {
+        visible = h.closest >= VRT_INF ? 1.0f : 0.0f;
+        state = ST_SEGMENT;
+        do_shade = true;
+      }
+    }
+
+    // ---- (4) shade: NEE contribution (if the sun is visible) + BSDF sample
+    if (do_shade) {
+      const uint32_t base = 8u * (uint32_t)depth;
+      Mat m = load_mat(s_mats, s_mat);
+      m.base_col = s_alb;
+      const MatK k = mat_constants(m);
+      f3 tang, bitang;
+      make_orthonormal_basis(s_n, tang, bitang);
+      if (visible != 0.0f) {
+        f3 bd, bs;
+        float lpdf;
+        eval_and_pdf(m, k, s_view, s_n, light_dir, tang, bitang, bd, bs, lpdf);
+        const float mis = power_heuristic(light_pdf_axis, lpdf);
+        f3 sky_T = mk3(1.0f);
+        if (P.use_sky) {
+          SkyTap t = sky_tap(P.sky_res, project_sky(light_dir, sky_fres));
+          sky_T = sky_fetch(P.sky_trans, t);
+          if (STATS) c_nee++;
+        }
+        const float ndl = dot(light_dir, s_n);
+        const f3 lr = sky_T * sun_rad * ndl;
+        if (depth == 0) {
+          // primary vertex: unweighted at accumulation time, MIS weight applied once at the end
+          // (pathtracer.py:470-472, :561-568); thr == 1 here.
+          fnee_d = firefly_filter(thr * (bd * lr)) * mis;
+          fnee_s = firefly_filter(thr * (bs * lr)) * mis;
+        } else {
+          contrib += firefly_filter(thr * ((mis * (bd + bs)) * lr));
+        }
+      }
+      f3 brdf;
+      float pdf;
+      int lobe;
+      const f3 nd = sample_disney(m, k, s_view, s_n, tang, bitang, rnd(key, base + 2), rnd(key, base + 3), rnd(key, base + 4), brdf, pdf, lobe);
+      f3 bounce_weight = brdf * saturate(dot(nd, s_n));
+      if (depth == 0) {
+        f_invpdf = 1.0f / pdf;
+        f_lobe = lobe;
+      } else {
+        bounce_weight = bounce_weight / pdf;
+        const float bsdf_sample_light_pdf = cone_sample_pdf(P.light_cos_max, dot(P.light_dir, nd));
+        bounce_weight *= power_heuristic(pdf, visible * bsdf_sample_light_pdf);
+      }
+      thr *= bounce_weight;
+      d = nd;
+      depth++;
+      // The reference keeps tracing zero-throughput paths; they add exact zeros, so stop here.
+      const bool dead = thr.x == 0.0f && thr.y == 0.0f && thr.z == 0.0f;
+      if (depth >= P.max_depth || dead) finish_path();
+    }
+  }
+
+  if (STATS) {
+    unsigned long long vals[8] = {c_paths, tc.rays, tc.steps, tc.queries, c_hits, c_escapes, c_nee, c_vertices};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      unsigned long long x = vals[i];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+      if (lane == 0 && x) atomicAdd(P.stats + i, x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- k_resolve
+HD float uchimura1(float x) {  // math_utils.py:160-186
+  const float Pm = 1.0f, a = 1.0f, m = 0.22f, l = 0.4f, c = 1.33f, b = 0.0f;
+  const float l0 = ((Pm - m) * l) / a;
+  const float S0 = m + l0;
+  const float S1 = m + a * l0;
+  const float C2 = (a * Pm) / (Pm - S1);
+  const float CP = -C2 / Pm;
+  float t = clampf(x / m, 0.0f, 1.0f);
+  float w0 = 1.0f - t * t * (3.0f - 2.0f * t);
+  float w2 = x < m + l0 ? 0.0f : 1.0f;
+  float w1 = 1.0f - w0 - w2;
+  float T = m * powf(x / m, c) + b;
+  float S = Pm - (Pm - S1) * expf(CP * (x - S0));
+  float L = m + a * (x - m);
+  return T * w0 + L * w1 + S * w2;
+}
+
+__global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accum, float4* __restrict__ hdr, float4* __restrict__ ldr, int W,
+                                                 int H, float exposure) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= W * H) return;
+  const int i = idx % W, j = idx / W;
+  float4 a = accum[idx];
+  const float inv = a.w > 0.0f ? 1.0f / a.w : 0.0f;
+  f3 c{a.x * inv, a.y * inv, a.z * inv};
+  if (hdr) hdr[idx] = make_float4(c.x, c.y, c.z, a.w);
+  if (ldr) {
+    float ux = (float)i / (float)W - 0.5f, uy = (float)j / (float)H - 0.5f;
+    float darken = 1.0f - 0.9f * fmaxf(sqrtf(ux * ux + uy * uy), 0.0f);
+    float s = darken * exposure;
+    ldr[idx] = make_float4(saturate(powf(uchimura1(c.x * s), 1.0f / 2.2f)), saturate(powf(uchimura1(c.y * s), 1.0f / 2.2f)),
+                           saturate(powf(uchimura1(c.z * s), 1.0f / 2.2f)), 1.0f);
+  }
+}
+
+// -------------------------------------------------------------------------------- launchers
+static size_t smem_bytes(const Params& P, int* upper_in_smem) {
+  size_t need = (size_t)SMEM_MAT_WORDS * 4 + (size_t)P.upper_words * 4;
+  *upper_in_smem = need <= 48 * 1024 ? 1 : 0;
+  return *upper_in_smem ? need : (size_t)SMEM_MAT_WORDS * 4;
+}
+
+cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st) {
+  int uis;
+  size_t sm = smem_bytes(P, &uis);
+  int warps = P.n_tiles;
+  int blocks = (warps * 32 + 127) / 128;
+  k_primary<<<blocks, 128, sm, st>>>(P, out, uis);
+  return cudaGetLastError();
+}
+
+cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out) {
+  int uis;
+  size_t sm = smem_bytes(P, &uis);
+  int per_sm = 0;
+  cudaError_t e;
+  if (stats)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<true>, 128, sm);
+  else
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<false>, 128, sm);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  int blocks = sm_count * per_sm;  // persistent: one wave, a multiple of the SM count
+  int max_useful = (P.n_tiles + 3) / 4;
+  if (blocks > max_useful) blocks = max_useful > 0 ? max_useful : 1;
+  if (blocks_out) *blocks_out = blocks;
+  if (stats)
+    k_path<true><<<blocks, 128, sm, st>>>(P, uis);
+  else
+    k_path<false><<<blocks, 128, sm, st>>>(P, uis);
+  return cudaGetLastError();
+}
+
+cudaError_t vrt_launch_resolve(const float4* accum, float4* hdr, float4* ldr, int W, int H, float exposure, cudaStream_t st) {
+  int n = W * H;
+  k_resolve<<<(n + 255) / 256, 256, 0, st>>>(accum, hdr, ldr, W, H, exposure);
+  return cudaGetLastError();
+}

@@ -1,0 +1,271 @@
+// Hierarchical 3-D DDA over 4^3 occupancy bricks + an upper bit pyramid.
+//
+// Replaces renderer/raytracer.py:17-155 (linearize_index / query_occupancy / raytrace),
+// renderer/math_utils.py:103-123 (ray_aabb_intersection), renderer/voxel_world.py:27-56
+// (voxel_surface_color) and renderer/pathtracer.py:152-244 (floor plane, next_hit).
+//
+// Layout (ours, not the reference's): LOD 0, 1 and 2 of a 4x4x4 block live in ONE 64-bit brick
+// word (bit = (z&3)*16 + (y&3)*4 + (x&3)); LOD1 is a 2^3 sub-mask test, LOD2 is word != 0, so a
+// single 8-byte load answers up to three of the reference's occupancy queries and the last word
+// is kept in a register while the ray stays inside the brick. LOD >= 3 are plain bit arrays
+// (<= 37 KB at 512^3) that the render kernels stage in shared memory.
+//
+// The stepping sequence (descend while occupied, step to the exit face of the empty LOD-l cell,
+// ascend one LOD) and every float op are the reference's, with no FMA contraction, so hits are
+// bit-identical to the CPU oracle.
+#pragma once
+#include "vrt_common.cuh"
+
+struct RayHit {
+  float t;  // voxel units, +inf on miss
+  int cx, cy, cz;
+  float nx, ny, nz;
+  int iters;
+};
+
+struct TraceCounters {
+  uint32_t rays, steps, queries;
+};
+
+HD bool upper_bit(const Params& P, const uint32_t* __restrict__ upper, int x, int y, int z, int lod) {
+  int r = P.R >> lod;
+  uint32_t idx = (uint32_t)((z * r + y) * r + x);
+  return (upper[P.upper_off[lod - 3] + (idx >> 5)] >> (idx & 31)) & 1u;
+}
+
+template <bool STATS>
+HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3 d, TraceCounters* tc) {
+  RayHit h;
+  h.t = VRT_INF;
+  h.cx = h.cy = h.cz = -1;
+  h.nx = h.ny = h.nz = 0.0f;
+  h.iters = 0;
+  const float Rf = (float)P.R;
+  if (STATS) tc->rays++;
+
+  // ray_aabb_intersection against [0,R]^3 (axes with d == 0 are skipped, as in the reference)
+  float near_int = -VRT_INF, far_int = VRT_INF;
+  {
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (dd[i] != 0.0f) {
+        float i1 = xdiv(xsub(0.0f, oo[i]), dd[i]);
+        float i2 = xdiv(xsub(Rf, oo[i]), dd[i]);
+        far_int = fminf(fmaxf(i1, i2), far_int);
+        near_int = fmaxf(fminf(i1, i2), near_int);
+      }
+    }
+  }
+  if (!(near_int <= far_int && VRT_EPS < far_int && near_int < VRT_INF)) {
+    return h;
+  }
+
+  float hit_distance = fmaxf(near_int, VRT_EPS);
+  const float t0 = xadd(hit_distance, VRT_EPS);
+  const float ipx = xadd(o.x, xmul(d.x, t0)), ipy = xadd(o.y, xmul(d.y, t0)), ipz = xadd(o.z, xmul(d.z, t0));
+  int px = (int)clampf(floorf(ipx), 0.0f, Rf - 1.0f);
+  int py = (int)clampf(floorf(ipy), 0.0f, Rf - 1.0f);
+  int pz = (int)clampf(floorf(ipz), 0.0f, Rf - 1.0f);
+  const float ivx = xdiv(1.0f, fabsf(d.x)), ivy = xdiv(1.0f, fabsf(d.y)), ivz = xdiv(1.0f, fabsf(d.z));
+  const float sgx = signf(d.x), sgy = signf(d.y), sgz = signf(d.z);
+  int lod = 0;
+  const float far = xsub(fminf(VRT_INF, far_int), VRT_EPS);
+  {
+    float ax = fabsf(xsub(ipx, xmul(Rf, 0.5f))), ay = fabsf(xsub(ipy, xmul(Rf, 0.5f))), az = fabsf(xsub(ipz, xmul(Rf, 0.5f)));
+    float m = fmaxf(fmaxf(ax, ay), az);
+    h.nx = (m == ax) ? 1.0f : 0.0f;
+    h.ny = (m == ay) ? 1.0f : 0.0f;
+    h.nz = (m == az) ? 1.0f : 0.0f;
+  }
+  const int top_lod = P.n_lods - 1;
+  int last_b = -1;
+  unsigned long long w = 0ull;
+  int iters = 0;
+  bool found = false;
+  while (iters < 512) {
+    if (hit_distance > far) {
+      hit_distance = VRT_INF;
+      break;
+    }
+    if ((unsigned)px >= (unsigned)P.R || (unsigned)py >= (unsigned)P.R || (unsigned)pz >= (unsigned)P.R) {
+      hit_distance = VRT_INF;  // stepped outside the grid: miss (pinned)
+      break;
+    }
+    // --- descend while occupied (raytracer.py:110-118)
+    bool occ = true;
+    while (lod >= 3) {
+      occ = upper_bit(P, upper, px >> lod, py >> lod, pz >> lod, lod);
+      if (STATS) tc->queries++;
+      if (!occ) break;
+      lod--;
+    }
+    if (occ) {
+      int b = ((pz >> 2) * P.brick_res + (py >> 2)) * P.brick_res + (px >> 2);
+      if (b != last_b) {
+        w = __ldg(P.bricks + b);
+        last_b = b;
+      }
+      if (lod == 2) {
+        if (STATS) tc->queries++;
+        if (w == 0ull)
+          occ = false;
+        else
+          lod = 1;
+      }
+      if (occ && lod == 1) {
+        if (STATS) tc->queries++;
+        int sh = ((px >> 1) & 1) * 2 + ((py >> 1) & 1) * 8 + ((pz >> 1) & 1) * 32;
+        if ((w & (0x0000000000330033ull << sh)) == 0ull)
+          occ = false;
+        else
+          lod = 0;
+      }
+      if (occ && lod == 0) {
+        if (STATS) tc->queries++;
+        occ = (w >> ((pz & 3) * 16 + (py & 3) * 4 + (px & 3))) & 1ull;
+      }
+    }
+    if (occ) {
+      found = true;
+      break;
+    }
+    // --- step to the exit face of the empty LOD-`lod` cell (raytracer.py:124-147)
+    const float cell_size = (float)(1 << lod);
+    const int cxi = px >> lod, cyi = py >> lod, czi = pz >> lod;
+    const float bx = xmul((float)cxi, cell_size), by = xmul((float)cyi, cell_size), bz = xmul((float)czi, cell_size);
+    const float fx = xsub(xadd(o.x, xmul(d.x, hit_distance)), bx);
+    const float fy = xsub(xadd(o.y, xmul(d.y, hit_distance)), by);
+    const float fz = xsub(xadd(o.z, xmul(d.z, hit_distance)), bz);
+    float tx = xmul(d.x > 0.0f ? xsub(cell_size, fx) : fx, ivx);
+    float ty = xmul(d.y > 0.0f ? xsub(cell_size, fy) : fy, ivy);
+    float tz = xmul(d.z > 0.0f ? xsub(cell_size, fz) : fz, ivz);
+    if (d.x == 0.0f) tx = VRT_INF;  // pinned, SURVEY A4
+    if (d.y == 0.0f) ty = VRT_INF;
+    if (d.z == 0.0f) tz = VRT_INF;
+    const float min_t = fminf(fminf(tx, ty), tz);
+    const float ex = clampf(floorf(xadd(fx, xmul(min_t, d.x))), 0.0f, cell_size - 1.0f);
+    const float ey = clampf(floorf(xadd(fy, xmul(min_t, d.y))), 0.0f, cell_size - 1.0f);
+    const float ez = clampf(floorf(xadd(fz, xmul(min_t, d.z))), 0.0f, cell_size - 1.0f);
+    hit_distance = xadd(hit_distance, min_t);
+    h.nx = (tx == min_t ? 1.0f : 0.0f) * sgx;
+    h.ny = (ty == min_t ? 1.0f : 0.0f) * sgy;
+    h.nz = (tz == min_t ? 1.0f : 0.0f) * sgz;
+    px = (int)(bx + ex + h.nx);
+    py = (int)(by + ey + h.ny);
+    pz = (int)(bz + ez + h.nz);
+    lod = min(top_lod, lod + 1);
+    iters++;
+    if (STATS) tc->steps++;
+  }
+  (void)found;
+  h.t = hit_distance;
+  h.cx = px, h.cy = py, h.cz = pz;
+  h.iters = iters;
+  // flip the normal against the ray (raytracer.py:152-153)
+  if (xadd(xadd(xmul(d.x, h.nx), xmul(d.y, h.ny)), xmul(d.z, h.nz)) > 0.0f) {
+    h.nx = -h.nx, h.ny = -h.ny, h.nz = -h.nz;
+  }
+  return h;
+}
+
+// Result of next_hit. Surface attributes are only filled for non-shadow rays.
+struct Hit {
+  float closest;  // world units, +inf on miss
+  float nx, ny, nz;
+  f3 albedo;
+  int mat_id;
+  int hit_light;
+  int kind;  // 0 miss, 1 floor, 2 voxel
+  int cx, cy, cz;
+};
+
+// pathtracer.py:218-244: floor plane first (:173-190), then the voxel grid (:192-216).
+// `shadow` is a run-time flag so that segment rays and shadow rays of different lanes share one
+// instance of the traversal loop (the path kernel traces both kinds in the same iteration).
+template <bool STATS>
+HD Hit next_hit(const Params& P, const uint32_t* __restrict__ upper, f3 pos, f3 d, const bool SHADOW, TraceCounters* tc,
+                uint32_t* n_hits) {
+  Hit h;
+  h.closest = VRT_INF;
+  h.nx = h.ny = h.nz = 0.0f;
+  h.albedo = mk3(1.0f);
+  h.mat_id = 0;
+  h.hit_light = 0;
+  h.kind = 0;
+  h.cx = h.cy = h.cz = -1;
+  // floor: dist = (h - p.y)/d.y ; accept if eps < dist and |(x-y, 0, z-y)| < 10   
+  {
+    float dist = xdiv(xsub(P.floor_height, pos.y), d.y);
+    if (dist > VRT_EPS && dist < h.closest) {
+      float hx = xadd(pos.x, xmul(d.x, dist)), hy = xadd(pos.y, xmul(d.y, dist)), hz = xadd(pos.z, xmul(d.z, dist));
+      float dn = xadd(xadd(xmul(hx, 0.0f), xmul(hy, 1.0f)), xmul(hz, 0.0f));
+      float ax = xsub(hx, dn), ay = xsub(hy, dn), az = xsub(hz, dn);
+      float len = xsqrt(xadd(xadd(xmul(ax, ax), xmul(ay, ay)), xmul(az, az)));
+      if (len < 10.0f) {
+        h.closest = dist;
+        h.nx = 0.0f, h.ny = 1.0f, h.nz = 0.0f;
+        if (xadd(xadd(xmul(0.0f, d.x), xmul(1.0f, d.y)), xmul(0.0f, d.z)) > 0.0f) h.ny = -1.0f;
+        if (!SHADOW) {
+          h.albedo = P.floor_color;
+          h.hit_light = P.floor_material == 2;
+          h.mat_id = P.floor_material;
+        }
+        h.kind = 1;
+      }
+    }
+  }
+  // world -> voxel space: inv_size * p - offset, offset = -R/2  (pathtracer.py:165-167)
+  f3 eye{xsub(xmul(P.voxel_inv_size, pos.x), -P.grid_half), xsub(xmul(P.voxel_inv_size, pos.y), -P.grid_half),
+         xsub(xmul(P.voxel_inv_size, pos.z), -P.grid_half)};
+  RayHit r = raytrace<STATS>(P, upper, eye, d, tc);
+  float tw = xmul(r.t, P.voxel_size);
+  if (tw < h.closest) {
+    h.closest = tw;
+    h.kind = 2;
+    h.cx = r.cx, h.cy = r.cy, h.cz = r.cz;
+    if (!SHADOW) {
+      // voxel_world.py:34-56
+      float uvx = clampf(xsub(xadd(eye.x, xmul(r.t, d.x)), (float)r.cx), 0.0f, 1.0f);
+      float uvy = clampf(xsub(xadd(eye.y, xmul(r.t, d.y)), (float)r.cy), 0.0f, 1.0f);
+      float uvz = clampf(xsub(xadd(eye.z, xmul(r.t, d.z)), (float)r.cz), 0.0f, 1.0f);
+      const float bnd = P.voxel_edges, hib = xsub(1.0f, P.voxel_edges);
+      int count = (uvx < bnd || uvx > hib) + (uvy < bnd || uvy > hib) + (uvz < bnd || uvz > hib);
+      float f = count >= 2 ? 1.0f : 0.0f;
+      f3 col = mk3(0.0f);
+      int mat = 0;
+      if ((unsigned)r.cx < (unsigned)P.R && (unsigned)r.cy < (unsigned)P.R && (unsigned)r.cz < (unsigned)P.R) {
+        int b = ((r.cz >> 2) * P.brick_res + (r.cy >> 2)) * P.brick_res + (r.cx >> 2);
+        uint32_t c = __ldg(P.color + (size_t)b * 64 + ((r.cz & 3) * 16 + (r.cy & 3) * 4 + (r.cx & 3)));
+        col = f3{xdiv((float)(c & 255u), 255.0f), xdiv((float)((c >> 8) & 255u), 255.0f), xdiv((float)((c >> 16) & 255u), 255.0f)};
+        mat = (int)(c >> 24);
+        if (STATS) (*n_hits)++;
+      }
+      float k = xsub(1.0f, xmul(0.9f, f));
+      h.albedo = f3{xmul(col.x, k), xmul(col.y, k), xmul(col.z, k)};
+      h.mat_id = mat;
+      h.hit_light = mat == 2;
+      h.nx = r.nx, h.ny = r.ny, h.nz = r.nz;
+    }
+  }
+  return h;
+}
+
+// pathtracer.py:293-312 + space_transformations.py:14-30, render_scale = 1, static camera.
+HD f3 get_cast_dir(const Params& P, float u, float v, float jx, float jy) {
+  float tx = xadd(xmul(xadd(u, 0.5f), xdiv(1.0f, (float)P.W)), xmul(jx, 0.5f));
+  float ty = xadd(xmul(xadd(v, 0.5f), xdiv(1.0f, (float)P.H)), xmul(jy, 0.5f));
+  float p[4] = {xsub(xmul(tx, 2.0f), 1.0f), xsub(xmul(ty, 2.0f), 1.0f), 1.0f, 1.0f};
+  float q[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    q[i] = xadd(xadd(xadd(xmul(P.inv_proj[i * 4 + 0], p[0]), xmul(P.inv_proj[i * 4 + 1], p[1])), xmul(P.inv_proj[i * 4 + 2], p[2])),
+                xmul(P.inv_proj[i * 4 + 3], p[3]));
+  f3 dv = xnormalize(f3{xdiv(q[0], q[3]), xdiv(q[1], q[3]), xdiv(q[2], q[3])});
+  float w[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    w[i] = xadd(xadd(xadd(xmul(P.inv_view[i * 4 + 0], dv.x), xmul(P.inv_view[i * 4 + 1], dv.y)), xmul(P.inv_view[i * 4 + 2], dv.z)),
+                xmul(P.inv_view[i * 4 + 3], 0.0f));
+  return f3{w[0], w[1], w[2]};
+}

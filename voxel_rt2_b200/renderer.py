@@ -1,0 +1,260 @@
+"""Host-side mirror of the reference's `Renderer` (renderer/pathtracer.py:27-1334) on top of the
+libvoxelrt C-ABI. Method names, argument meaning and defaults follow the reference so scene.py
+(and tests) read like the reference's callers; everything device-side is CUDA.
+
+No CPU path exists here: constructing a Renderer without libvoxelrt.so or without a CUDA device
+raises RuntimeError."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import _cabi
+from .camera import look_at, perspective
+from .materials import material_table
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("cell", "<i4", (3,)), ("normal", "<f4", (3,)), ("flags", "<u4")])
+_ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+
+def _f32(a, n=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+    if n is not None and a.size != n:
+        raise ValueError("expected %d floats, got %d" % (n, a.size))
+    return a
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Renderer:
+    """Renderer(dx, image_res, up, voxel_edges, exposure) — pathtracer.py:28.
+
+    Extra keyword arguments expose what the reference hard-codes: grid_res (128,
+    pathtracer.py:83), max_depth (MAX_RAY_DEPTH = 4, :17), sky_res (3840, atmos.py:66-67),
+    cloud_passes (32, scene.py:199), device, seed, jitter (TAA jitter on/off)."""
+
+    def __init__(self, dx=1 / 64, image_res=(1920, 1080), up=(0, 1, 0), voxel_edges=0.06, exposure=3, *,
+                 grid_res=128, max_depth=4, sky_res=3840, cloud_passes=32, device=0, seed=0, jitter=True):
+        self._lib = _cabi.load()
+        self.image_res = (int(image_res[0]), int(image_res[1]))
+        self.voxel_grid_res = int(grid_res)
+        self.voxel_dx = float(dx)
+        self.exposure = float(exposure)
+        self.max_depth = int(max_depth)
+        self.sky_res = int(sky_res)
+        self.up = tuple(float(x) for x in up)
+        self.current_spp = 0
+        self.current_frame = 0
+        self.sample_stride = 1   # sample sharding: this renderer draws indices offset, offset+stride, ...
+        self.sample_offset = 0
+        cfg = _cabi.vrt_config(
+            width=self.image_res[0], height=self.image_res[1], grid_res=self.voxel_grid_res, voxel_dx=self.voxel_dx,
+            voxel_edges=float(voxel_edges), exposure=self.exposure, max_depth=self.max_depth, sky_res=self.sky_res,
+            cloud_passes=int(cloud_passes), device=int(device), seed=int(seed) & 0xFFFFFFFF, jitter_mode=1 if jitter else 0)
+        h = C.c_void_p()
+        rc = self._lib.vrt_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("vrt_create failed (%d): %s" % (rc, self._lib.vrt_last_error(None).decode()))
+        self._h = h
+        # reference defaults (pathtracer.py:89-93, scene.py:28-30,127)
+        self.fov = math.radians(50.0)
+        self._camera_pos = np.array((0.4, 0.5, 2.0), np.float64)
+        self._look_at = np.array((0.0, 0.0, 0.0), np.float64)
+        self.floor_height, self.floor_color, self.floor_material = 0.0, (1.0, 1.0, 1.0), 1
+        self.background_color = (0.0, 0.0, 0.0)
+        self.use_physical_atmosphere = 0
+        self.use_clouds = 0
+        self._dirty_camera = True
+        self._check(self._lib.vrt_set_materials(self._h, _fp(material_table().reshape(-1))))
+        tex = np.load(os.path.join(_ASSETS, "cloud_texture.npz"))["tex"]
+        self.set_cloud_texture(tex)
+        self.set_directional_light((1, 1, 1), 0.1, (0.0, 0.0, 0.0))
+        self.set_floor(self.floor_height, self.floor_color, self.floor_material)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("libvoxelrt error %d: %s" % (rc, self._lib.vrt_last_error(self._h).decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vrt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle):
+        """Run all work on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._lib.vrt_set_stream(self._h, C.c_void_p(cuda_stream_handle or None)))
+
+    # ------------------------------------------------------------------ scene state
+    def set_voxels(self, material, color):
+        """Upload the host voxel arrays: material int8 [R,R,R], color uint8 [R,R,R,3] (index = ijk + R/2).
+        Replaces the device-side set_voxel/get_voxel fields (pathtracer.py:1325-1334)."""
+        R = self.voxel_grid_res
+        material = np.ascontiguousarray(material, dtype=np.int8)
+        color = np.ascontiguousarray(color, dtype=np.uint8)
+        if material.shape != (R, R, R) or color.shape != (R, R, R, 3):
+            raise ValueError("voxel arrays must be [%d,%d,%d] and [%d,%d,%d,3]" % ((R,) * 6))
+        self._check(self._lib.vrt_upload_voxels(self._h, material.ctypes.data_as(C.c_void_p), color.ctypes.data_as(C.c_void_p)))
+
+    def set_directional_light(self, direction, light_cone_angle, light_color):  # pathtracer.py:139-144
+        self.light_direction = tuple(float(x) for x in direction)
+        self.light_cone_angle = float(light_cone_angle)
+        self.light_color = tuple(float(x) for x in light_color)
+        self._check(self._lib.vrt_set_light(self._h, _fp(_f32(direction, 3)), C.c_float(light_cone_angle), _fp(_f32(light_color, 3))))
+
+    def set_floor(self, height, color, material=1):  # scene.py:148-151
+        self.floor_height, self.floor_color, self.floor_material = float(height), tuple(color), int(material)
+        self._check(self._lib.vrt_set_floor(self._h, C.c_float(height), _fp(_f32(color, 3)), int(material)))
+
+    def set_background_color(self, color):  # scene.py:156-157
+        self.background_color = tuple(color)
+        self._check(self._lib.vrt_set_background(self._h, _fp(_f32(color, 3))))
+
+    def set_use_physical_sky(self, use, clouds=None):  # scene.py:159-169
+        self.use_physical_atmosphere = 1 if use else 0
+        if clouds is not None:
+            self.use_clouds = 1 if clouds else 0
+        self._check(self._lib.vrt_set_sky(self._h, self.use_physical_atmosphere, self.use_clouds))
+
+    def set_use_clouds(self, use):
+        self.use_clouds = 1 if use else 0
+        self._check(self._lib.vrt_set_sky(self._h, self.use_physical_atmosphere, self.use_clouds))
+
+    def set_materials(self, table128x14):
+        self._check(self._lib.vrt_set_materials(self._h, _fp(_f32(table128x14, 128 * 14))))
+
+    def set_cloud_texture(self, tex):
+        tex = np.ascontiguousarray(tex, dtype=np.uint8)
+        if tex.shape != (256, 256, 3):
+            raise ValueError("cloud texture must be uint8 [256,256,3]")
+        self._check(self._lib.vrt_set_cloud_texture(self._h, tex.ctypes.data_as(C.c_void_p)))
+
+    # ------------------------------------------------------------------ camera (pathtracer.py:246-281)
+    def set_camera_pos(self, x, y, z):
+        self._camera_pos = np.array((x, y, z), np.float64)
+        self._dirty_camera = True
+
+    def set_look_at(self, x, y, z):
+        self._look_at = np.array((x, y, z), np.float64)
+        self._dirty_camera = True
+
+    def set_up(self, x, y, z):
+        self.up = (float(x), float(y), float(z))
+        self._dirty_camera = True
+
+    def set_fov(self, fov):
+        self.fov = float(fov)
+        self._dirty_camera = True
+
+    def set_view_proj(self, pos, view, proj):
+        """Explicit matrices (row-major 4x4), as scene.py:233-237 uploads them."""
+        self._check(self._lib.vrt_set_camera(self._h, _fp(_f32(pos, 3)), _fp(_f32(view, 16)), _fp(_f32(proj, 16))))
+        self._dirty_camera = False
+
+    def _sync_camera(self):
+        if self._dirty_camera:
+            view = look_at(self._camera_pos, self._look_at, self.up)
+            proj = perspective(self.fov, self.image_res[0] / self.image_res[1])
+            self.set_view_proj(self._camera_pos, view, proj)
+
+    # ------------------------------------------------------------------ frame pipeline
+    def prepare_data(self):
+        """pathtracer.py:314-323 + the sky start-up frames of Scene.finish (scene.py:243-253)."""
+        self._sync_camera()
+        self._check(self._lib.vrt_prepare(self._h))
+
+    def set_tile_shard(self, rank, n):
+        self._check(self._lib.vrt_set_tile_shard(self._h, int(rank), int(n)))
+
+    def set_sample_shard(self, rank, n):
+        """Sample sharding: this renderer renders sample indices rank, rank+n, rank+2n, ..."""
+        self.sample_offset, self.sample_stride = int(rank), int(n)
+
+    def accumulate(self, spp=1, stats=False):
+        """pathtracer.py:1310-1319, `spp` frames in one launch."""
+        self._sync_camera()
+        first = self.sample_offset + self.current_spp * self.sample_stride
+        self._check(self._lib.vrt_accumulate(self._h, first, int(spp), self.sample_stride, 1 if stats else 0))
+        self.current_spp += int(spp)
+        self.current_frame += int(spp)
+
+    def reset_framebuffer(self):  # pathtracer.py:664-668
+        self.current_spp = 0
+        self._check(self._lib.vrt_reset(self._h))
+
+    def fetch_image(self):
+        """pathtracer.py:1321-1323 -> float32 [H, W, 4] tonemapped image (row 0 = bottom row v=0)."""
+        out = np.empty((self.image_res[1], self.image_res[0], 4), np.float32)
+        self._check(self._lib.vrt_fetch_ldr(self._h, _fp(out)))
+        return out
+
+    def fetch_hdr(self):
+        """Mean linear radiance, float32 [H, W, 4] (w = samples accumulated)."""
+        out = np.empty((self.image_res[1], self.image_res[0], 4), np.float32)
+        self._check(self._lib.vrt_fetch_hdr(self._h, _fp(out)))
+        return out
+
+    def resolve_ldr_device(self):
+        p = C.c_void_p()
+        self._check(self._lib.vrt_resolve_ldr_device(self._h, C.byref(p)))
+        return p.value
+
+    def trace_primary(self):
+        """Primary-hit dump: structured array [H, W] of (t, cell, normal, flags)."""
+        self._sync_camera()
+        out = np.empty((self.image_res[1], self.image_res[0]), HIT_DTYPE)
+        self._check(self._lib.vrt_trace_primary(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def accum_device_ptr(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.vrt_accum_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def accum_tensor(self):
+        """The float4 accumulation buffer as a torch CUDA tensor [H, W, 4] sharing memory with the
+        library (for torch.distributed collectives)."""
+        import torch
+
+        ptr, nbytes = self.accum_device_ptr()
+
+        class _Wrap:
+            pass
+
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (self.image_res[1], self.image_res[0], 4), "typestr": "<f4",
+                                      "data": (ptr, False), "version": 3}
+        return torch.as_tensor(w, device="cuda")
+
+    def get_sky_tables(self):
+        S = self.sky_res
+        a = np.empty((S, S, 3), np.float32)
+        b = np.empty((S, S, 3), np.float32)
+        self._check(self._lib.vrt_get_sky_tables(self._h, _fp(a), _fp(b)))
+        return a, b
+
+    def set_sky_tables(self, scattering, transmittance):
+        S = self.sky_res
+        self._check(self._lib.vrt_set_sky_tables(self._h, _fp(_f32(scattering, S * S * 3)), _fp(_f32(transmittance, S * S * 3))))
+
+    def get_trans_lut(self):
+        a = np.empty((256, 128, 3), np.float16)
+        self._check(self._lib.vrt_get_trans_lut(self._h, a.ctypes.data_as(C.c_void_p)))
+        return a
+
+    def stats(self):
+        s = _cabi.vrt_stats()
+        self._check(self._lib.vrt_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _cabi.vrt_stats._fields_}
+
+    def synchronize(self):
+        self._check(self._lib.vrt_synchronize(self._h))
