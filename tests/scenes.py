@@ -48,7 +48,7 @@ def city(R=128, seed=0, n=50):
             else:
                 put(i, 0, j, 1, (0.9, 0.1, 0.1))
                 if rng.random() < 0.04:
-                    height = int(rng.random() * 20)
+                    height = min(int(rng.random() * 20), R // 2 - 1)
                     for k in range(1, height):
                         put(i, k, j, 1, (0.0, 0.5, 0.9))
                     if height:

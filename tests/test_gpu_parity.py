@@ -107,8 +107,8 @@ def test_radiance_city_background_sky(vrt, oracle):
     # zero-throughput paths lets the GPU trace a few rays fewer)
     cg, co = g.stats(), o.counters()
     assert cg["paths"] == co["paths"]
-    assert abs(cg["vertices"] - co["vertices"]) <= 0.02 * co["vertices"]
-    assert cg["rays"] <= co["rays"] * 1.001
+    assert 0.9 * co["vertices"] <= cg["vertices"] <= co["vertices"]
+    assert 0.9 * co["rays"] <= cg["rays"] <= co["rays"]
 
 
 def test_radiance_material_zoo_all_lobes(vrt, oracle):

@@ -1,0 +1,85 @@
+"""N > 1 host logic on CPU: world_size-2 gloo. Each rank renders its sample shard (engine: the
+CPU oracle — test infrastructure standing in for the per-rank CUDA context) and the product's
+merge helper (voxel_rt2_b200.parallel) all-reduces the accumulation buffers; the merged image
+must equal the unsharded render. The same helper runs over NCCL in bench.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, mode, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    import scenes
+    from oracle.binding import OracleRenderer
+    from voxel_rt2_b200 import parallel
+    from voxel_rt2_b200.materials import material_table
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    R, res, spp = 32, (64, 32), 4
+    o = OracleRenderer(dx=2.0 / R, image_res=res, grid_res=R, sky_res=0, seed=3, materials=material_table())
+    o.n_threads = 2
+    o.set_voxels(*scenes.random_grid(R, 0.3, 9))
+    o.set_background_color((0.5, 0.6, 0.7))
+    o.set_directional_light((1, 1, 1), 0.1, (1, 1, 1))
+    r, w = parallel.rank_world()
+    if mode == "sample":
+        parallel.shard_samples(o, r, w)
+        o.prepare_data()
+        o.accumulate(spp // w)
+    else:
+        parallel.shard_tiles(o, r, w)
+        o.prepare_data()
+        o.accumulate(spp)
+    h = o.fetch_hdr()
+    accum = torch.from_numpy(np.concatenate([h[..., :3] * h[..., 3:4], h[..., 3:4]], axis=-1).copy())
+    if mode == "tile":
+        # pixels outside this rank's tiles were never rendered
+        assert float((accum[..., 3] == 0).float().mean()) > 0.4
+    parallel.merge_accumulation(accum)
+    mean = parallel.mean_from_accumulation(accum)
+    if rank == 0:
+        q.put(mean.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["sample", "tile"])
+def test_world_size_2_gloo_merge_equals_unsharded(oracle, mode):
+    import torch.multiprocessing as mp
+
+    import scenes
+    from voxel_rt2_b200.materials import material_table
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (0 if mode == "sample" else 1)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    R, res, spp = 32, (64, 32), 4
+    o = oracle.OracleRenderer(dx=2.0 / R, image_res=res, grid_res=R, sky_res=0, seed=3, materials=material_table())
+    o.set_voxels(*scenes.random_grid(R, 0.3, 9))
+    o.set_background_color((0.5, 0.6, 0.7))
+    o.set_directional_light((1, 1, 1), 0.1, (1, 1, 1))
+    o.prepare_data()
+    o.accumulate(spp)
+    full = o.fetch_hdr()
+    assert np.array_equal(merged[..., 3], full[..., 3])
+    if mode == "tile":
+        assert np.allclose(merged[..., :3], full[..., :3], rtol=1e-6, atol=1e-7)
+    else:
+        # same sample set, summed in a different order (running means vs sums)
+        assert np.allclose(merged[..., :3], full[..., :3], rtol=2e-5, atol=1e-6)

@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, 
   // lane state
   int pix = PIX_IDLE;
   int s_i = 0, depth = 0, state = ST_SEGMENT, f_lobe = 0;
-  bool sky_ray = false;
   uint32_t key = 0, pm_info = 0;
   f3 pos = mk3(0.0f), d = mk3(0.0f), thr = mk3(1.0f), contrib = mk3(0.0f), acc = mk3(0.0f);
   f3 fnee_d = mk3(0.0f), fnee_s = mk3(0.0f);
@@ -112,45 +111,36 @@ __global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, 
   TraceCounters tc{0, 0, 0};
   uint32_t c_hits = 0, c_escapes = 0, c_nee = 0, c_vertices = 0, c_paths = 0;
 
-  auto start_path = [&]() {
-    const int tile = P.tile_rank + P.tile_n * (pix >> 5);
-    const int u = (tile % P.tiles_x) * 8 + (pix & 7), v = (tile / P.tiles_x) * 4 + ((pix >> 3) & 3);
-    const uint32_t sample = (uint32_t)(P.first_sample + s_i * P.stride);
-    key = path_key((uint32_t)(v * P.W + u), sample, P.seed);
-    const float2 j = P.jitter[s_i];
-    d = get_cast_dir(P, (float)u, (float)v, j.x, j.y);
-    pos = P.cam_pos;
-    thr = mk3(1.0f), contrib = mk3(0.0f), fnee_d = mk3(0.0f), fnee_s = mk3(0.0f);
-    f_invpdf = 1.0f, f_lobe = 0, pm_info = 0, sky_ray = false, depth = 0, state = ST_SEGMENT;
-    if (STATS) c_paths++;
-  };
-  // pathtracer.py:609-619 + NaN scrub :1068-1075, then either the next sample of this pixel or
-  // the single read-modify-write of the accumulation texel.
-  auto finish_path = [&]() {
-    f3 emission = mk3(0.0f);
-    if ((pm_info & 255u) == 2u)
-      emission = f3{(float)((pm_info >> 8) & 255u) / 255.0f, (float)((pm_info >> 16) & 255u) / 255.0f, (float)((pm_info >> 24) & 255u) / 255.0f};
-    f3 diffuse = fnee_d, specular = fnee_s;
-    if (f_lobe == LOBE_DIFFUSE) diffuse += contrib * f_invpdf + emission;
-    if (f_lobe == LOBE_SPEC_REFL) specular += contrib * f_invpdf;
-    if (bad3(diffuse)) diffuse = mk3(0.0f);
-    if (bad3(specular)) specular = mk3(0.0f);
-    acc += diffuse + specular;
-    s_i++;
-    if (s_i < P.n_samples) {
-      start_path();
-    } else {
-      const int tile = P.tile_rank + P.tile_n * (pix >> 5);
-      const int u = (tile % P.tiles_x) * 8 + (pix & 7), v = (tile / P.tiles_x) * 4 + ((pix >> 3) & 3);
-      float4* dst = P.accum + (size_t)v * P.W + u;
-      float4 a = *dst;
-      a.x += acc.x, a.y += acc.y, a.z += acc.z, a.w += (float)P.n_samples;
-      *dst = a;
-      pix = PIX_IDLE;
-    }
-  };
+  bool finished = false, restart = false;
 
   for (;;) {
+    // ---- (0) retire finished paths at one converged site: pixel sample value
+    // (pathtracer.py:609-619), NaN scrub (:1068-1075), then either the next sample of this
+    // pixel or the single read-modify-write of its accumulation texel.
+    if (finished) {
+      finished = false;
+      f3 emission = mk3(0.0f);
+      if ((pm_info & 255u) == 2u)
+        emission = f3{(float)((pm_info >> 8) & 255u) / 255.0f, (float)((pm_info >> 16) & 255u) / 255.0f, (float)((pm_info >> 24) & 255u) / 255.0f};
+      f3 diffuse = fnee_d, specular = fnee_s;
+      if (f_lobe == LOBE_DIFFUSE) diffuse += contrib * f_invpdf + emission;
+      if (f_lobe == LOBE_SPEC_REFL) specular += contrib * f_invpdf;
+      if (bad3(diffuse)) diffuse = mk3(0.0f);
+      if (bad3(specular)) specular = mk3(0.0f);
+      acc += diffuse + specular;
+      s_i++;
+      if (s_i < P.n_samples) {
+        restart = true;
+      } else {
+        const int tile = P.tile_rank + P.tile_n * (pix >> 5);
+        const int u = (tile % P.tiles_x) * 8 + (pix & 7), v = (tile / P.tiles_x) * 4 + ((pix >> 3) & 3);
+        float4* dst = P.accum + (size_t)v * P.W + u;
+        float4 a = *dst;
+        a.x += acc.x, a.y += acc.y, a.z += acc.z, a.w += (float)P.n_samples;
+        *dst = a;
+        pix = PIX_IDLE;
+      }
+    }
     // ---- (1) refill idle lanes from the warp's tile queue
     for (;;) {
       const unsigned need = __ballot_sync(FULL, pix == PIX_IDLE);
@@ -171,9 +161,23 @@ __global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, 
         pix = chunk_base + (32 - chunk_rem) + rank;
         s_i = 0;
         acc = mk3(0.0f);
-        start_path();
+        restart = true;
       }
       chunk_rem -= min(__popc(need), chunk_rem);
+    }
+    // ---- (1b) start the next path (new pixel or next sample of the same pixel), one site
+    if (restart) {
+      restart = false;
+      const int tile = P.tile_rank + P.tile_n * (pix >> 5);
+      const int u = (tile % P.tiles_x) * 8 + (pix & 7), v = (tile / P.tiles_x) * 4 + ((pix >> 3) & 3);
+      const uint32_t sample = (uint32_t)(P.first_sample + s_i * P.stride);
+      key = path_key((uint32_t)(v * P.W + u), sample, P.seed);
+      const float2 j = P.jitter[s_i];
+      d = get_cast_dir(P, (float)u, (float)v, j.x, j.y);
+      pos = P.cam_pos;
+      thr = mk3(1.0f), contrib = mk3(0.0f), fnee_d = mk3(0.0f), fnee_s = mk3(0.0f);
+      f_invpdf = 1.0f, f_lobe = 0, pm_info = 0, depth = 0, state = ST_SEGMENT;
+      if (STATS) c_paths++;
     }
     if (__all_sync(FULL, pix == PIX_DONE)) break;
     const bool active = pix >= 0;
@@ -203,13 +207,12 @@ __global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, 
           }
           f3 sky_emission = firefly_filter(sky_scattering + sky_T * sun_rad * hit_sun);
           contrib += thr * sky_emission;
-          if (depth == 0) sky_ray = true;
-          finish_path();
+          finished = true;
         } else if (h.hit_light) {
           // emissive voxel / floor terminates the path (pathtracer.py:519-525)
           if (depth > 0) contrib += thr * h.albedo;
           if (depth == 0) pm_info = encode_material(h.mat_id, h.albedo);
-          finish_path();
+          finished = true;
         } else {
           if (STATS) c_vertices++;
           s_n = f3{h.nx, h.ny, h.nz};
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, 
       depth++;
       // The reference keeps tracing zero-throughput paths; they add exact zeros, so stop here.
       const bool dead = thr.x == 0.0f && thr.y == 0.0f && thr.z == 0.0f;
-      if (depth >= P.max_depth || dead) finish_path();
+      if (depth >= P.max_depth || dead) finished = true;
     }
   }
 
