@@ -39,7 +39,7 @@ SUN = ((1, 1, 1), 0.025, (1.0 * 1.3, 0.949 * 1.3, 0.937 * 1.3))  # example6.py:1
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=8, help="samples per pixel per step (per GPU)")
@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--res", default="1920x1080")
     ap.add_argument("--sky-res", type=int, default=3840)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-spp", type=int, default=4, help="samples per pixel of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-spp", type=int, default=48, help="samples per pixel of the bounded CPU-baseline sample")
     return ap.parse_args()
 
 
