@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvoxelrt.so")
+# VRT_LIB selects an alternative build of the same library (kernel tuning variants); never a fallback
+LIB_PATH = os.environ.get("VRT_LIB") or os.path.join(HERE, "libvoxelrt.so")
 
 EXPORTS = [
     "vrt_create", "vrt_destroy", "vrt_last_error", "vrt_set_stream", "vrt_upload_voxels", "vrt_set_camera",

@@ -38,6 +38,32 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """Tuning variant of the library (e.g. a different __launch_bounds__), built next to the
+    default one as variants/libvoxelrt_<name>.so and selected with VRT_LIB=<path>."""
+    nvcc = _nvcc()
+    ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(vdir, "%s_%s" % (name, src.replace(".cu", ".o")))
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-ccbin", ccbin] if ccbin else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on %s" % src)
+        objs.append(obj)
+    lib = os.path.join(vdir, "libvoxelrt_%s.so" % name)
+    r = subprocess.run([nvcc, "-shared", "-o", lib] + (["-ccbin", ccbin] if ccbin else []) + objs + ["-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    for o in objs:
+        os.remove(o)
+    return lib
+
+
 def build(force=False, verbose=False):
     """Compile every CUDA translation unit for sm_100a and link libvoxelrt.so."""
     if not force and not _stale():

@@ -114,14 +114,32 @@ static double halton(uint32_t i, uint32_t b) {
   return r;
 }
 
-static void default_materials(float* t) {  // materials.py:50-63
-  for (int i = 0; i < 128; i++) {
-    float* r = t + i * 16;
-    memset(r, 0, 16 * sizeof(float));
-    r[0] = r[1] = r[2] = 1.0f;
-    r[5] = 0.04f;  // specular
-    r[7] = 0.9f;   // roughness
-  }
+// One 20-float device row per material from the 14 reference parameters (bsdf.py:26-37 order:
+// base rgb, subsurface, metallic, specular, specular_tint, roughness, anisotropic, sheen,
+// sheen_tint, clearcoat, clearcoat_gloss, ior_minus_one) + the per-material constants the
+// reference recomputes at every vertex (bsdf.py:92-95, :113-118, :351-363), in float32.
+static void pack_material(const float* p, float* r) {
+  const float pi = 3.14159265358979323846f;
+  const float subsurface = p[3], metallic = p[4], specular = p[5], specular_tint = p[6], roughness = p[7], anisotropic = p[8];
+  const float sheen = p[9], sheen_tint = p[10], clearcoat = p[11], clearcoat_gloss = p[12];
+  float dw = (1.0f - metallic) * fmaxf(0.4f, fminf(0.9f, 1.0f - specular));
+  float sw = 1.0f - dw;
+  float cw = clearcoat * 0.7f;
+  const float w_sum = dw + sw + cw;
+  dw /= w_sum, sw /= w_sum, cw /= w_sum;
+  const float aspect = sqrtf(1.0f - 0.9f * anisotropic);
+  const float ax = fmaxf(roughness * roughness / aspect, 1e-3f), ay = fmaxf(roughness * roughness * aspect, 1e-3f);
+  const float cc_alpha = 0.1f * (1.0f - clearcoat_gloss) + 0.001f * clearcoat_gloss;
+  const float a2 = cc_alpha * cc_alpha;
+  const float cc_norm = cc_alpha >= 1.0f ? 1.0f / pi : (a2 - 1.0f) / (pi * logf(a2));
+  const float row[20] = {p[0], p[1], p[2], subsurface, metallic, specular, specular_tint, roughness, sheen, sheen_tint,
+                         clearcoat, cc_alpha, dw, sw, cw, cc_norm, ax, ay, 1.0f / (pi * ax * ay), 0.0f};
+  memcpy(r, row, sizeof row);
+}
+
+static void default_materials(float* rows) {  // materials.py:50-63
+  const float d[14] = {1.0f, 1.0f, 1.0f, 0.0f, 0.0f, 0.04f, 0.0f, 0.9f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  for (int i = 0; i < 128; i++) pack_material(d, rows + i * 20);
 }
 
 static int n_local_tiles(const vrt_ctx* ctx) {
@@ -252,7 +270,7 @@ int vrt_create(const vrt_config* cfg, vrt_ctx** out) {
   CKC(cudaMalloc(&ctx->d_bricks, nvox / 64 * sizeof(unsigned long long)));
   CKC(cudaMalloc(&ctx->d_color, nvox * 4));
   CKC(cudaMalloc(&ctx->d_upper, (size_t)(ctx->upper_words > 0 ? ctx->upper_words : 1) * 4));
-  CKC(cudaMalloc(&ctx->d_mats, 128 * 16 * sizeof(float)));
+  CKC(cudaMalloc(&ctx->d_mats, 128 * 20 * sizeof(float)));
   const size_t npx = (size_t)cfg->width * cfg->height;
   CKC(cudaMalloc(&ctx->d_accum, npx * sizeof(float4)));
   CKC(cudaMalloc(&ctx->d_out, npx * sizeof(float4)));
@@ -269,7 +287,7 @@ int vrt_create(const vrt_config* cfg, vrt_ctx** out) {
     CKC(cudaMalloc(&ctx->d_trans_lut, 256 * 128 * 3 * sizeof(__half)));
   }
   {
-    std::vector<float> t(128 * 16);
+    std::vector<float> t(128 * 20);
     default_materials(t.data());
     CKC(cudaMemcpyAsync(ctx->d_mats, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
@@ -366,9 +384,8 @@ int vrt_set_materials(vrt_ctx* ctx, const float* t) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(t, "vrt_set_materials: null pointer");
   CK(cudaSetDevice(ctx->device));
-  std::vector<float> rows(128 * 16, 0.0f);
-  for (int i = 0; i < 128; i++)
-    for (int j = 0; j < 14; j++) rows[i * 16 + j] = t[i * 14 + j];
+  std::vector<float> rows(128 * 20, 0.0f);
+  for (int i = 0; i < 128; i++) pack_material(t + i * 14, rows.data() + i * 20);
   CK(cudaMemcpyAsync(ctx->d_mats, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return VRT_OK;

@@ -11,13 +11,15 @@ enum { LOBE_DIFFUSE = 0, LOBE_SPEC_REFL = 1, LOBE_CLEARC = 2 };
 
 HD Mat load_mat(const float4* __restrict__ mats, int id) {
   id = min(max(id, 0), 127);
-  float4 a = mats[id * 4 + 0], b = mats[id * 4 + 1], c = mats[id * 4 + 2], d = mats[id * 4 + 3];
+  const float4* r = mats + id * MAT_ROW_F4;
+  float4 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4];
   Mat m;
   m.base_col = f3{a.x, a.y, a.z};
   m.subsurface = a.w;
   m.metallic = b.x, m.specular = b.y, m.specular_tint = b.z, m.roughness = b.w;
-  m.anisotropic = c.x, m.sheen = c.y, m.sheen_tint = c.z, m.clearcoat = c.w;
-  m.clearcoat_gloss = d.x;
+  m.sheen = c.x, m.sheen_tint = c.y, m.clearcoat = c.z, m.cc_alpha = c.w;
+  m.dw = d.x, m.sw = d.y, m.cw = d.z, m.cc_norm = d.w;
+  m.ax = e.x, m.ay = e.y, m.inv_pi_axay = e.z;
   return m;
 }
 
@@ -31,46 +33,26 @@ HD void make_orthonormal_basis(f3 n, f3& x, f3& y) {
 // math_utils.py:21-30
 HD f3 sample_cosine_weighted_hemisphere(f3 n, float u0, float u1) {
   float a = 1.0f - 2.0f * u0;
-  float b = sqrtf(1.0f - a * a);
+  float b = fsqrt(1.0f - a * a);
   a *= 1.0f - 1e-5f;
   b *= 1.0f - 1e-5f;
   float s, c;
-  sincosf(2.0f * VRT_PI * u1, &s, &c);
+  __sincosf(2.0f * VRT_PI * u1, &s, &c);
   return normalize(f3{n.x + b * c, n.y + b * s, n.z + a});
 }
 
 // math_utils.py:44-59 (basis supplied by the caller: the sun axis is a per-launch constant)
 HD f3 sample_cone_oriented(float cos_theta_max, f3 n, f3 bx, f3 by, float u0, float u1) {
   float cos_theta = (1.0f - u0) + u0 * cos_theta_max;
-  float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+  float sin_theta = fsqrt(1.0f - cos_theta * cos_theta);
   float s, c;
-  sincosf(2.0f * VRT_PI * u1, &s, &c);
+  __sincosf(2.0f * VRT_PI * u1, &s, &c);
   float sx = sin_theta * c, sy = sin_theta * s, sz = cos_theta;
   return f3{(bx.x * sx + by.x * sy) + n.x * sz, (bx.y * sx + by.y * sy) + n.y * sz, (bx.z * sx + by.z * sy) + n.z * sz};
 }
 // math_utils.py:61-63
 HD float cone_sample_pdf(float cos_theta_max, float cos_theta) {
   return cos_theta >= cos_theta_max ? 1.0f / (2.0f * VRT_PI * (1.0f - cos_theta_max)) : 0.0f;
-}
-
-// Per-vertex constants derived from the material (bsdf.py:92-95,113,351-363).
-struct MatK {
-  float dw, sw, cw;      // lobe probabilities
-  float ax, ay;          // anisotropic GGX alphas
-  float cc_alpha;        // clear-coat GTR1 alpha
-};
-HD MatK mat_constants(const Mat& m) {
-  MatK k;
-  float dw = (1.0f - m.metallic) * clampf(1.0f - m.specular, 0.4f, 0.9f);
-  float sw = 1.0f - dw;
-  float cw = m.clearcoat * 0.7f;
-  float w_sum = dw + sw + cw;
-  k.dw = dw / w_sum, k.sw = sw / w_sum, k.cw = cw / w_sum;
-  float aspect = sqrtf(1.0f - 0.9f * m.anisotropic);
-  k.ax = fmaxf(sqr(m.roughness) / aspect, 1e-3f);
-  k.ay = fmaxf(sqr(m.roughness) * aspect, 1e-3f);
-  k.cc_alpha = mixf(0.1f, 0.001f, m.clearcoat_gloss);
-  return k;
 }
 
 // bsdf.py:39-67 diffuse + retro-reflection + sheen + subsurface
@@ -90,39 +72,44 @@ HD f3 disney_diffuse(const Mat& m, float n_dot_l, float n_dot_v, float l_dot_h) 
   if (m.subsurface != 0.0f) {
     float Fss90 = l_dot_h * l_dot_h * m.roughness;
     float Fss = mixf(1.0f, Fss90, F_L) * mixf(1.0f, Fss90, F_V);
-    float ss = 1.25f * (Fss * (1.0f / (n_dot_l + n_dot_v) - 0.5f) + 0.5f);
+    float ss = 1.25f * (Fss * (frcp(n_dot_l + n_dot_v) - 0.5f) + 0.5f);
     f3 sub = ((1.0f / VRT_PI) * ss) * m.base_col;
     f_d = mix3(f_d, sub, m.subsurface);
   }
   return f_d + sheen;
 }
 
-HD float GTR2_anisotropic(float n_dot_h, float h_dot_x, float h_dot_y, float ax, float ay) {  // bsdf.py:69-71
-  return 1.0f / (VRT_PI * ax * ay * sqr(sqr(h_dot_x / ax) + sqr(h_dot_y / ay) + sqr(n_dot_h)));
+// bsdf.py:69-71: 1 / (pi ax ay (hx^2/ax^2 + hy^2/ay^2 + nh^2)^2); 1/(pi ax ay) comes from the table
+HD float GTR2_anisotropic(const Mat& m, float n_dot_h, float h_dot_x, float h_dot_y) {
+  float q = sqr(fdiv(h_dot_x, m.ax)) + sqr(fdiv(h_dot_y, m.ay)) + sqr(n_dot_h);
+  return m.inv_pi_axay * frcp(q * q);
 }
 HD float smithG_GGX_aniso(float n_dot_v, float v_dot_x, float v_dot_y, float ax, float ay) {  // bsdf.py:73-75
-  return 1.0f / (n_dot_v + sqrtf(sqr(v_dot_x * ax) + sqr(v_dot_y * ay) + sqr(n_dot_v)));
+  return frcp(n_dot_v + fsqrt(sqr(v_dot_x * ax) + sqr(v_dot_y * ay) + sqr(n_dot_v)));
 }
 HD f3 disney_fresnel(const Mat& m, float l_dot_h) {  // bsdf.py:77-83
-  float albedo_lum = luminance(m.base_col);
-  f3 spec_tint = albedo_lum > 0.0f ? m.base_col / albedo_lum : mk3(1.0f);
-  f3 spec_col = mix3((m.specular * 0.08f) * mix3(mk3(1.0f), spec_tint, m.specular_tint), m.base_col, m.metallic);
+  f3 tint = mk3(1.0f);
+  if (m.specular_tint != 0.0f) {  // mix(1, spec_tint, 0) == 1 otherwise
+    float albedo_lum = luminance(m.base_col);
+    f3 spec_tint = albedo_lum > 0.0f ? m.base_col / albedo_lum : mk3(1.0f);
+    tint = mix3(mk3(1.0f), spec_tint, m.specular_tint);
+  }
+  f3 spec_col = mix3((m.specular * 0.08f) * tint, m.base_col, m.metallic);
   return mix3(spec_col, mk3(1.0f), pow5(1.0f - l_dot_h));
 }
-HD float GTR1(float n_dot_h, float alpha) {  // bsdf.py:112-121
-  float a2 = alpha * alpha;
+// bsdf.py:112-121 with (a2-1)/(pi log a2) hoisted into the material row (cc_norm; 1/pi if alpha >= 1)
+HD float GTR1(const Mat& m, float n_dot_h) {
+  float a2 = m.cc_alpha * m.cc_alpha;
   float t = 1.0f + (a2 - 1.0f) * n_dot_h * n_dot_h;
-  float D = (a2 - 1.0f) / (VRT_PI * logf(a2) * t);
-  if (alpha >= 1.0f) D = 1.0f / VRT_PI;
-  return D;
+  return m.cc_alpha >= 1.0f ? m.cc_norm : fdiv(m.cc_norm, t);
 }
 HD float smithG_GGX(float n_dot_v, float alpha) {  // bsdf.py:123-127
   float a2 = alpha * alpha;
   float b = n_dot_v * n_dot_v;
-  return 1.0f / (n_dot_v + sqrtf(a2 + b - a2 * b));
+  return frcp(n_dot_v + fsqrt(a2 + b - a2 * b));
 }
-HD float disney_clearcoat(const Mat& m, const MatK& k, float n_dot_l, float n_dot_v, float n_dot_h, float l_dot_h) {  // :129-135
-  float D = GTR1(fabsf(n_dot_h), k.cc_alpha);
+HD float disney_clearcoat(const Mat& m, float n_dot_l, float n_dot_v, float n_dot_h, float l_dot_h) {  // :129-135
+  float D = GTR1(m, fabsf(n_dot_h));
   float F = mixf(0.04f, 1.0f, pow5(1.0f - l_dot_h));
   float G = smithG_GGX(n_dot_l, 0.25f) * smithG_GGX(n_dot_v, 0.25f);
   return m.clearcoat * D * F * G;
@@ -142,32 +129,32 @@ HD Geo make_geo(f3 v, f3 n, f3 l, f3 tang, f3 bitang) {
   g.v_dot_x = dot(v, tang), g.v_dot_y = dot(v, bitang);
   return g;
 }
-HD f3 disney_specular(const Mat& m, const MatK& k, const Geo& g) {  // bsdf.py:86-105
-  float D = GTR2_anisotropic(g.n_dot_h, g.h_dot_x, g.h_dot_y, k.ax, k.ay);
-  float G = smithG_GGX_aniso(g.n_dot_l, g.l_dot_x, g.l_dot_y, k.ax, k.ay) * smithG_GGX_aniso(g.n_dot_v, g.v_dot_x, g.v_dot_y, k.ax, k.ay);
+HD f3 disney_specular(const Mat& m, const Geo& g) {  // bsdf.py:86-105
+  float D = GTR2_anisotropic(m, g.n_dot_h, g.h_dot_x, g.h_dot_y);
+  float G = smithG_GGX_aniso(g.n_dot_l, g.l_dot_x, g.l_dot_y, m.ax, m.ay) * smithG_GGX_aniso(g.n_dot_v, g.v_dot_x, g.v_dot_y, m.ax, m.ay);
   return (D * G) * disney_fresnel(m, g.l_dot_h);
 }
 
 // bsdf.py:138-177 disney_evaluate_split and :382-393 pdf_disney for the same (v,n,l): the NEE
 // sample needs both, and they share the half vector and the GGX D term.
-HD void eval_and_pdf(const Mat& m, const MatK& k, f3 v, f3 n, f3 l, f3 tang, f3 bitang, f3& bsdf_d, f3& bsdf_s, float& pdf) {
+HD void eval_and_pdf(const Mat& m, f3 v, f3 n, f3 l, f3 tang, f3 bitang, f3& bsdf_d, f3& bsdf_s, float& pdf) {
   Geo g = make_geo(v, n, l, tang, bitang);
   bsdf_d = mk3(0.0f);
   bsdf_s = mk3(0.0f);
-  float D = GTR2_anisotropic(g.n_dot_h, g.h_dot_x, g.h_dot_y, k.ax, k.ay);
-  float Gv = smithG_GGX_aniso(g.n_dot_v, g.v_dot_x, g.v_dot_y, k.ax, k.ay);
+  float D = GTR2_anisotropic(m, g.n_dot_h, g.h_dot_x, g.h_dot_y);
+  float Gv = smithG_GGX_aniso(g.n_dot_v, g.v_dot_x, g.v_dot_y, m.ax, m.ay);
   if (g.n_dot_l > 0.0f && g.n_dot_v > 0.0f) {
     bsdf_d = disney_diffuse(m, g.n_dot_l, g.n_dot_v, g.l_dot_h) * (1.0f - m.metallic);
-    float Gl = smithG_GGX_aniso(g.n_dot_l, g.l_dot_x, g.l_dot_y, k.ax, k.ay);
+    float Gl = smithG_GGX_aniso(g.n_dot_l, g.l_dot_x, g.l_dot_y, m.ax, m.ay);
     bsdf_s = (D * (Gl * Gv)) * disney_fresnel(m, g.l_dot_h);
-    if (m.clearcoat != 0.0f) bsdf_s += mk3(disney_clearcoat(m, k, g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
+    if (m.clearcoat != 0.0f) bsdf_s += mk3(disney_clearcoat(m, g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
   }
   // pdf_disney = sum of lobe pdfs times lobe probabilities
-  pdf = (saturate(g.n_dot_l) / VRT_PI) * k.dw;
-  pdf += (Gv * fabsf(g.l_dot_h) * D / fabsf(g.n_dot_l)) * k.sw;  // bsdf.py:254-277
-  if (k.cw != 0.0f) {                                             // bsdf.py:190-199 (cw == 0 adds 0)
+  pdf = (saturate(g.n_dot_l) * (1.0f / VRT_PI)) * m.dw;
+  pdf += fdiv(Gv * fabsf(g.l_dot_h) * D, fabsf(g.n_dot_l)) * m.sw;  // bsdf.py:254-277
+  if (m.cw != 0.0f) {                                               // bsdf.py:190-199 (cw == 0 adds 0)
     float ndh = fabsf(g.n_dot_h);
-    pdf += (GTR1(ndh, k.cc_alpha) * ndh / (4.0f * g.v_dot_h)) * k.cw;
+    pdf += fdiv(GTR1(m, ndh) * ndh, 4.0f * g.v_dot_h) * m.cw;
   }
 }
 
@@ -177,14 +164,14 @@ HD f3 GGX_VNDF_aniso(f3 v, f3 n, f3 tang, f3 bitang, float ax, float ay, float u
   f3 V = normalize(f3{v_t.x * ax, v_t.y, v_t.z * ay});
   f3 t1 = V.y < 0.9999f ? normalize(cross(V, f3{0.0f, 1.0f, 0.0f})) : f3{1.0f, 0.0f, 0.0f};
   f3 t2 = cross(t1, V);
-  float a = 1.0f / (1.0f + V.y);
-  float r = sqrtf(ux);
-  float phi = uy < a ? (uy / a) * VRT_PI : VRT_PI + (uy - a) / (1.0f - a) * VRT_PI;
+  float a = frcp(1.0f + V.y);
+  float r = fsqrt(ux);
+  float phi = uy < a ? fdiv(uy, a) * VRT_PI : VRT_PI + fdiv(uy - a, 1.0f - a) * VRT_PI;
   float s, c;
-  sincosf(phi, &s, &c);
+  __sincosf(phi, &s, &c);
   float p1 = r * c;
   float p2 = r * s * (uy < a ? 1.0f : V.y);
-  f3 mm = p1 * t1 + p2 * t2 + sqrtf(fmaxf(0.0f, 1.0f - p1 * p1 - p2 * p2)) * V;
+  f3 mm = p1 * t1 + p2 * t2 + fsqrt(fmaxf(0.0f, 1.0f - p1 * p1 - p2 * p2)) * V;
   mm = normalize(f3{ax * mm.x, mm.y, ay * mm.z});
   f3 h = mm.x * tang + mm.z * bitang + mm.y * n;
   if (dot(h, v) < 0.0f) h *= -1.0f;
@@ -193,42 +180,41 @@ HD f3 GGX_VNDF_aniso(f3 v, f3 n, f3 tang, f3 bitang, float ax, float ay, float u
 
 // bsdf.py:395-458 sample_disney: returns direction, brdf of the chosen lobe, pdf (lobe pdf x
 // lobe probability; inf/NaN -> 1) and the lobe id.
-HD f3 sample_disney(const Mat& m, const MatK& k, f3 v, f3 n, f3 tang, f3 bitang, float u_lobe, float ux, float uy, f3& brdf,
-                    float& pdf, int& lobe) {
+HD f3 sample_disney(const Mat& m, f3 v, f3 n, f3 tang, f3 bitang, float u_lobe, float ux, float uy, f3& brdf, float& pdf, int& lobe) {
   f3 dir;
-  if (u_lobe <= k.dw) {
+  if (u_lobe <= m.dw) {
     dir = sample_cosine_weighted_hemisphere(n, ux, uy);
     float n_dot_l = dot(n, dir);
-    pdf = (saturate(n_dot_l) / VRT_PI) * k.dw;
+    pdf = (saturate(n_dot_l) * (1.0f / VRT_PI)) * m.dw;
     lobe = LOBE_DIFFUSE;
     f3 h = normalize(dir + v);
     brdf = disney_diffuse(m, n_dot_l, dot(n, v), dot(dir, h)) * (1.0f - m.metallic);
-  } else if (u_lobe <= k.dw + k.sw) {
-    f3 h = GGX_VNDF_aniso(v, n, tang, bitang, k.ax, k.ay, ux, uy);
+  } else if (u_lobe <= m.dw + m.sw) {
+    f3 h = GGX_VNDF_aniso(v, n, tang, bitang, m.ax, m.ay, ux, uy);
     dir = reflect(-v, h);
     // pdf with the sampled micro-normal (bsdf.py:290-302)
-    float D = GTR2_anisotropic(dot(n, h), dot(h, tang), dot(h, bitang), k.ax, k.ay);
-    float Gv = smithG_GGX_aniso(dot(n, v), dot(v, tang), dot(v, bitang), k.ax, k.ay);
-    pdf = (Gv * fabsf(dot(dir, h)) * D / fabsf(dot(n, dir))) * k.sw;
+    float D = GTR2_anisotropic(m, dot(n, h), dot(h, tang), dot(h, bitang));
+    float Gv = smithG_GGX_aniso(dot(n, v), dot(v, tang), dot(v, bitang), m.ax, m.ay);
+    pdf = fdiv(Gv * fabsf(dot(dir, h)) * D, fabsf(dot(n, dir))) * m.sw;
     lobe = LOBE_SPEC_REFL;
     // brdf with the half vector recomputed from (dir, v) as the reference does (:430-450)
     Geo g = make_geo(v, n, dir, tang, bitang);
-    brdf = disney_specular(m, k, g);
+    brdf = disney_specular(m, g);
   } else {
     // bsdf.py:201-224 sample_clearcoat
-    float a2 = sqr(k.cc_alpha);
-    float cosTheta = sqrtf(fmaxf(1e-4f, (1.0f - powf(a2, 1.0f - ux)) / (1.0f - a2)));
-    float sinTheta = sqrtf(fmaxf(1e-4f, 1.0f - cosTheta * cosTheta));
+    float a2 = sqr(m.cc_alpha);
+    float cosTheta = fsqrt(fmaxf(1e-4f, fdiv(1.0f - __powf(a2, 1.0f - ux), 1.0f - a2)));
+    float sinTheta = fsqrt(fmaxf(1e-4f, 1.0f - cosTheta * cosTheta));
     float s, c;
-    sincosf(2.0f * VRT_PI * uy, &s, &c);
+    __sincosf(2.0f * VRT_PI * uy, &s, &c);
     f3 h = (sinTheta * c) * tang + (sinTheta * s) * bitang + cosTheta * n;
     if (dot(h, v) < 0.0f) h *= -1.0f;
     dir = reflect(-v, h);
     float ndh = fabsf(dot(n, h));
-    pdf = (GTR1(ndh, k.cc_alpha) * ndh / (4.0f * dot(v, h))) * k.cw;
+    pdf = fdiv(GTR1(m, ndh) * ndh, 4.0f * dot(v, h)) * m.cw;
     lobe = LOBE_CLEARC;
     Geo g = make_geo(v, n, dir, tang, bitang);
-    brdf = mk3(disney_clearcoat(m, k, g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
+    brdf = mk3(disney_clearcoat(m, g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
   }
   if (isbad(pdf)) pdf = 1.0f;
   return dir;

@@ -22,10 +22,30 @@ HD f3 mk3(float a) { return f3{a, a, a}; }
 HD f3 operator+(f3 a, f3 b) { return f3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 HD f3 operator-(f3 a, f3 b) { return f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
 HD f3 operator*(f3 a, f3 b) { return f3{a.x * b.x, a.y * b.y, a.z * b.z}; }
-HD f3 operator/(f3 a, f3 b) { return f3{a.x / b.x, a.y / b.y, a.z / b.z}; }
+HD f3 operator/(f3 a, f3 b) { return f3{__fdividef(a.x, b.x), __fdividef(a.y, b.y), __fdividef(a.z, b.z)}; }
 HD f3 operator*(f3 a, float s) { return f3{a.x * s, a.y * s, a.z * s}; }
 HD f3 operator*(float s, f3 a) { return f3{s * a.x, s * a.y, s * a.z}; }
-HD f3 operator/(f3 a, float s) { return f3{a.x / s, a.y / s, a.z / s}; }
+// Approximate (1-2 ulp, flush-to-zero) SFU ops for the shading code; never used by the traversal.
+HD float frcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+HD float fdiv(float a, float b) { return __fdividef(a, b); }
+HD float fsqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+HD float frsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+HD f3 operator/(f3 a, float s) {
+  float r = frcp(s);
+  return f3{a.x * r, a.y * r, a.z * r};
+}
 HD f3 operator-(f3 a) { return f3{-a.x, -a.y, -a.z}; }
 HD f3& operator+=(f3& a, f3 b) {
   a = a + b;
@@ -41,9 +61,9 @@ HD f3& operator*=(f3& a, float s) {
 }
 HD float dot(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 HD f3 cross(f3 a, f3 b) { return f3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-HD float length(f3 a) { return sqrtf(dot(a, a)); }
+HD float length(f3 a) { return fsqrt(dot(a, a)); }
 HD f3 normalize(f3 a) {
-  float inv = 1.0f / sqrtf(dot(a, a));
+  float inv = frsqrt(dot(a, a));
   return inv * a;
 }
 HD float clampf(float x, float lo, float hi) { return fmaxf(lo, fminf(hi, x)); }
@@ -95,13 +115,17 @@ HD float rnd(uint32_t key, uint32_t dim) {
   return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
-// Material row in device memory: 16 floats (4 x float4).
-//  [0] base rgb, subsurface   [1] metallic, specular, specular_tint, roughness
-//  [2] anisotropic, sheen, sheen_tint, clearcoat   [3] clearcoat_gloss, ior_minus_one, -, -
+// Material row in device memory: 20 floats (5 x float4), derived constants precomputed on the host
+// (vrt_api.cu pack_materials):
+//  [0] base rgb, subsurface           [1] metallic, specular, specular_tint, roughness
+//  [2] sheen, sheen_tint, clearcoat, cc_alpha (mix(0.1, 0.001, clearcoat_gloss), bsdf.py:113)
+//  [3] dw, sw, cw (lobe probabilities, bsdf.py:351-363), cc_norm = (a2-1)/(pi*log(a2)) (bsdf.py:116-117)
+//  [4] ax, ay (bsdf.py:92-95), 1/(pi*ax*ay), -
+#define MAT_ROW_F4 5
 struct Mat {
   f3 base_col;
-  float subsurface, metallic, specular, specular_tint, roughness, anisotropic, sheen, sheen_tint, clearcoat,
-      clearcoat_gloss;
+  float subsurface, metallic, specular, specular_tint, roughness, sheen, sheen_tint, clearcoat;
+  float cc_alpha, dw, sw, cw, cc_norm, ax, ay, inv_pi_axay;
 };
 
 struct Params {

@@ -16,7 +16,7 @@
 HD f3 firefly_filter(f3 v) { return clamp3(v, 0.0f, RADIANCE_CLAMP); }
 HD float power_heuristic(float a, float b) {  // pathtracer.py:349-353
   float a_sqr = a * a;
-  return a_sqr / fmaxf(a_sqr + b * b, 1e-4f);
+  return __fdividef(a_sqr, fmaxf(a_sqr + b * b, 1e-4f));
 }
 HD uint32_t encode_material(int mat_id, f3 albedo) {  // math_utils.py:231-236
   return (uint32_t)mat_id | ((uint32_t)(albedo.x * 255.0f) << 8) | ((uint32_t)(albedo.y * 255.0f) << 16) |
@@ -24,12 +24,12 @@ HD uint32_t encode_material(int mat_id, f3 albedo) {  // math_utils.py:231-236
 }
 HD bool bad3(f3 c) { return isbad(c.x) || isbad(c.y) || isbad(c.z) || c.x < 0.0f || c.y < 0.0f || c.z < 0.0f; }
 
-#define SMEM_MAT_WORDS 2048  // 128 materials x 16 floats
+#define SMEM_MAT_WORDS (128 * MAT_ROW_F4 * 4)  // 128 material rows x 20 floats
 
 // Stage the material table and (when it fits) the upper occupancy pyramid in shared memory.
 HD const uint32_t* stage_shared(const Params& P, uint32_t* smem, int upper_in_smem) {
   float4* s_mats = reinterpret_cast<float4*>(smem);
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_mats[i] = P.mats[i];
+  for (int i = threadIdx.x; i < 128 * MAT_ROW_F4; i += blockDim.x) s_mats[i] = P.mats[i];
   const uint32_t* upper = P.upper;
   if (upper_in_smem) {
     uint32_t* s_upper = smem + SMEM_MAT_WORDS;
@@ -79,8 +79,12 @@ __global__ void __launch_bounds__(128) k_primary(const __grid_constant__ Params 
 enum { ST_SEGMENT = 0, ST_SHADOW = 1 };
 enum { PIX_IDLE = -1, PIX_DONE = -2 };
 
+#ifndef VRT_PATH_MIN_BLOCKS
+#define VRT_PATH_MIN_BLOCKS 6  // resident CTAs per SM the register allocation is tuned for
+#endif
+
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, int upper_in_smem) {
+__global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem) {
   extern __shared__ uint32_t smem[];
   const uint32_t* upper = stage_shared(P, smem, upper_in_smem);
   const float4* s_mats = reinterpret_cast<const float4*>(smem);
@@ -240,13 +244,12 @@ __global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, 
       const uint32_t base = 8u * (uint32_t)depth;
       Mat m = load_mat(s_mats, s_mat);
       m.base_col = s_alb;
-      const MatK k = mat_constants(m);
       f3 tang, bitang;
       make_orthonormal_basis(s_n, tang, bitang);
       if (visible != 0.0f) {
         f3 bd, bs;
         float lpdf;
-        eval_and_pdf(m, k, s_view, s_n, light_dir, tang, bitang, bd, bs, lpdf);
+        eval_and_pdf(m, s_view, s_n, light_dir, tang, bitang, bd, bs, lpdf);
         const float mis = power_heuristic(light_pdf_axis, lpdf);
         f3 sky_T = mk3(1.0f);
         if (P.use_sky) {
@@ -268,13 +271,13 @@ __global__ void __launch_bounds__(128) k_path(const __grid_constant__ Params P, 
       f3 brdf;
       float pdf;
       int lobe;
-      const f3 nd = sample_disney(m, k, s_view, s_n, tang, bitang, rnd(key, base + 2), rnd(key, base + 3), rnd(key, base + 4), brdf, pdf, lobe);
+      const f3 nd = sample_disney(m, s_view, s_n, tang, bitang, rnd(key, base + 2), rnd(key, base + 3), rnd(key, base + 4), brdf, pdf, lobe);
       f3 bounce_weight = brdf * saturate(dot(nd, s_n));
       if (depth == 0) {
-        f_invpdf = 1.0f / pdf;
+        f_invpdf = frcp(pdf);
         f_lobe = lobe;
       } else {
-        bounce_weight = bounce_weight / pdf;
+        bounce_weight = bounce_weight * frcp(pdf);
         const float bsdf_sample_light_pdf = cone_sample_pdf(P.light_cos_max, dot(P.light_dir, nd));
         bounce_weight *= power_heuristic(pdf, visible * bsdf_sample_light_pdf);
       }

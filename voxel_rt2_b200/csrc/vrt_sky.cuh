@@ -4,13 +4,45 @@
 #pragma once
 #include "vrt_common.cuh"
 
+// Polynomial atan2 / acos (max abs error 1.7e-7 / 3.3e-7 rad = 1e-4 / 2e-4 sky texels at 3840^2;
+// coefficients: Chebyshev fits evaluated in float32, see tests/test_host.py::test_fast_trig_error).
+HD float fast_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = __fdividef(mn, mx);
+  const float z = a * a;
+  float r = -0.004668773151934147f;
+  r = r * z + 0.02416618913412094f;
+  r = r * z - 0.0593671016395092f;
+  r = r * z + 0.09906096756458282f;
+  r = r * z - 0.14016585052013397f;
+  r = r * z + 0.19969235360622406f;
+  r = r * z - 0.33331960439682007f;
+  r = r * z + 0.9999998807907104f;
+  r *= a;
+  if (ay > ax) r = 1.57079632679489662f - r;
+  if (x < 0.0f) r = VRT_PI - r;
+  return y < 0.0f ? -r : r;
+}
+HD float fast_acos(float x) {
+  const float a = fabsf(x);
+  float r = 0.002251368248835206f;
+  r = r * a - 0.011012386530637741f;
+  r = r * a + 0.02674933150410652f;
+  r = r * a - 0.048724401742219925f;
+  r = r * a + 0.08873733133077621f;
+  r = r * a - 0.21458369493484497f;
+  r = r * a + 1.5707961320877075f;
+  r *= fsqrt(fmaxf(1.0f - a, 0.0f));
+  return x < 0.0f ? VRT_PI - r : r;
+}
+
 HD f2 project_sky(f3 d, float fres) {
-  float il = 1.0f / sqrtf(d.x * d.x + d.z * d.z);
-  float px = il * d.x, py = il * d.z;
-  float azimuth = VRT_PI + atan2f(px, -py);
-  float elevation = VRT_PI * 0.5f - acosf(d.y);
-  float cx = azimuth / (VRT_PI * 2.0f);
-  float cy = 0.5f + 0.5f * signf(elevation) * sqrtf(2.0f / VRT_PI * fabsf(elevation));
+  // atan2 is scale invariant: the normalisation of d.xz (atmos.py:430) is not needed
+  float azimuth = VRT_PI + fast_atan2(d.x, -d.z);
+  float elevation = VRT_PI * 0.5f - fast_acos(d.y);
+  float cx = azimuth * (1.0f / (VRT_PI * 2.0f));
+  float cy = 0.5f + 0.5f * signf(elevation) * fsqrt(2.0f / VRT_PI * fabsf(elevation));
   return f2{cx * (1.0f - fres) + 0.5f * fres, cy * (1.0f - fres) + 0.5f * fres};
 }
 
