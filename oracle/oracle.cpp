@@ -19,6 +19,7 @@
 
 #include "../include/voxelrt.h"
 #include "obsdf.h"
+#include "orestir.h"
 #include "osky.h"
 #include "otrace.h"
 
@@ -39,6 +40,11 @@ struct Ctx {
   Counters counters;
   double last_ms = 0;
   int tile_rank = 0, tile_n = 1;
+  // ReSTIR mode buffers (pathtracer.py:109-125): one packed reservoir + G-buffer + the frame's
+  // diffuse / specular colour per pixel
+  std::vector<StorageReservoir> reservoirs;
+  std::vector<GBufferPx> gbuf;
+  std::vector<V3> col_d, col_s;
 };
 
 static const float RADIANCE_CLAMP = 300.0f;  // pathtracer.py:20
@@ -176,6 +182,341 @@ static void trace_path(const Ctx& c, int u, int v, uint32_t sample, Counters* cn
   specular += first_NEE_s;
   out.diffuse = diffuse;
   out.specular = specular;
+}
+
+// ------------------------------------------------------------------------------- ReSTIR mode
+static inline void decode_material(const Ctx& c, uint32_t enc, Mat& m, int& mat_id) {  // math_utils.py:238-247
+  mat_id = (int)(enc & 255u);
+  m = mat_at(c, mat_id);
+  m.base_col = V3{(float)((enc >> 8) & 255u) / 255.0f, (float)((enc >> 16) & 255u) / 255.0f, (float)((enc >> 24) & 255u) / 255.0f};
+}
+
+// pathtracer.py:355-632 with USE_RESTIR_PT = True: same walk as trace_path plus the reservoir /
+// G-buffer bookkeeping. Random dimension 40 is the input_sample draw (reservoir.py:71).
+static void trace_path_restir(const Ctx& c, int u, int v, uint32_t sample, Counters* cnt, Reservoir& res, GBufferPx& gb, V3& out_d,
+                              V3& out_s) {
+  const Scene& s = c.scene;
+  const uint32_t key = path_key((uint32_t)(v * s.W + u), sample, c.seed);
+  V3 d = get_cast_dir(s, (float)u, (float)v);
+  V3 pos = s.cam_pos;
+  V3 contrib{0, 0, 0}, throughput{1, 1, 1};
+  res = Reservoir();
+  V3 primary_normal{0, 0, 0}, primary_pos{0, 0, 0};
+  uint32_t primary_mat_info = 0;
+  V3 throughput_after_rc{1, 1, 1};
+  int first_bounce_lobe_id = 0, rc_bounce_lobe_id = 0;
+  float first_bounce_invpdf = 1.0f;
+  V3 first_NEE_d{0, 0, 0}, first_NEE_s{0, 0, 0}, first_bounce_dir{0, 0, 0}, first_light_sample_dir{0, 0, 0};
+  float first_light_sample_bsdf_pdf = 1.0f;
+  bool is_sky_ray = false;
+  if (cnt) cnt->paths++;
+
+  for (int depth = 0; depth < c.max_depth; depth++) {
+    const uint32_t base = 8u * (uint32_t)depth;
+    Hit h = next_hit(s, pos, d, kInf, false, cnt);
+    Mat hit_mat = mat_at(c, h.mat_id);
+    V3 hit_pos = pos + h.closest * d;
+    if (depth == 0) {
+      primary_normal = h.normal;
+      primary_pos = hit_pos;
+      primary_mat_info = encode_material(h.mat_id, h.albedo);
+    } else if (depth == 1) {
+      res.z.rc_pos = hit_pos;
+      res.z.rc_normal = h.normal;
+      res.z.rc_mat_info = encode_material(h.mat_id, h.albedo);
+      first_bounce_dir = d;
+    } else if (depth == 2) {
+      res.z.rc_incident_dir = d;
+    }
+    if (!h.hit_light && h.closest < kInf) {
+      if (cnt) cnt->vertices++;
+      V3 normal = h.normal;
+      pos = hit_pos + normal * kEps;
+      hit_mat.base_col = h.albedo;
+      V3 view = -d;
+      V3 tang, bitang;
+      make_orthonormal_basis(normal, tang, bitang);
+      float NEE_visible = 0.0f;
+      {
+        V3 light_dir = sample_cone_oriented(s.light_cos_max, s.light_dir, rnd(key, base + 0), rnd(key, base + 1));
+        float ndl = dot(light_dir, normal);
+        float light_sample_bsdf_pdf = pdf_disney(hit_mat, view, normal, light_dir, tang, bitang);
+        if (depth == 0) {
+          first_light_sample_bsdf_pdf = light_sample_bsdf_pdf;
+          first_light_sample_dir = light_dir;
+        }
+        if (ndl > 0.0f) {
+          Hit sh = next_hit(s, pos, light_dir, kInf, true, cnt);
+          if (sh.closest >= kInf) {
+            NEE_visible = 1.0f;
+            if (depth == 1) res.z.rc_NEE_dir = light_dir;
+            float mis = 1.0f;
+            if (depth > 0) mis = power_heuristic(cone_sample_pdf(s.light_cos_max, 1.0f), light_sample_bsdf_pdf);
+            V3 bd, bs;
+            disney_evaluate_split(hit_mat, view, normal, light_dir, tang, bitang, bd, bs);
+            V3 skyT{1, 1, 1};
+            if (s.use_physical_sky == 1) {
+              skyT = sample_skybox_transmittance(s.sky_trans, s.sky_res, light_dir);
+              if (cnt) cnt->N++;
+            }
+            V3 nee_d = mis * bd * skyT * s.light_weight * s.light_color * ndl;
+            V3 nee_s = mis * bs * skyT * s.light_weight * s.light_color * ndl;
+            if (depth == 0) {
+              first_NEE_d += firefly_filter(throughput * nee_d);
+              first_NEE_s += firefly_filter(throughput * nee_s);
+            } else {
+              contrib += firefly_filter(throughput * (nee_d + nee_s));
+            }
+            if (depth >= 2) res.z.rc_incident_L += throughput_after_rc * (nee_d + nee_s);
+          }
+        }
+      }
+      V3 bsdf;
+      float pdf;
+      int lobe_id;
+      d = sample_disney(hit_mat, view, normal, tang, bitang, rnd(key, base + 2), rnd(key, base + 3), rnd(key, base + 4), bsdf, pdf, lobe_id);
+      V3 bounce_weight = bsdf * saturate(dot(d, normal));
+      if (depth == 0) {
+        first_bounce_invpdf = 1.0f / pdf;
+        first_bounce_lobe_id = lobe_id;
+      } else {
+        bounce_weight = bounce_weight / pdf;
+        float bsdf_sample_light_pdf = cone_sample_pdf(s.light_cos_max, dot(s.light_dir, d));
+        bounce_weight *= power_heuristic(pdf, NEE_visible * bsdf_sample_light_pdf);
+        if (depth == 1) rc_bounce_lobe_id = lobe_id;
+        if (depth >= 2) throughput_after_rc *= bounce_weight;
+      }
+      throughput *= bounce_weight;
+    } else {
+      if (h.closest == kInf) {
+        float hit_sun = dot(s.light_dir, d) >= s.light_cos_max ? 1.0f : 0.0f;
+        V3 sky_scattering = s.background;
+        V3 sky_T{1, 1, 1};
+        if (s.use_physical_sky == 1) {
+          sample_skybox(s.sky_scatter, s.sky_trans, s.sky_res, d, rnd(key, base + 5), rnd(key, base + 6), rnd(key, base + 7), sky_scattering,
+                        sky_T);
+          if (cnt) cnt->E++;
+        }
+        V3 sky_emission = firefly_filter(sky_scattering + sky_T * s.light_weight * s.light_color * hit_sun);
+        contrib += throughput * sky_emission;
+        if (depth == 0) {
+          primary_pos = V3{0, 0, 0};
+          is_sky_ray = true;
+        } else if (depth == 1) {
+          res.z.rc_pos = d;
+          res.z.rc_incident_L = sky_emission;
+        }
+        if (depth >= 2) res.z.rc_incident_L += firefly_filter(throughput_after_rc * sky_emission);
+      } else {
+        if (depth > 0) contrib += throughput * h.albedo;
+        if (depth >= 2) res.z.rc_incident_L += firefly_filter(throughput_after_rc * h.albedo);
+      }
+      break;
+    }
+  }
+  // G-buffer (:535-540)
+  gb.position = primary_pos;
+  gb.mat_info = primary_mat_info;
+  gb.sky = is_sky_ray ? 1 : 0;
+  gb.n_oct[0] = gb.n_oct[1] = 0.0f;
+  if (!is_sky_ray) encode_unit_vector_3x16(primary_normal, gb.n_oct[0], gb.n_oct[1]);
+  // reservoir (:548-607)
+  res.z.F = contrib;
+  res.z.lobes = rc_bounce_lobe_id * 10 + first_bounce_lobe_id;
+  res.M = 1.0f;
+  res.update_cached_jacobian_term(primary_pos);
+  bool chose_NEE = false;
+  if (!is_sky_ray) {
+    float bsdf_sample_bsdf_pdf = 1.0f / first_bounce_invpdf;
+    float bsdf_sample_light_pdf = cone_sample_pdf(s.light_cos_max, dot(s.light_dir, first_bounce_dir));
+    if (is_vec_zero(first_NEE_d + first_NEE_s)) bsdf_sample_light_pdf = 0.0f;
+    float bsdf_sample_mis_weight = power_heuristic(bsdf_sample_bsdf_pdf, bsdf_sample_light_pdf);
+    float light_sample_mis_weight = power_heuristic(cone_sample_pdf(s.light_cos_max, 1.0f), first_light_sample_bsdf_pdf);
+    float p_hat = luminance(res.z.F);
+    res.weight = bsdf_sample_mis_weight * p_hat * first_bounce_invpdf;
+    float light_sample_weight = light_sample_mis_weight * luminance(first_NEE_d + first_NEE_s);
+    V3 skyT = s.use_physical_sky == 1 ? sample_skybox_transmittance(s.sky_trans, s.sky_res, first_light_sample_dir) : V3{1, 1, 1};
+    Sample ls;
+    ls.F = first_NEE_d + first_NEE_s;
+    ls.rc_pos = first_light_sample_dir;
+    ls.rc_incident_L = skyT * s.light_weight * s.light_color;
+    ls.cached_jacobian_term = 1.0f;
+    ls.lobes = LOBE_ALL * 10 + LOBE_ALL;
+    chose_NEE = res.input_sample(light_sample_weight, ls, rnd(key, 40));
+    res.finalize_without_M();
+  } else {
+    res.weight = 1.0f;
+  }
+  out_d = V3{0, 0, 0};
+  out_s = V3{0, 0, 0};
+  if (!chose_NEE) {
+    if (first_bounce_lobe_id == LOBE_DIFFUSE) out_d += res.z.F;
+    if (first_bounce_lobe_id == LOBE_SPEC_REFL) out_s += res.z.F;
+  } else {
+    out_d += first_NEE_d;
+    out_s += first_NEE_s;
+  }
+}
+
+// pathtracer.py:672-812 shift(): integrand of src_reservoir's sample reconnected at dst, and the
+// Jacobian of the shift.
+static void shift_sample(const Ctx& c, V3 dst_pos, V3 dst_normal, const Mat& dst_material, V3 src_pos, const Reservoir& src, V3& diffuse,
+                         V3& specular, float& jacobian_out) {
+  const Scene& s = c.scene;
+  const Sample& z = src.z;
+  const bool rc_is_escape_vertex = is_vec_zero(z.rc_normal);
+  const bool rc_is_last_vertex = is_vec_zero(z.rc_incident_dir);
+  const bool rc_is_NEE_visible = !is_vec_zero(z.rc_NEE_dir);
+  V3 dir_to_rc_vertex = rc_is_escape_vertex ? z.rc_pos : normalize(z.rc_pos - dst_pos);
+  V3 src_dir_to_rc_vertex = rc_is_escape_vertex ? z.rc_pos : normalize(z.rc_pos - src_pos);
+  float passed_checks = 1.0f;
+  if (dot(dst_normal, dir_to_rc_vertex) < 1e-5f || (!rc_is_escape_vertex && dot(z.rc_normal, -dir_to_rc_vertex) < 1e-5f)) passed_checks = 0.0f;
+  V3 rc_tang, rc_bitang;
+  make_orthonormal_basis(z.rc_normal, rc_tang, rc_bitang);
+  Mat rc_mat;
+  int rc_mat_id;
+  decode_material(c, z.rc_mat_info, rc_mat, rc_mat_id);
+  V3 rc_brdf{0, 0, 0};
+  float dst_rc_pdf = 1.0f;
+  if (!rc_is_last_vertex && !rc_is_escape_vertex) {
+    rc_brdf = disney_evaluate_lobewise(rc_mat, -dir_to_rc_vertex, z.rc_normal, z.rc_incident_dir, rc_tang, rc_bitang, z.lobes / 10);
+    rc_brdf *= saturate(dot(z.rc_normal, z.rc_incident_dir));
+    dst_rc_pdf = pdf_disney_lobewise(rc_mat, -dir_to_rc_vertex, z.rc_normal, z.rc_incident_dir, rc_tang, rc_bitang, z.lobes / 10);
+  }
+  (void)src_dir_to_rc_vertex;  // src_rc_pdf (:707-713) only feeds commented-out Jacobian terms
+  V3 rc_nee_brdf{0, 0, 0};
+  if (rc_is_NEE_visible) {
+    rc_nee_brdf = disney_evaluate(rc_mat, -dir_to_rc_vertex, z.rc_normal, z.rc_NEE_dir, rc_tang, rc_bitang);
+    rc_nee_brdf *= saturate(dot(z.rc_normal, z.rc_NEE_dir));
+  }
+  V3 dst_tang, dst_bitang;
+  make_orthonormal_basis(dst_normal, dst_tang, dst_bitang);
+  V3 view = normalize(s.cam_pos - dst_pos);
+  V3 primary_brdf_d, primary_brdf_s;
+  disney_evaluate_lobewise_split(dst_material, view, dst_normal, dir_to_rc_vertex, dst_tang, dst_bitang, z.lobes % 10, primary_brdf_d,
+                                 primary_brdf_s);
+  float cosd = saturate(dot(dst_normal, dir_to_rc_vertex));
+  primary_brdf_d *= cosd;
+  primary_brdf_s *= cosd;
+  V3 contrib{0, 0, 0};
+  if (!rc_is_escape_vertex && !rc_is_last_vertex) {
+    float rc_bsdf_sample_light_pdf = cone_sample_pdf(s.light_cos_max, dot(s.light_dir, z.rc_incident_dir));
+    float rc_bsdf_mis_weight = power_heuristic(dst_rc_pdf, rc_bsdf_sample_light_pdf * (rc_is_NEE_visible ? 1.0f : 0.0f));
+    contrib += firefly_filter(rc_bsdf_mis_weight * rc_brdf / dst_rc_pdf * z.rc_incident_L);
+  }
+  if (rc_is_escape_vertex) contrib += firefly_filter(z.rc_incident_L);
+  if (rc_is_NEE_visible && !rc_is_escape_vertex) {
+    float rc_light_sample_bsdf_pdf = pdf_disney(rc_mat, -dir_to_rc_vertex, z.rc_normal, z.rc_NEE_dir, rc_tang, rc_bitang);
+    float rc_light_sample_mis_weight = power_heuristic(cone_sample_pdf(s.light_cos_max, 1.0f), rc_light_sample_bsdf_pdf);
+    V3 skyT = s.use_physical_sky == 1 ? sample_skybox_transmittance(s.sky_trans, s.sky_res, z.rc_NEE_dir) : V3{1, 1, 1};
+    contrib += firefly_filter(rc_light_sample_mis_weight * rc_nee_brdf * skyT * s.light_weight * s.light_color);
+  }
+  if (rc_mat_id == 2) contrib += rc_mat.base_col;
+  diffuse = primary_brdf_d * contrib;
+  specular = primary_brdf_s * contrib;
+  float jacobian = 1.0f;
+  if (!rc_is_escape_vertex) {
+    jacobian = z.cached_jacobian_term;
+    V3 dir_y1_to_x2 = z.rc_pos - dst_pos;
+    jacobian *= std::fabs(dot(normalize(dir_y1_to_x2), z.rc_normal)) / dot(dir_y1_to_x2, dir_y1_to_x2);
+  }
+  if (jacobian < 0.0f || isbad(jacobian)) jacobian = 0.0f;  // (:799-803; the nested 11x test never fires)
+  jacobian_out = jacobian * passed_checks;
+}
+
+// pathtracer.py:815-989 spatial_GRIS(pass_id = 0, max_radius = 24, max_taps = 32, pass_total = 1)
+// for one pixel. Random dimensions: 65 radius shift, 66+i merge draw of tap i, 98 canonical merge.
+static void spatial_gris_pixel(const Ctx& c, int u, int v, uint32_t frame, V3& out_d, V3& out_s) {
+  const Scene& s = c.scene;
+  const int W = s.W, H = s.H;
+  const size_t pi = (size_t)v * W + u;
+  const float max_radius = 24.0f;
+  const int max_taps = 32;
+  const uint32_t key = path_key((uint32_t)pi, frame, c.seed);
+  Reservoir center = decode_reservoir(c.reservoirs[pi]);
+  const GBufferPx& g = c.gbuf[pi];
+  if (g.sky) {  // :854-856
+    out_d = center.z.F;
+    out_s = V3{0, 0, 0};
+    return;
+  }
+  uint32_t seed = hash3((uint32_t)u >> 3, (uint32_t)v >> 3, frame * 2u + 0u);
+  float angle_shift = (float)((seed & 0x007FFFFFu) | 0x3F800000u) / 4294967295.0f * kPi;  // numeric u32 -> f32 cast (:832)
+  float radius_shift = rnd(key, 65);
+  Reservoir out;
+  V3 center_x1 = g.position;
+  float center_dist = length(center_x1 - s.cam_pos);
+  V3 center_n1 = decode_unit_vector_3x16(g.n_oct[0], g.n_oct[1]);
+  Mat center_mat;
+  int center_mat_id;
+  decode_material(c, g.mat_info, center_mat, center_mat_id);
+  int valid_samples = 0;
+  float canonical_mis_weight = 1.0f;
+  V3 chosen_F_d{0, 0, 0}, chosen_F_s{0, 0, 0};
+  for (int i = 0; i < max_taps; i++) {
+    const float golden_angle = 2.399963229728f;
+    float angle = ((float)i + angle_shift) * golden_angle;
+    float offset_radius = std::sqrt(((float)i + radius_shift) / (float)max_taps) * max_radius;
+    int ox = (int)(std::cos(angle) * offset_radius), oy = (int)(std::sin(angle) * offset_radius);
+    if (ox == 0 && oy == 0) continue;
+    int tu = u + ox, tv = v + oy;
+    if (tu < 0 || tv < 0 || tu >= W || tv >= H) continue;
+    const size_t ti = (size_t)tv * W + tu;
+    const GBufferPx& ng = c.gbuf[ti];
+    if (ng.sky) continue;
+    V3 neighbour_n1 = decode_unit_vector_3x16(ng.n_oct[0], ng.n_oct[1]);
+    V3 neighbour_x1 = ng.position;
+    float neighbour_dist = length(neighbour_x1 - s.cam_pos);
+    Reservoir nb = decode_reservoir(c.reservoirs[ti]);
+    if (std::fabs(neighbour_dist - center_dist) > 0.1f * center_dist || dot(center_n1, neighbour_n1) < 0.5f) continue;
+    Mat neighbour_mat;
+    int neighbour_mat_id;
+    decode_material(c, ng.mat_info, neighbour_mat, neighbour_mat_id);
+    V3 c_d, c_s, s_d, s_s;
+    float c_jacobian, jacobian;
+    shift_sample(c, neighbour_x1, neighbour_n1, neighbour_mat, center_x1, center, c_d, c_s, c_jacobian);
+    shift_sample(c, center_x1, center_n1, center_mat, neighbour_x1, nb, s_d, s_s, jacobian);
+    float center_p_hat = luminance(c_d + c_s) * c_jacobian;
+    float canonical_weight = center_p_hat * nb.M;
+    canonical_weight /= center_p_hat * nb.M + luminance(center.z.F) * center.M / (float)max_taps;
+    canonical_mis_weight += 1.0f - canonical_weight;
+    float p_hat = luminance(s_d + s_s);
+    float p_hat_from_neighbour = p_hat / jacobian;
+    float neighbour_mis_weight = p_hat_from_neighbour * nb.M;
+    neighbour_mis_weight /= p_hat_from_neighbour * nb.M + p_hat * center.M / (float)max_taps;
+    if (isbad(neighbour_mis_weight)) neighbour_mis_weight = 0.0f;
+    nb.z.F = s_d + s_s;
+    bool selected = out.merge(nb, nb.weight * p_hat * jacobian * neighbour_mis_weight, rnd(key, 66 + (uint32_t)i));
+    if (selected) {
+      chosen_F_d = s_d;
+      chosen_F_s = s_s;
+    }
+    valid_samples += 1;
+  }
+  // visibility of the resampled reconnection (:957-965)
+  bool force_add_canonical = false;
+  if (out.weight > 0.0f) {
+    const bool esc = is_vec_zero(out.z.rc_normal);
+    V3 dir_to_rc_vertex = esc ? out.z.rc_pos : normalize(out.z.rc_pos - center_x1);
+    Hit sh = next_hit(s, center_x1 + center_n1 * 0.003f * center_dist, dir_to_rc_vertex, kInf, true, nullptr);
+    float actual_dist = esc ? kInf : length(center_x1 - out.z.rc_pos);
+    if (sh.closest < kInf && std::fabs(sh.closest - actual_dist) > 0.1f * actual_dist) {
+      out.weight = 0.0f;
+      force_add_canonical = true;
+    }
+  }
+  float center_p_hat = luminance(center.z.F);
+  bool selected = out.merge(center, center.weight * center_p_hat * canonical_mis_weight, rnd(key, 98), force_add_canonical);
+  if (selected) {
+    chosen_F_d = c.col_d[pi];
+    chosen_F_s = c.col_s[pi];
+  }
+  out.finalize_without_M();
+  out.weight /= (float)(valid_samples + 1);
+  V3 emission = center_mat_id == 2 ? center_mat.base_col : V3{0, 0, 0};
+  float Wc = clampf(out.weight, 0.0f, 50.0f);
+  out_d = chosen_F_d * Wc + emission;
+  out_s = chosen_F_s * Wc;
 }
 
 static inline bool bad3(V3 c) {  // pathtracer.py:1068-1075
@@ -439,6 +780,64 @@ void orc_accumulate(void* p, int first_sample, int n_samples, int stride, int st
   }
   c->last_ms = (omp_get_wtime() - t0) * 1e3;
 }
+// accumulate() with USE_RESTIR_PT (pathtracer.py:1310-1319): render -> spatial_GRIS -> static
+// camera temporal filters, one frame per sample index.
+void orc_accumulate_restir(void* p, int first_sample, int n_samples, int stride, int n_threads) {
+  Ctx* c = (Ctx*)p;
+  Scene& s = c->scene;
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+  double t0 = omp_get_wtime();
+  const size_t npx = (size_t)s.W * s.H;
+  c->reservoirs.resize(npx);
+  c->gbuf.resize(npx);
+  c->col_d.resize(npx);
+  c->col_s.resize(npx);
+  const float max_accum = 999999999.0f;
+  std::vector<V3> fin_d(npx), fin_s(npx);
+  for (int k = 0; k < n_samples; k++) {
+    uint32_t sample = (uint32_t)(first_sample + k * stride);
+    set_jitter(*c, sample);
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int v = 0; v < s.H; v++)
+      for (int u = 0; u < s.W; u++) {
+        size_t i = (size_t)v * s.W + u;
+        Reservoir r;
+        trace_path_restir(*c, u, v, sample, nullptr, r, c->gbuf[i], c->col_d[i], c->col_s[i]);
+        c->reservoirs[i] = encode_reservoir(r);
+      }
+#pragma omp parallel for schedule(dynamic, 2)
+    for (int v = 0; v < s.H; v++)
+      for (int u = 0; u < s.W; u++) spatial_gris_pixel(*c, u, v, sample, fin_d[(size_t)v * s.W + u], fin_s[(size_t)v * s.W + u]);
+    for (size_t i = 0; i < npx; i++) {
+      V3 dd = fin_d[i], ss = fin_s[i];
+      if (bad3(dd)) dd = V3{0, 0, 0};
+      if (bad3(ss)) ss = V3{0, 0, 0};
+      float* hd = &c->hist_d[i * 4];
+      float* hs = &c->hist_s[i * 4];
+      hd[3] = fminf_(hd[3] + 1.0f, max_accum);
+      float wd = 1.0f / hd[3];
+      hd[0] = mixf(hd[0], dd.x, wd), hd[1] = mixf(hd[1], dd.y, wd), hd[2] = mixf(hd[2], dd.z, wd);
+      hs[3] = fminf_(hs[3] + 1.0f, max_accum);
+      float ws = 1.0f / hs[3];
+      hs[0] = mixf(hs[0], ss.x, ws), hs[1] = mixf(hs[1], ss.y, ws), hs[2] = mixf(hs[2], ss.z, ws);
+    }
+  }
+  c->last_ms = (omp_get_wtime() - t0) * 1e3;
+}
+// packed reservoirs / G-buffer of the last ReSTIR frame (for parity tests): 56 B and 24 B per pixel
+void orc_get_reservoirs(void* p, void* out) {
+  Ctx* c = (Ctx*)p;
+  std::memcpy(out, c->reservoirs.data(), c->reservoirs.size() * sizeof(StorageReservoir));
+}
+// octahedral / arbitrary-bit packing probes
+void orc_oct_round_trip(int n, const float* v, float* enc, float* dec) {
+  for (int i = 0; i < n; i++) {
+    encode_unit_vector_3x16(V3{v[3 * i], v[3 * i + 1], v[3 * i + 2]}, enc[2 * i], enc[2 * i + 1]);
+    V3 d = decode_unit_vector_3x16(enc[2 * i], enc[2 * i + 1]);
+    dec[3 * i] = d.x, dec[3 * i + 1] = d.y, dec[3 * i + 2] = d.z;
+  }
+}
+uint32_t orc_hash3(uint32_t x, uint32_t y, uint32_t z) { return hash3(x, y, z); }
 double orc_last_ms(void* p) { return ((Ctx*)p)->last_ms; }
 void orc_reset(void* p) {
   Ctx* c = (Ctx*)p;

@@ -25,14 +25,19 @@ HD uint32_t encode_material(int mat_id, f3 albedo) {  // math_utils.py:231-236
 HD bool bad3(f3 c) { return isbad(c.x) || isbad(c.y) || isbad(c.z) || c.x < 0.0f || c.y < 0.0f || c.z < 0.0f; }
 
 #define SMEM_MAT_WORDS (128 * MAT_ROW_F4 * 4)  // 128 material rows x 20 floats
+#define SMEM_UNORM_WORDS 256                   // k / 255.0f for the RGBA8 colour decode
+#define SMEM_FIXED_WORDS (SMEM_MAT_WORDS + SMEM_UNORM_WORDS)
 
-// Stage the material table and (when it fits) the upper occupancy pyramid in shared memory.
+// Stage the material table, the UNORM8 decode table and (when it fits) the upper occupancy
+// pyramid in shared memory.
 HD const uint32_t* stage_shared(const Params& P, uint32_t* smem, int upper_in_smem) {
   float4* s_mats = reinterpret_cast<float4*>(smem);
   for (int i = threadIdx.x; i < 128 * MAT_ROW_F4; i += blockDim.x) s_mats[i] = P.mats[i];
+  float* s_unorm = reinterpret_cast<float*>(smem + SMEM_MAT_WORDS);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = xdiv((float)i, 255.0f);
   const uint32_t* upper = P.upper;
   if (upper_in_smem) {
-    uint32_t* s_upper = smem + SMEM_MAT_WORDS;
+    uint32_t* s_upper = smem + SMEM_FIXED_WORDS;
     for (int i = threadIdx.x; i < P.upper_words; i += blockDim.x) s_upper[i] = P.upper[i];
     upper = s_upper;
   }
@@ -44,12 +49,13 @@ HD const uint32_t* stage_shared(const Params& P, uint32_t* smem, int upper_in_sm
 __global__ void __launch_bounds__(128) k_primary(const __grid_constant__ Params P, vrt_hit* __restrict__ out, int upper_in_smem) {
   extern __shared__ uint32_t smem[];
   const uint32_t* upper = stage_shared(P, smem, upper_in_smem);
+  const float* unorm8 = reinterpret_cast<const float*>(smem + SMEM_MAT_WORDS);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= P.n_tiles) return;
   const int tile = P.tile_rank + P.tile_n * warp;
   const int u = (tile % P.tiles_x) * 8 + (lane & 7), v = (tile / P.tiles_x) * 4 + (lane >> 3);
   f3 d = get_cast_dir(P, (float)u, (float)v, 0.0f, 0.0f);
-  Hit h = next_hit<false>(P, upper, P.cam_pos, d, false, nullptr, nullptr);
+  Hit h = next_hit<false>(P, upper, unorm8, P.cam_pos, d, false, nullptr, nullptr);
   uint32_t shadow = 3u;
   const int kind = h.closest < VRT_INF ? h.kind : 0;
   if (!h.hit_light && h.closest < VRT_INF) {
@@ -58,7 +64,7 @@ __global__ void __launch_bounds__(128) k_primary(const __grid_constant__ Params 
            xadd(xadd(P.cam_pos.z, xmul(h.closest, d.z)), xmul(n.z, VRT_EPS))};
     float ndl = xdot(P.light_dir, n);
     if (ndl > 0.0f) {
-      Hit sh = next_hit<false>(P, upper, pos, P.light_dir, true, nullptr, nullptr);
+      Hit sh = next_hit<false>(P, upper, unorm8, pos, P.light_dir, true, nullptr, nullptr);
       shadow = sh.closest >= VRT_INF ? 0u : 1u;
     } else {
       shadow = 2u;
@@ -80,7 +86,7 @@ enum { ST_SEGMENT = 0, ST_SHADOW = 1 };
 enum { PIX_IDLE = -1, PIX_DONE = -2 };
 
 #ifndef VRT_PATH_MIN_BLOCKS
-#define VRT_PATH_MIN_BLOCKS 6  // resident CTAs per SM the register allocation is tuned for
+#define VRT_PATH_MIN_BLOCKS 5  // resident CTAs per SM the register allocation is tuned for
 #endif
 
 template <bool STATS>
@@ -88,6 +94,7 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
   extern __shared__ uint32_t smem[];
   const uint32_t* upper = stage_shared(P, smem, upper_in_smem);
   const float4* s_mats = reinterpret_cast<const float4*>(smem);
+  const float* unorm8 = reinterpret_cast<const float*>(smem + SMEM_MAT_WORDS);
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
       finished = false;
       f3 emission = mk3(0.0f);
       if ((pm_info & 255u) == 2u)
-        emission = f3{(float)((pm_info >> 8) & 255u) / 255.0f, (float)((pm_info >> 16) & 255u) / 255.0f, (float)((pm_info >> 24) & 255u) / 255.0f};
+        emission = f3{unorm8[(pm_info >> 8) & 255u], unorm8[(pm_info >> 16) & 255u], unorm8[(pm_info >> 24) & 255u]};
       f3 diffuse = fnee_d, specular = fnee_s;
       if (f_lobe == LOBE_DIFFUSE) diffuse += contrib * f_invpdf + emission;
       if (f_lobe == LOBE_SPEC_REFL) specular += contrib * f_invpdf;
@@ -136,8 +143,7 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
       if (s_i < P.n_samples) {
         restart = true;
       } else {
-        const int tile = P.tile_rank + P.tile_n * (pix >> 5);
-        const int u = (tile % P.tiles_x) * 8 + (pix & 7), v = (tile / P.tiles_x) * 4 + ((pix >> 3) & 3);
+        const int u = pix & 0xffff, v = pix >> 16;
         float4* dst = P.accum + (size_t)v * P.W + u;
         float4 a = *dst;
         a.x += acc.x, a.y += acc.y, a.z += acc.z, a.w += (float)P.n_samples;
@@ -162,7 +168,11 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
       }
       const int rank = __popc(need & lt_mask);
       if (pix == PIX_IDLE && rank < chunk_rem) {
-        pix = chunk_base + (32 - chunk_rem) + rank;
+        // pix = u | v << 16 of the pixel this lane now owns (one integer division per pixel)
+        const int item = chunk_base + (32 - chunk_rem) + rank;
+        const int tile = P.tile_rank + P.tile_n * (item >> 5);
+        const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
+        pix = (tx * 8 + (item & 7)) | ((ty * 4 + ((item >> 3) & 3)) << 16);
         s_i = 0;
         acc = mk3(0.0f);
         restart = true;
@@ -172,8 +182,7 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
     // ---- (1b) start the next path (new pixel or next sample of the same pixel), one site
     if (restart) {
       restart = false;
-      const int tile = P.tile_rank + P.tile_n * (pix >> 5);
-      const int u = (tile % P.tiles_x) * 8 + (pix & 7), v = (tile / P.tiles_x) * 4 + ((pix >> 3) & 3);
+      const int u = pix & 0xffff, v = pix >> 16;
       const uint32_t sample = (uint32_t)(P.first_sample + s_i * P.stride);
       key = path_key((uint32_t)(v * P.W + u), sample, P.seed);
       const float2 j = P.jitter[s_i];
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
     // ---- (2) trace the lane's current ray (path segment or sun shadow ray)
     Hit h;
     h.closest = VRT_INF, h.hit_light = 0, h.mat_id = 0, h.kind = 0, h.nx = h.ny = h.nz = 0.0f, h.albedo = mk3(1.0f);
-    if (active) h = next_hit<STATS>(P, upper, pos, d, state == ST_SHADOW, &tc, &c_hits);
+    if (active) h = next_hit<STATS>(P, upper, unorm8, pos, d, state == ST_SHADOW, &tc, &c_hits);
 
     // ---- (3) classify
     bool do_shade = false;
@@ -339,9 +348,9 @@ __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accu
 
 // -------------------------------------------------------------------------------- launchers
 static size_t smem_bytes(const Params& P, int* upper_in_smem) {
-  size_t need = (size_t)SMEM_MAT_WORDS * 4 + (size_t)P.upper_words * 4;
+  size_t need = (size_t)SMEM_FIXED_WORDS * 4 + (size_t)P.upper_words * 4;
   *upper_in_smem = need <= 48 * 1024 ? 1 : 0;
-  return *upper_in_smem ? need : (size_t)SMEM_MAT_WORDS * 4;
+  return *upper_in_smem ? need : (size_t)SMEM_FIXED_WORDS * 4;
 }
 
 cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st) {

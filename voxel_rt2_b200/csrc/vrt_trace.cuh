@@ -43,7 +43,9 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
   const float Rf = (float)P.R;
   if (STATS) tc->rays++;
 
-  // ray_aabb_intersection against [0,R]^3 (axes with d == 0 are skipped, as in the reference)
+  // ray_aabb_intersection against [0,R]^3 (axes with d == 0 are skipped, as in the reference).
+  // (Skipping the three entry-side divisions for origins inside the box is exact but was measured
+  // 6 % slower: primary and secondary rays share warps, so both variants execute.)
   float near_int = -VRT_INF, far_int = VRT_INF;
   {
     const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
@@ -67,7 +69,7 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
   int px = (int)clampf(floorf(ipx), 0.0f, Rf - 1.0f);
   int py = (int)clampf(floorf(ipy), 0.0f, Rf - 1.0f);
   int pz = (int)clampf(floorf(ipz), 0.0f, Rf - 1.0f);
-  const float ivx = xdiv(1.0f, fabsf(d.x)), ivy = xdiv(1.0f, fabsf(d.y)), ivz = xdiv(1.0f, fabsf(d.z));
+  const float ivx = __frcp_rn(fabsf(d.x)), ivy = __frcp_rn(fabsf(d.y)), ivz = __frcp_rn(fabsf(d.z));  // == 1.0f / |d|, correctly rounded
   const float sgx = signf(d.x), sgy = signf(d.y), sgz = signf(d.z);
   int lod = 0;
   const float far = xsub(fminf(VRT_INF, far_int), VRT_EPS);
@@ -184,8 +186,8 @@ struct Hit {
 // `shadow` is a run-time flag so that segment rays and shadow rays of different lanes share one
 // instance of the traversal loop (the path kernel traces both kinds in the same iteration).
 template <bool STATS>
-HD Hit next_hit(const Params& P, const uint32_t* __restrict__ upper, f3 pos, f3 d, const bool SHADOW, TraceCounters* tc,
-                uint32_t* n_hits) {
+HD Hit next_hit(const Params& P, const uint32_t* __restrict__ upper, const float* __restrict__ unorm8, f3 pos, f3 d, const bool SHADOW,
+                TraceCounters* tc, uint32_t* n_hits) {
   Hit h;
   h.closest = VRT_INF;
   h.nx = h.ny = h.nz = 0.0f;
@@ -237,7 +239,7 @@ HD Hit next_hit(const Params& P, const uint32_t* __restrict__ upper, f3 pos, f3 
       if ((unsigned)r.cx < (unsigned)P.R && (unsigned)r.cy < (unsigned)P.R && (unsigned)r.cz < (unsigned)P.R) {
         int b = ((r.cz >> 2) * P.brick_res + (r.cy >> 2)) * P.brick_res + (r.cx >> 2);
         uint32_t c = __ldg(P.color + (size_t)b * 64 + ((r.cz & 3) * 16 + (r.cy & 3) * 4 + (r.cx & 3)));
-        col = f3{xdiv((float)(c & 255u), 255.0f), xdiv((float)((c >> 8) & 255u), 255.0f), xdiv((float)((c >> 16) & 255u), 255.0f)};
+        col = f3{unorm8[c & 255u], unorm8[(c >> 8) & 255u], unorm8[(c >> 16) & 255u]};  // k / 255.0f, correctly rounded
         mat = (int)(c >> 24);
         if (STATS) (*n_hits)++;
       }
