@@ -69,6 +69,7 @@ typedef struct vrt_stats {
   float last_resolve_ms;  /* device time of the last tonemap pass */
   float sky_precompute_ms;
   uint32_t kernel_launches; /* kernels launched by the last vrt_accumulate */
+  float last_gris_ms;       /* device time of the spatial resampling kernel(s), ReSTIR mode */
 } vrt_stats;
 
 /* Renderer.__init__ (pathtracer.py:28-136) */
@@ -122,6 +123,15 @@ int vrt_trace_primary(vrt_ctx* ctx, vrt_hit* out);
 /* Renderer.accumulate (pathtracer.py:1310-1319) for sample indices first, first+stride, ...
  * (n_samples of them). stats != 0 also fills the counters. */
 int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_t stride, int32_t stats);
+
+/* Renderer.accumulate with USE_RESTIR_PT = True (pathtracer.py:15,1310-1319): per frame, render
+ * writes one packed reservoir + G-buffer record per pixel (pathtracer.py:535-607) and
+ * spatial_GRIS(0, 24.0, 32, 1) (pathtracer.py:815-989) resamples 32 neighbours; the frame is then
+ * accumulated like a path-traced one. n_frames frames with sample indices first, first+stride... */
+int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, int32_t stride);
+/* Packed reservoirs of the last ReSTIR frame: 56 bytes per pixel, row-major (reservoir.py:8-19
+ * field order; byte 55 carries the escape / last-vertex / NEE-visible flags). */
+int vrt_get_reservoirs(vrt_ctx* ctx, void* out56_per_pixel);
 
 /* Only pixels in 8x4 tiles with tile_id % n == rank are rendered (tile sharding). Default 0,1. */
 int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n);

@@ -54,6 +54,11 @@ def load():
     lib.orc_set_tile_shard.argtypes = [P, C.c_int, C.c_int]
     lib.orc_trace_primary.argtypes = [P, P]
     lib.orc_accumulate.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.orc_accumulate_restir.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.orc_get_reservoirs.argtypes = [P, P]
+    lib.orc_oct_round_trip.argtypes = [C.c_int, fp, fp, fp]
+    lib.orc_hash3.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.orc_hash3.restype = C.c_uint32
     lib.orc_last_ms.argtypes = [P]
     lib.orc_last_ms.restype = C.c_double
     lib.orc_reset.argtypes = [P]
@@ -235,6 +240,18 @@ class OracleRenderer:
         first = self.sample_offset + self.current_spp * self.sample_stride
         self._lib.orc_accumulate(self._h, first, int(spp), self.sample_stride, 1 if stats else 0, int(self.n_threads))
         self.current_spp += int(spp)
+
+    def accumulate_restir(self, frames=1):
+        """accumulate() with USE_RESTIR_PT = True (pathtracer.py:1310-1319): render + spatial_GRIS per frame."""
+        self._sync_camera()
+        first = self.sample_offset + self.current_spp * self.sample_stride
+        self._lib.orc_accumulate_restir(self._h, first, int(frames), self.sample_stride, int(self.n_threads))
+        self.current_spp += int(frames)
+
+    def get_reservoirs(self):
+        out = np.empty((self.image_res[1], self.image_res[0], 56), np.uint8)
+        self._lib.orc_get_reservoirs(self._h, out.ctypes.data_as(C.c_void_p))
+        return out
 
     def last_ms(self):
         return float(self._lib.orc_last_ms(self._h))

@@ -10,7 +10,7 @@ EXPORTS = [
     "vrt_create", "vrt_destroy", "vrt_last_error", "vrt_set_stream", "vrt_upload_voxels", "vrt_set_camera",
     "vrt_set_light", "vrt_set_floor", "vrt_set_background", "vrt_set_sky", "vrt_set_materials",
     "vrt_set_cloud_texture", "vrt_prepare", "vrt_get_sky_tables", "vrt_set_sky_tables", "vrt_get_trans_lut",
-    "vrt_trace_primary", "vrt_accumulate", "vrt_set_tile_shard", "vrt_reset", "vrt_accum_device_ptr",
+    "vrt_trace_primary", "vrt_accumulate", "vrt_accumulate_restir", "vrt_get_reservoirs", "vrt_set_tile_shard", "vrt_reset", "vrt_accum_device_ptr",
     "vrt_fetch_hdr", "vrt_fetch_ldr", "vrt_resolve_ldr_device", "vrt_get_stats", "vrt_synchronize",
 ]
 
@@ -33,7 +33,7 @@ class vrt_stats(C.Structure):
         ("paths", C.c_uint64), ("rays", C.c_uint64), ("steps", C.c_uint64), ("queries", C.c_uint64),
         ("hits", C.c_uint64), ("sky_escapes", C.c_uint64), ("nee_visible", C.c_uint64), ("vertices", C.c_uint64),
         ("last_render_ms", C.c_float), ("last_resolve_ms", C.c_float), ("sky_precompute_ms", C.c_float),
-        ("kernel_launches", C.c_uint32),
+        ("kernel_launches", C.c_uint32), ("last_gris_ms", C.c_float),
     ]
 
 
@@ -72,6 +72,8 @@ def load():
     lib.vrt_get_trans_lut.argtypes = [P, P]
     lib.vrt_trace_primary.argtypes = [P, P]
     lib.vrt_accumulate.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.vrt_accumulate_restir.argtypes = [P, C.c_int32, C.c_int32, C.c_int32]
+    lib.vrt_get_reservoirs.argtypes = [P, P]
     lib.vrt_set_tile_shard.argtypes = [P, C.c_int32, C.c_int32]
     lib.vrt_reset.argtypes = [P]
     lib.vrt_accum_device_ptr.argtypes = [P, C.POINTER(P), C.POINTER(C.c_uint64)]

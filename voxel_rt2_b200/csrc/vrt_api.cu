@@ -53,6 +53,7 @@ struct vrt_ctx {
   int jitter_cap = 0;
   unsigned int* d_work = nullptr;
   unsigned long long* d_stats = nullptr;
+  RestirBuffers rb{nullptr, nullptr, nullptr, nullptr, nullptr};  // allocated on first ReSTIR frame
 
   int tile_rank = 0, tile_n = 1;
   vrt_stats stats;
@@ -196,6 +197,7 @@ void vrt_destroy(vrt_ctx* ctx) {
   cudaFree(ctx->d_mats), cudaFree(ctx->d_sky_scatter), cudaFree(ctx->d_sky_trans), cudaFree(ctx->d_trans_lut);
   cudaFree(ctx->d_cloud_tex), cudaFree(ctx->d_cloud_ambient), cudaFree(ctx->d_accum), cudaFree(ctx->d_out), cudaFree(ctx->d_hits);
   cudaFree(ctx->d_jitter), cudaFree(ctx->d_work), cudaFree(ctx->d_stats);
+  cudaFree(ctx->rb.reservoirs), cudaFree(ctx->rb.gpos), cudaFree(ctx->rb.gattr), cudaFree(ctx->rb.col_d), cudaFree(ctx->rb.col_s);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -559,6 +561,69 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
     ctx->stats.paths = h[0], ctx->stats.rays = h[1], ctx->stats.steps = h[2], ctx->stats.queries = h[3], ctx->stats.hits = h[4];
     ctx->stats.sky_escapes = h[5], ctx->stats.nee_visible = h[6], ctx->stats.vertices = h[7];
   }
+  return VRT_OK;
+}
+
+int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, int32_t stride) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(n_frames > 0 && stride > 0 && first_sample >= 0, "vrt_accumulate_restir: bad sample range");
+  REQUIRE(ctx->tile_n == 1, "vrt_accumulate_restir: tile sharding needs a 24-pixel halo (not implemented); use sample sharding");
+  int rc = check_ready(ctx, "vrt_accumulate_restir");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t npx = (size_t)ctx->cfg.width * ctx->cfg.height;
+  if (!ctx->rb.reservoirs) {
+    CK(cudaMalloc(&ctx->rb.reservoirs, npx * 56));
+    CK(cudaMalloc(&ctx->rb.gpos, npx * sizeof(float4)));
+    CK(cudaMalloc(&ctx->rb.gattr, npx * sizeof(uint2)));
+    CK(cudaMalloc(&ctx->rb.col_d, npx * sizeof(float4)));
+    CK(cudaMalloc(&ctx->rb.col_s, npx * sizeof(float4)));
+  }
+  if (ctx->jitter_cap < 1) {
+    CK(cudaMalloc(&ctx->d_jitter, sizeof(float2)));
+    ctx->jitter_cap = 1;
+  }
+  float render_ms = 0.0f, gris_ms = 0.0f;
+  for (int k = 0; k < n_frames; k++) {
+    const uint32_t s = (uint32_t)(first_sample + k * stride);
+    float2 jit = make_float2(0.0f, 0.0f);
+    if (ctx->cfg.jitter_mode == 1)
+      jit = make_float2((float)((halton(s + 1, 2) * 2.0 - 1.0) / (double)ctx->cfg.width), (float)((halton(s + 1, 3) * 2.0 - 1.0) / (double)ctx->cfg.height));
+    CK(cudaMemcpyAsync(ctx->d_jitter, &jit, sizeof jit, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
+    Params P;
+    fill_params(ctx, P);
+    P.first_sample = (int)s, P.n_samples = 1, P.stride = 1;
+    cudaEvent_t evm;
+    CK(cudaEventCreate(&evm));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(vrt_launch_path_restir(P, ctx->rb, ctx->sm_count, ctx->stream));
+    CK(cudaEventRecord(evm, ctx->stream));
+    CK(vrt_launch_gris(P, ctx->rb, s, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // jit lives on the stack
+    float a = 0.0f, b = 0.0f;
+    CK(cudaEventElapsedTime(&a, ctx->ev0, evm));
+    CK(cudaEventElapsedTime(&b, evm, ctx->ev1));
+    cudaEventDestroy(evm);
+    render_ms += a, gris_ms += b;
+  }
+  ctx->stats.last_render_ms = render_ms;
+  ctx->stats.last_gris_ms = gris_ms;
+  ctx->stats.kernel_launches = 2u * (uint32_t)n_frames;
+  return VRT_OK;
+}
+
+int vrt_get_reservoirs(vrt_ctx* ctx, void* out) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(out, "vrt_get_reservoirs: null pointer");
+  if (!ctx->rb.reservoirs) {
+    ctx->err = "vrt_get_reservoirs: no ReSTIR frame has been rendered";
+    return VRT_ERR_NOT_PREPARED;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->rb.reservoirs, (size_t)ctx->cfg.width * ctx->cfg.height * 56, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return VRT_OK;
 }
 

@@ -219,3 +219,41 @@ HD f3 sample_disney(const Mat& m, f3 v, f3 n, f3 tang, f3 bitang, float u_lobe, 
   if (isbad(pdf)) pdf = 1.0f;
   return dir;
 }
+
+// ---- lobe-wise variants used by the ReSTIR reconnection shift (pathtracer.py:672-812)
+enum { LOBE_ALL = 9 };
+
+// bsdf.py:306-349 disney_evaluate_lobewise_split (lobe LOBE_ALL == disney_evaluate_split)
+HD void disney_evaluate_lobewise_split(const Mat& m, f3 v, f3 n, f3 l, f3 tang, f3 bitang, int lobe_id, f3& bsdf_d, f3& bsdf_s) {
+  Geo g = make_geo(v, n, l, tang, bitang);
+  bsdf_d = mk3(0.0f);
+  bsdf_s = mk3(0.0f);
+  if (g.n_dot_l > 0.0f && g.n_dot_v > 0.0f) {
+    if (lobe_id == LOBE_DIFFUSE || lobe_id == LOBE_ALL) bsdf_d = disney_diffuse(m, g.n_dot_l, g.n_dot_v, g.l_dot_h) * (1.0f - m.metallic);
+    if (lobe_id == LOBE_SPEC_REFL || lobe_id == LOBE_ALL) bsdf_s = disney_specular(m, g);
+    if ((lobe_id == LOBE_CLEARC || lobe_id == LOBE_ALL) && m.clearcoat != 0.0f)
+      bsdf_s += mk3(disney_clearcoat(m, g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
+  }
+}
+HD f3 disney_evaluate_lobewise(const Mat& m, f3 v, f3 n, f3 l, f3 tang, f3 bitang, int lobe_id) {
+  f3 d, s;
+  disney_evaluate_lobewise_split(m, v, n, l, tang, bitang, lobe_id, d, s);
+  return d + s;
+}
+// bsdf.py:365-380 pdf_disney_lobewise (inf/NaN -> 1)
+HD float pdf_disney_lobewise(const Mat& m, f3 v, f3 n, f3 l, f3 tang, f3 bitang, int lobe_id) {
+  Geo g = make_geo(v, n, l, tang, bitang);
+  float pdf;
+  if (lobe_id == LOBE_DIFFUSE) {
+    pdf = (saturate(g.n_dot_l) * (1.0f / VRT_PI)) * m.dw;
+  } else if (lobe_id == LOBE_SPEC_REFL) {
+    float D = GTR2_anisotropic(m, g.n_dot_h, g.h_dot_x, g.h_dot_y);
+    float Gv = smithG_GGX_aniso(g.n_dot_v, g.v_dot_x, g.v_dot_y, m.ax, m.ay);
+    pdf = fdiv(Gv * fabsf(g.l_dot_h) * D, fabsf(g.n_dot_l)) * m.sw;
+  } else {
+    float ndh = fabsf(g.n_dot_h);
+    pdf = fdiv(GTR1(m, ndh) * ndh, 4.0f * g.v_dot_h) * m.cw;
+  }
+  if (isbad(pdf)) pdf = 1.0f;
+  return pdf;
+}

@@ -5,10 +5,15 @@
 
 #include "../../include/voxelrt.h"
 #include "vrt_common.cuh"
+#include "vrt_restir.cuh"
 
 // vrt_render.cu
 cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st);
 cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out);
+cudaError_t vrt_launch_path_restir(const Params& P, const RestirBuffers& RB, int sm_count, cudaStream_t st);
+size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem);
+// vrt_restir.cu — spatial_GRIS (pathtracer.py:815-989); adds the frame's colour into P.accum
+cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t frame, cudaStream_t st);
 cudaError_t vrt_launch_resolve(const float4* accum, float4* hdr, float4* ldr, int W, int H, float exposure, cudaStream_t st);
 
 // vrt_build.cu — voxel arrays ([x][y][z], z fastest) -> bricks, colour SoA, upper pyramid

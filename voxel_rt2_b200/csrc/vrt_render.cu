@@ -9,6 +9,7 @@
 //              renderer/math_utils.py:160-186), float4 in / float4 out
 #include "vrt_bsdf.cuh"
 #include "vrt_internal.h"
+#include "vrt_restir.cuh"
 #include "vrt_sky.cuh"
 #include "vrt_trace.cuh"
 
@@ -89,8 +90,13 @@ enum { PIX_IDLE = -1, PIX_DONE = -2 };
 #define VRT_PATH_MIN_BLOCKS 5  // resident CTAs per SM the register allocation is tuned for
 #endif
 
-template <bool STATS>
-__global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem) {
+// RESTIR = true is the USE_RESTIR_PT variant of render (pathtracer.py:15): besides the pixel
+// colour it records the reconnection data of the path (first vertex after the primary hit) into a
+// packed reservoir, merges the primary-vertex NEE sample into it (reservoir.py:64-74) and writes
+// the G-buffer the spatial pass needs. It runs one sample per launch and never retires
+// zero-throughput paths early (their reconnection data is still used by the shift).
+template <bool STATS, bool RESTIR>
+__global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem, RestirBuffers RB) {
   extern __shared__ uint32_t smem[];
   const uint32_t* upper = stage_shared(P, smem, upper_in_smem);
   const float4* s_mats = reinterpret_cast<const float4*>(smem);
@@ -121,6 +127,13 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
   int s_mat = 0;
   TraceCounters tc{0, 0, 0};
   uint32_t c_hits = 0, c_escapes = 0, c_nee = 0, c_vertices = 0, c_paths = 0;
+  // ReSTIR bookkeeping (dead code when !RESTIR)
+  RSample rz;
+  f3 thr_after_rc = mk3(1.0f), primary_pos = mk3(0.0f);
+  float f_lpdf = 1.0f, f_bounce_light_pdf = 0.0f;
+  uint32_t primary_noct = 0u;
+  int rc_lobe = 0;
+  bool sky_ray = false;
 
   bool finished = false, restart = false;
 
@@ -133,21 +146,81 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
       f3 emission = mk3(0.0f);
       if ((pm_info & 255u) == 2u)
         emission = f3{unorm8[(pm_info >> 8) & 255u], unorm8[(pm_info >> 16) & 255u], unorm8[(pm_info >> 24) & 255u]};
-      f3 diffuse = fnee_d, specular = fnee_s;
-      if (f_lobe == LOBE_DIFFUSE) diffuse += contrib * f_invpdf + emission;
-      if (f_lobe == LOBE_SPEC_REFL) specular += contrib * f_invpdf;
-      if (bad3(diffuse)) diffuse = mk3(0.0f);
-      if (bad3(specular)) specular = mk3(0.0f);
-      acc += diffuse + specular;
+      f3 diffuse, specular;
+      const int u = pix & 0xffff, v = pix >> 16;
+      const size_t pidx = (size_t)v * P.W + u;
+      if (!RESTIR) {
+        diffuse = fnee_d, specular = fnee_s;
+        if (f_lobe == LOBE_DIFFUSE) diffuse += contrib * f_invpdf + emission;
+        if (f_lobe == LOBE_SPEC_REFL) specular += contrib * f_invpdf;
+        if (bad3(diffuse)) diffuse = mk3(0.0f);
+        if (bad3(specular)) specular = mk3(0.0f);
+        acc += diffuse + specular;
+      } else {
+        // pathtracer.py:548-607: reservoir of the BSDF-sampled path, RIS-merged with the NEE sample
+        RReservoir res;
+        res.z = rz;
+        res.z.F = contrib;
+        res.z.lobes = rc_lobe * 10 + f_lobe;
+        res.M = 1.0f;
+        res.z.cached_jacobian_term = jacobian_term(res.z.rc_pos, res.z.rc_normal, primary_pos);
+        bool chose_NEE = false;
+        if (!sky_ray) {
+          float bsdf_light_pdf = f_bounce_light_pdf;
+          if (is_vec_zero(fnee_d + fnee_s)) bsdf_light_pdf = 0.0f;
+          const float bsdf_mis = power_heuristic(frcp(f_invpdf), bsdf_light_pdf);
+          const float light_mis = power_heuristic(light_pdf_axis, f_lpdf);
+          res.weight = bsdf_mis * luminance(res.z.F) * f_invpdf;
+          const float in_w = light_mis * luminance(fnee_d + fnee_s);
+          res.M += 1.0f;  // input_sample (reservoir.py:64-74)
+          if (in_w > 0.0f) {
+            res.weight += in_w;
+            if (rnd(key, 40) * res.weight <= in_w) {
+              chose_NEE = true;
+              const f3 first_light_dir = sample_cone_oriented(P.light_cos_max, P.light_dir, sun_bx, sun_by, rnd(key, 0), rnd(key, 1));
+              f3 sky_T = mk3(1.0f);
+              if (P.use_sky) sky_T = sky_fetch(P.sky_trans, sky_tap(P.sky_res, project_sky(first_light_dir, sky_fres)));
+              rinit(res);
+              res.M = 2.0f;
+              res.weight = bsdf_mis * luminance(contrib) * f_invpdf + in_w;
+              res.z.F = fnee_d + fnee_s;
+              res.z.rc_pos = first_light_dir;
+              res.z.rc_incident_L = sky_T * sun_rad;
+              res.z.lobes = LOBE_ALL * 10 + LOBE_ALL;
+            }
+          }
+          const float p_hat = luminance(res.z.F);  // finalize_without_M
+          res.weight = p_hat < 1e-6f ? 0.0f : fdiv(res.weight, p_hat);
+        } else {
+          res.weight = 1.0f;
+        }
+        uint32_t w[14];
+        encode_reservoir(res, w);
+        uint2* dst = RB.reservoirs + pidx * 7;
+#pragma unroll
+        for (int i = 0; i < 7; i++) dst[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+        RB.gpos[pidx] = make_float4(primary_pos.x, primary_pos.y, primary_pos.z, sky_ray ? 1.0f : 0.0f);
+        RB.gattr[pidx] = make_uint2(primary_noct, pm_info);
+        diffuse = mk3(0.0f), specular = mk3(0.0f);
+        if (!chose_NEE) {
+          if (f_lobe == LOBE_DIFFUSE) diffuse = res.z.F;
+          if (f_lobe == LOBE_SPEC_REFL) specular = res.z.F;
+        } else {
+          diffuse = fnee_d, specular = fnee_s;
+        }
+        RB.col_d[pidx] = make_float4(diffuse.x, diffuse.y, diffuse.z, 0.0f);
+        RB.col_s[pidx] = make_float4(specular.x, specular.y, specular.z, 0.0f);
+      }
       s_i++;
-      if (s_i < P.n_samples) {
+      if (s_i < P.n_samples && !RESTIR) {
         restart = true;
       } else {
-        const int u = pix & 0xffff, v = pix >> 16;
-        float4* dst = P.accum + (size_t)v * P.W + u;
-        float4 a = *dst;
-        a.x += acc.x, a.y += acc.y, a.z += acc.z, a.w += (float)P.n_samples;
-        *dst = a;
+        if (!RESTIR) {
+          float4* dst = P.accum + pidx;
+          float4 a = *dst;
+          a.x += acc.x, a.y += acc.y, a.z += acc.z, a.w += (float)P.n_samples;
+          *dst = a;
+        }
         pix = PIX_IDLE;
       }
     }
@@ -190,6 +263,12 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
       pos = P.cam_pos;
       thr = mk3(1.0f), contrib = mk3(0.0f), fnee_d = mk3(0.0f), fnee_s = mk3(0.0f);
       f_invpdf = 1.0f, f_lobe = 0, pm_info = 0, depth = 0, state = ST_SEGMENT;
+      if (RESTIR) {
+        rz.F = rz.rc_pos = rz.rc_normal = rz.rc_incident_dir = rz.rc_incident_L = rz.rc_NEE_dir = mk3(0.0f);
+        rz.rc_mat_info = 0u, rz.cached_jacobian_term = 1.0f, rz.lobes = 0;
+        thr_after_rc = mk3(1.0f), primary_pos = mk3(0.0f), f_lpdf = 1.0f, f_bounce_light_pdf = 0.0f, primary_noct = 0u, rc_lobe = 0;
+        sky_ray = false;
+      }
       if (STATS) c_paths++;
     }
     if (__all_sync(FULL, pix == PIX_DONE)) break;
@@ -207,6 +286,23 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
     if (active) {
       if (state == ST_SEGMENT) {
         const uint32_t base = 8u * (uint32_t)depth;
+        if (RESTIR) {  // pathtracer.py:402-417
+          const f3 hit_pos = pos + h.closest * d;
+          if (depth == 0) {
+            primary_pos = hit_pos;
+            pm_info = encode_material(h.mat_id, h.albedo);
+            float ex = 0.0f, ey = 0.0f;
+            if (h.closest < VRT_INF) encode_unit_vector_3x16(f3{h.nx, h.ny, h.nz}, ex, ey);
+            primary_noct = h16bits(ex) | (h16bits(ey) << 16);
+          } else if (depth == 1) {
+            rz.rc_pos = hit_pos;
+            rz.rc_normal = f3{h.nx, h.ny, h.nz};
+            rz.rc_mat_info = encode_material(h.mat_id, h.albedo);
+            f_bounce_light_pdf = cone_sample_pdf(P.light_cos_max, dot(P.light_dir, d));
+          } else if (depth == 2) {
+            rz.rc_incident_dir = d;
+          }
+        }
         if (h.closest == VRT_INF) {
           // escaped: background or sky tables + sun disk (pathtracer.py:499-511)
           const float hit_sun = dot(P.light_dir, d) >= P.light_cos_max ? 1.0f : 0.0f;
@@ -220,11 +316,23 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
           }
           f3 sky_emission = firefly_filter(sky_scattering + sky_T * sun_rad * hit_sun);
           contrib += thr * sky_emission;
+          if (RESTIR) {  // pathtracer.py:509-517
+            if (depth == 0) {
+              primary_pos = mk3(0.0f);
+              sky_ray = true;
+            } else if (depth == 1) {
+              rz.rc_pos = d;
+              rz.rc_incident_L = sky_emission;
+            } else {
+              rz.rc_incident_L += firefly_filter(thr_after_rc * sky_emission);
+            }
+          }
           finished = true;
         } else if (h.hit_light) {
           // emissive voxel / floor terminates the path (pathtracer.py:519-525)
           if (depth > 0) contrib += thr * h.albedo;
           if (depth == 0) pm_info = encode_material(h.mat_id, h.albedo);
+          if (RESTIR && depth >= 2) rz.rc_incident_L += firefly_filter(thr_after_rc * h.albedo);
           finished = true;
         } else {
           if (STATS) c_vertices++;
@@ -270,11 +378,17 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
         const f3 lr = sky_T * sun_rad * ndl;
         if (depth == 0) {
           // primary vertex: unweighted at accumulation time, MIS weight applied once at the end
-          // (pathtracer.py:470-472, :561-568); thr == 1 here.
-          fnee_d = firefly_filter(thr * (bd * lr)) * mis;
-          fnee_s = firefly_filter(thr * (bs * lr)) * mis;
+          // (pathtracer.py:470-472, :561-568); thr == 1 here. The ReSTIR variant keeps the
+          // unweighted value: the MIS weight goes into the RIS weight instead (:565-568).
+          fnee_d = firefly_filter(thr * (bd * lr)) * (RESTIR ? 1.0f : mis);
+          fnee_s = firefly_filter(thr * (bs * lr)) * (RESTIR ? 1.0f : mis);
+          if (RESTIR) f_lpdf = lpdf;
         } else {
           contrib += firefly_filter(thr * ((mis * (bd + bs)) * lr));
+          if (RESTIR) {
+            if (depth == 1) rz.rc_NEE_dir = light_dir;
+            if (depth >= 2) rz.rc_incident_L += thr_after_rc * ((mis * (bd + bs)) * lr);
+          }
         }
       }
       f3 brdf;
@@ -289,12 +403,16 @@ __global__ void __launch_bounds__(128, VRT_PATH_MIN_BLOCKS) k_path(const __grid_
         bounce_weight = bounce_weight * frcp(pdf);
         const float bsdf_sample_light_pdf = cone_sample_pdf(P.light_cos_max, dot(P.light_dir, nd));
         bounce_weight *= power_heuristic(pdf, visible * bsdf_sample_light_pdf);
+        if (RESTIR) {
+          if (depth == 1) rc_lobe = lobe;
+          if (depth >= 2) thr_after_rc *= bounce_weight;
+        }
       }
       thr *= bounce_weight;
       d = nd;
       depth++;
       // The reference keeps tracing zero-throughput paths; they add exact zeros, so stop here.
-      const bool dead = thr.x == 0.0f && thr.y == 0.0f && thr.z == 0.0f;
+      const bool dead = !RESTIR && thr.x == 0.0f && thr.y == 0.0f && thr.z == 0.0f;
       if (depth >= P.max_depth || dead) finished = true;
     }
   }
@@ -362,27 +480,32 @@ cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out) {
+template <bool STATS, bool RESTIR>
+static cudaError_t launch_path_t(const Params& P, int sm_count, cudaStream_t st, int* blocks_out, const RestirBuffers& RB) {
   int uis;
   size_t sm = smem_bytes(P, &uis);
   int per_sm = 0;
-  cudaError_t e;
-  if (stats)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<true>, 128, sm);
-  else
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<false>, 128, sm);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<STATS, RESTIR>, 128, sm);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   int blocks = sm_count * per_sm;  // persistent: one wave, a multiple of the SM count
   int max_useful = (P.n_tiles + 3) / 4;
   if (blocks > max_useful) blocks = max_useful > 0 ? max_useful : 1;
   if (blocks_out) *blocks_out = blocks;
-  if (stats)
-    k_path<true><<<blocks, 128, sm, st>>>(P, uis);
-  else
-    k_path<false><<<blocks, 128, sm, st>>>(P, uis);
+  k_path<STATS, RESTIR><<<blocks, 128, sm, st>>>(P, uis, RB);
   return cudaGetLastError();
 }
+
+cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out) {
+  RestirBuffers none{nullptr, nullptr, nullptr, nullptr, nullptr};
+  return stats ? launch_path_t<true, false>(P, sm_count, st, blocks_out, none) : launch_path_t<false, false>(P, sm_count, st, blocks_out, none);
+}
+
+cudaError_t vrt_launch_path_restir(const Params& P, const RestirBuffers& RB, int sm_count, cudaStream_t st) {
+  return launch_path_t<false, true>(P, sm_count, st, nullptr, RB);
+}
+
+size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem) { return smem_bytes(P, upper_in_smem); }
 
 cudaError_t vrt_launch_resolve(const float4* accum, float4* hdr, float4* ldr, int W, int H, float exposure, cudaStream_t st) {
   int n = W * H;

@@ -1,0 +1,267 @@
+// Spatial reservoir resampling (GRIS) for the ReSTIR-PT mode. Replaces, in
+// renderer/pathtracer.py: shift() :672-812 and spatial_GRIS :815-989 (pass 0 of 1, radius 24,
+// 32 taps), followed by the static-camera accumulation of :1185-1303 (running mean == sum).
+// One thread per pixel in 8x4 tiles; per tap it reads the neighbour's 56-byte reservoir and
+// 24-byte G-buffer record (the pass is the bandwidth-heavy kernel of the mode: 32 x 80 B per
+// pixel, mostly L2 hits because 48x48-pixel footprints of neighbouring pixels overlap).
+// Pinned holes of the upstream code: see DESIGN.md "ReSTIR pins" and oracle/orestir.h.
+#include "vrt_bsdf.cuh"
+#include "vrt_internal.h"
+#include "vrt_restir.cuh"
+#include "vrt_sky.cuh"
+#include "vrt_trace.cuh"
+
+namespace {
+
+#define RADIANCE_CLAMP 300.0f
+HD f3 firefly_filter(f3 v) { return clamp3(v, 0.0f, RADIANCE_CLAMP); }
+HD float power_heuristic(float a, float b) {
+  float a_sqr = a * a;
+  return __fdividef(a_sqr, fmaxf(a_sqr + b * b, 1e-4f));
+}
+HD bool bad3(f3 c) { return isbad(c.x) || isbad(c.y) || isbad(c.z) || c.x < 0.0f || c.y < 0.0f || c.z < 0.0f; }
+HD uint32_t hash3(uint32_t x, uint32_t y, uint32_t z) {  // math_utils.py:217-229
+  x += x >> 11;
+  x ^= x << 7;
+  x += y;
+  x ^= x << 3;
+  x += z ^ (x >> 14);
+  x ^= x << 6;
+  x += x >> 15;
+  x ^= x << 5;
+  x += x >> 12;
+  x ^= x << 9;
+  return x;
+}
+
+struct GrisCtx {
+  const float4* mats;
+  const float* unorm8;
+  f3 cam_pos, light_dir, sun_rad;
+  float light_cos_max, light_pdf_axis;
+  int use_sky, sky_res;
+  const float4* sky_trans;
+};
+
+HD Mat decode_material(const GrisCtx& G, uint32_t enc, int& mat_id) {  // math_utils.py:238-247
+  mat_id = (int)(enc & 255u);
+  Mat m = load_mat(G.mats, mat_id);
+  m.base_col = f3{G.unorm8[(enc >> 8) & 255u], G.unorm8[(enc >> 16) & 255u], G.unorm8[(enc >> 24) & 255u]};
+  return m;
+}
+
+// pathtracer.py:672-812
+HD void shift_sample(const GrisCtx& G, f3 dst_pos, f3 dst_normal, const Mat& dst_material, const RReservoir& src, f3& diffuse, f3& specular,
+                     float& jacobian_out) {
+  const RSample& z = src.z;
+  const bool esc = is_vec_zero(z.rc_normal), last = is_vec_zero(z.rc_incident_dir), nee = !is_vec_zero(z.rc_NEE_dir);
+  const f3 dir = esc ? z.rc_pos : normalize(z.rc_pos - dst_pos);
+  float passed_checks = 1.0f;
+  if (dot(dst_normal, dir) < 1e-5f || (!esc && dot(z.rc_normal, -dir) < 1e-5f)) passed_checks = 0.0f;
+  f3 rc_tang, rc_bitang;
+  make_orthonormal_basis(z.rc_normal, rc_tang, rc_bitang);
+  int rc_mat_id;
+  const Mat rc_mat = decode_material(G, z.rc_mat_info, rc_mat_id);
+  f3 contrib = mk3(0.0f);
+  if (!last && !esc) {
+    f3 rc_brdf = disney_evaluate_lobewise(rc_mat, -dir, z.rc_normal, z.rc_incident_dir, rc_tang, rc_bitang, z.lobes / 10);
+    rc_brdf *= saturate(dot(z.rc_normal, z.rc_incident_dir));
+    const float dst_rc_pdf = pdf_disney_lobewise(rc_mat, -dir, z.rc_normal, z.rc_incident_dir, rc_tang, rc_bitang, z.lobes / 10);
+    const float lp = cone_sample_pdf(G.light_cos_max, dot(G.light_dir, z.rc_incident_dir));
+    const float w = power_heuristic(dst_rc_pdf, lp * (nee ? 1.0f : 0.0f));
+    contrib += firefly_filter((w * rc_brdf) * frcp(dst_rc_pdf) * z.rc_incident_L);
+  }
+  if (esc) contrib += firefly_filter(z.rc_incident_L);
+  if (nee && !esc) {
+    f3 bd, bs;
+    float lpdf;
+    eval_and_pdf(rc_mat, -dir, z.rc_normal, z.rc_NEE_dir, rc_tang, rc_bitang, bd, bs, lpdf);
+    const f3 rc_nee_brdf = (bd + bs) * saturate(dot(z.rc_normal, z.rc_NEE_dir));
+    const float w = power_heuristic(G.light_pdf_axis, lpdf);
+    f3 sky_T = mk3(1.0f);
+    if (G.use_sky) sky_T = sky_fetch(G.sky_trans, sky_tap(G.sky_res, project_sky(z.rc_NEE_dir, 1.0f / (float)G.sky_res)));
+    contrib += firefly_filter((w * rc_nee_brdf) * sky_T * G.sun_rad);
+  }
+  if (rc_mat_id == 2) contrib += rc_mat.base_col;
+  f3 dst_tang, dst_bitang;
+  make_orthonormal_basis(dst_normal, dst_tang, dst_bitang);
+  const f3 view = normalize(G.cam_pos - dst_pos);
+  f3 pd, ps;
+  disney_evaluate_lobewise_split(dst_material, view, dst_normal, dir, dst_tang, dst_bitang, z.lobes % 10, pd, ps);
+  const float cosd = saturate(dot(dst_normal, dir));
+  diffuse = (pd * cosd) * contrib;
+  specular = (ps * cosd) * contrib;
+  float jacobian = 1.0f;
+  if (!esc) {
+    const f3 y = z.rc_pos - dst_pos;
+    jacobian = z.cached_jacobian_term * fdiv(fabsf(dot(normalize(y), z.rc_normal)), dot(y, y));
+  }
+  if (jacobian < 0.0f || isbad(jacobian)) jacobian = 0.0f;
+  jacobian_out = jacobian * passed_checks;
+}
+
+HD void load_reservoir(const uint2* __restrict__ base, size_t pidx, const float* unorm8, RReservoir& r) {
+  uint32_t w[14];
+  const uint2* src = base + pidx * 7;
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    uint2 t = __ldg(src + i);
+    w[2 * i] = t.x, w[2 * i + 1] = t.y;
+  }
+  decode_reservoir(w, unorm8, r);
+}
+
+__global__ void __launch_bounds__(128) k_gris(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int upper_in_smem, int fixed_words) {
+  extern __shared__ uint32_t smem[];
+  // same staging layout as the render kernels: materials, UNORM8 table, upper pyramid
+  float4* s_mats = reinterpret_cast<float4*>(smem);
+  for (int i = threadIdx.x; i < 128 * MAT_ROW_F4; i += blockDim.x) s_mats[i] = P.mats[i];
+  float* s_unorm = reinterpret_cast<float*>(smem + 128 * MAT_ROW_F4 * 4);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = xdiv((float)i, 255.0f);
+  const uint32_t* upper = P.upper;
+  if (upper_in_smem) {
+    uint32_t* s_upper = smem + fixed_words;
+    for (int i = threadIdx.x; i < P.upper_words; i += blockDim.x) s_upper[i] = P.upper[i];
+    upper = s_upper;
+  }
+  __syncthreads();
+
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P.n_tiles) return;
+  const int tile = P.tile_rank + P.tile_n * warp;
+  const int u = (tile % P.tiles_x) * 8 + (lane & 7), v = (tile / P.tiles_x) * 4 + (lane >> 3);
+  const int W = P.W, H = P.H;
+  const size_t pidx = (size_t)v * W + u;
+
+  GrisCtx G;
+  G.mats = s_mats, G.unorm8 = s_unorm;
+  G.cam_pos = P.cam_pos, G.light_dir = P.light_dir, G.sun_rad = P.light_weight * P.light_color;
+  G.light_cos_max = P.light_cos_max, G.light_pdf_axis = cone_sample_pdf(P.light_cos_max, 1.0f);
+  G.use_sky = P.use_sky, G.sky_res = P.sky_res, G.sky_trans = P.sky_trans;
+
+  const float max_radius = 24.0f;
+  const int max_taps = 32;
+  const uint32_t key = path_key((uint32_t)pidx, frame, P.seed);
+  RReservoir center;
+  load_reservoir(RB.reservoirs, pidx, s_unorm, center);
+  const float4 gp = RB.gpos[pidx];
+  f3 out_d, out_s;
+  if (gp.w != 0.0f) {  // primary ray escaped: pass the sample through (pathtracer.py:854-856)
+    out_d = center.z.F;
+    out_s = mk3(0.0f);
+  } else {
+    const uint2 ga = RB.gattr[pidx];
+    const uint32_t seed = hash3((uint32_t)u >> 3, (uint32_t)v >> 3, frame * 2u);
+    const float angle_shift = (float)((seed & 0x007FFFFFu) | 0x3F800000u) / 4294967295.0f * VRT_PI;
+    const float radius_shift = rnd(key, 65);
+    RReservoir out;
+    rinit(out);
+    const f3 center_x1{gp.x, gp.y, gp.z};
+    const float center_dist = length(center_x1 - P.cam_pos);
+    const f3 center_n1 = decode_unit_vector_3x16(h16val(ga.x), h16val(ga.x >> 16));
+    int center_mat_id;
+    const Mat center_mat = decode_material(G, ga.y, center_mat_id);
+    int valid_samples = 0;
+    float canonical_mis_weight = 1.0f;
+    f3 chosen_F_d = mk3(0.0f), chosen_F_s = mk3(0.0f);
+    const float center_F_lum = luminance(center.z.F);
+    for (int i = 0; i < max_taps; i++) {
+      const float golden_angle = 2.399963229728f;
+      const float angle = ((float)i + angle_shift) * golden_angle;
+      const float offset_radius = sqrtf(((float)i + radius_shift) / (float)max_taps) * max_radius;
+      float sn, cs;
+      sincosf(angle, &sn, &cs);
+      const int ox = (int)(cs * offset_radius), oy = (int)(sn * offset_radius);
+      if (ox == 0 && oy == 0) continue;
+      const int tu = u + ox, tv = v + oy;
+      if (tu < 0 || tv < 0 || tu >= W || tv >= H) continue;
+      const size_t ti = (size_t)tv * W + tu;
+      const float4 ngp = __ldg(RB.gpos + ti);
+      if (ngp.w != 0.0f) continue;
+      const uint2 nga = __ldg(RB.gattr + ti);
+      const f3 neighbour_n1 = decode_unit_vector_3x16(h16val(nga.x), h16val(nga.x >> 16));
+      const f3 neighbour_x1{ngp.x, ngp.y, ngp.z};
+      const float neighbour_dist = length(neighbour_x1 - P.cam_pos);
+      if (fabsf(neighbour_dist - center_dist) > 0.1f * center_dist || dot(center_n1, neighbour_n1) < 0.5f) continue;
+      RReservoir nb;
+      load_reservoir(RB.reservoirs, ti, s_unorm, nb);
+      int neighbour_mat_id;
+      const Mat neighbour_mat = decode_material(G, nga.y, neighbour_mat_id);
+      f3 c_d, c_s, s_d, s_s;
+      float c_jacobian, jacobian;
+      shift_sample(G, neighbour_x1, neighbour_n1, neighbour_mat, center, c_d, c_s, c_jacobian);
+      shift_sample(G, center_x1, center_n1, center_mat, nb, s_d, s_s, jacobian);
+      const float center_p_hat = luminance(c_d + c_s) * c_jacobian;
+      float canonical_weight = center_p_hat * nb.M;
+      canonical_weight = canonical_weight / (center_p_hat * nb.M + center_F_lum * center.M / (float)max_taps);
+      canonical_mis_weight += 1.0f - canonical_weight;
+      const float p_hat = luminance(s_d + s_s);
+      const float p_hat_from_neighbour = p_hat / jacobian;
+      float neighbour_mis_weight = p_hat_from_neighbour * nb.M;
+      neighbour_mis_weight = neighbour_mis_weight / (p_hat_from_neighbour * nb.M + p_hat * center.M / (float)max_taps);
+      if (isbad(neighbour_mis_weight)) neighbour_mis_weight = 0.0f;
+      // merge (reservoir.py:76-86)
+      const float in_w = nb.weight * p_hat * jacobian * neighbour_mis_weight;
+      out.M += nb.M;
+      if (in_w > 0.0f) {
+        out.weight += in_w;
+        if (rnd(key, 66u + (uint32_t)i) * out.weight <= in_w) {
+          out.z = nb.z;
+          out.z.F = s_d + s_s;
+          chosen_F_d = s_d;
+          chosen_F_s = s_s;
+        }
+      }
+      valid_samples += 1;
+    }
+    // visibility of the resampled reconnection (pathtracer.py:957-965)
+    bool force_add_canonical = false;
+    if (out.weight > 0.0f) {
+      const bool esc = is_vec_zero(out.z.rc_normal);
+      const f3 dir = esc ? out.z.rc_pos : normalize(out.z.rc_pos - center_x1);
+      const f3 org = center_x1 + center_n1 * (0.003f * center_dist);
+      Hit sh = next_hit<false>(P, upper, s_unorm, org, dir, true, nullptr, nullptr);
+      const float actual_dist = esc ? VRT_INF : length(center_x1 - out.z.rc_pos);
+      if (sh.closest < VRT_INF && fabsf(sh.closest - actual_dist) > 0.1f * actual_dist) {
+        out.weight = 0.0f;
+        force_add_canonical = true;
+      }
+    }
+    {
+      const float in_w = center.weight * center_F_lum * canonical_mis_weight;
+      out.M += center.M;
+      if (in_w > 0.0f) {
+        out.weight += in_w;
+        if (rnd(key, 98) * out.weight <= in_w || force_add_canonical) {
+          out.z = center.z;
+          const float4 cd = RB.col_d[pidx], cs4 = RB.col_s[pidx];
+          chosen_F_d = f3{cd.x, cd.y, cd.z};
+          chosen_F_s = f3{cs4.x, cs4.y, cs4.z};
+        }
+      }
+    }
+    const float p_hat = luminance(out.z.F);  // finalize_without_M, then / (valid + 1)
+    float Wt = p_hat < 1e-6f ? 0.0f : out.weight / p_hat;
+    Wt = Wt / (float)(valid_samples + 1);
+    const f3 emission = center_mat_id == 2 ? center_mat.base_col : mk3(0.0f);
+    const float Wc = clampf(Wt, 0.0f, 50.0f);
+    out_d = chosen_F_d * Wc + emission;
+    out_s = chosen_F_s * Wc;
+  }
+  if (bad3(out_d)) out_d = mk3(0.0f);
+  if (bad3(out_s)) out_s = mk3(0.0f);
+  float4 a = P.accum[pidx];
+  a.x += out_d.x + out_s.x, a.y += out_d.y + out_s.y, a.z += out_d.z + out_s.z, a.w += 1.0f;
+  P.accum[pidx] = a;
+}
+
+}  // namespace
+
+cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t frame, cudaStream_t st) {
+  int uis;
+  size_t sm = vrt_render_smem_bytes(P, &uis);
+  const int fixed_words = 128 * MAT_ROW_F4 * 4 + 256;
+  int blocks = (P.n_tiles * 32 + 127) / 128;
+  k_gris<<<blocks, 128, sm, st>>>(P, RB, frame, uis, fixed_words);
+  return cudaGetLastError();
+}

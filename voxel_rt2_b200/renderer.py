@@ -187,6 +187,21 @@ class Renderer:
         self.current_spp += int(spp)
         self.current_frame += int(spp)
 
+    def accumulate_restir(self, frames=1):
+        """accumulate() with USE_RESTIR_PT = True (pathtracer.py:15,1310-1319): per frame one path per
+        pixel into a reservoir, then spatial_GRIS(0, 24.0, 32, 1), then accumulation."""
+        self._sync_camera()
+        first = self.sample_offset + self.current_spp * self.sample_stride
+        self._check(self._lib.vrt_accumulate_restir(self._h, first, int(frames), self.sample_stride))
+        self.current_spp += int(frames)
+        self.current_frame += int(frames)
+
+    def get_reservoirs(self):
+        """Packed 56-byte reservoirs of the last ReSTIR frame, uint8 [H, W, 56]."""
+        out = np.empty((self.image_res[1], self.image_res[0], 56), np.uint8)
+        self._check(self._lib.vrt_get_reservoirs(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def reset_framebuffer(self):  # pathtracer.py:664-668
         self.current_spp = 0
         self._check(self._lib.vrt_reset(self._h))
