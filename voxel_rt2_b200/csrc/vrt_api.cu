@@ -3,6 +3,7 @@
 // there is no CUDA device, vrt_create fails with VRT_ERR_NO_DEVICE.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -548,7 +549,15 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
   P.stats = stats ? ctx->d_stats : nullptr;
   if (P.n_tiles <= 0) return VRT_OK;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  CK(vrt_launch_path(P, stats != 0, ctx->sm_count, ctx->stream, nullptr));
+  {
+    // VRT_KERNEL=pool selects the experimental shared-memory wavefront kernel (vrt_pool.cu): correct,
+    // but measured 25-40 % slower than the per-lane kernel in round 1 (profiles/r01_pool_experiment.md)
+    const char* k = getenv("VRT_KERNEL");
+    if (k && !strcmp(k, "pool"))
+      CK(vrt_launch_path_pool(P, stats != 0, ctx->sm_count, ctx->stream, nullptr));
+    else
+      CK(vrt_launch_path(P, stats != 0, ctx->sm_count, ctx->stream, nullptr));
+  }
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->stats.kernel_launches = 1;
   // the jitter vector is read by the async copy above: wait before it goes out of scope

@@ -10,6 +10,8 @@
 // vrt_render.cu
 cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st);
 cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out);
+// vrt_pool.cu — shared-memory wavefront version of the path kernel (default for path tracing)
+cudaError_t vrt_launch_path_pool(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out);
 cudaError_t vrt_launch_path_restir(const Params& P, const RestirBuffers& RB, int sm_count, cudaStream_t st);
 size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem);
 // vrt_restir.cu — spatial_GRIS (pathtracer.py:815-989); adds the frame's colour into P.accum

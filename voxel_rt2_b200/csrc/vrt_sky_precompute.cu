@@ -40,7 +40,11 @@ HD f2 rsi(f3 pos, f3 dir, float r) {
   return f2{xadd(-b, -discr), xadd(-b, discr)};
 }
 HD float rayleigh_phase(float c) { return 3.0f / (16.0f * VRT_PI) * (1.0f + c * c); }
-HD float mie_phase(float c, float g) { return (1.0f - g * g) / (4.0f * VRT_PI * powf(1.0f + g * g - 2.0f * g * c, 1.5f)); }
+// atmos.py:22-25; x^1.5 as x*sqrt(x): powf was ~40 % of the skybox kernel's instructions
+HD float mie_phase(float c, float g) {
+  const float t = 1.0f + g * g - 2.0f * g * c;
+  return (1.0f - g * g) / (4.0f * VRT_PI * (t * sqrtf(t)));
+}
 HD f3 get_unit_vec(float rx, float ry) {
   rx *= VRT_PI * 2.0f;
   ry = ry * 2.0f - 1.0f;
