@@ -267,3 +267,29 @@ def test_restir_converges_to_path_traced_image(vrt):
     ma, mb = a.fetch_hdr()[..., :3].mean(), b.fetch_hdr()[..., :3].mean()
     print("pt mean %.5f restir mean %.5f" % (ma, mb))
     assert abs(mb / ma - 1.0) < 0.03
+
+
+def test_sky_table_cache_round_trip(vrt, tmp_path, monkeypatch):
+    """VRT_SKY_CACHE: the second renderer with the same sun / cloud settings loads
+    the tables from disk instead of recomputing them, bit-identically."""
+    monkeypatch.setenv("VRT_SKY_CACHE", str(tmp_path))
+
+    def mk():
+        g = vrt.Renderer(dx=2.0 / 32, image_res=(64, 32), grid_res=32, sky_res=48, cloud_passes=2, seed=2)
+        g.set_voxels(*scenes.random_grid(32, 0.2, 3))
+        g.set_directional_light((1, 1, -1), 0.025, (1.3, 1.2, 1.2))
+        g.set_use_physical_sky(True, True)
+        g.prepare_data()
+        return g
+
+    a = mk()
+    assert a.stats()["sky_precompute_ms"] > 0.0
+    files = list(tmp_path.glob("sky_*.npy"))
+    assert len(files) == 1
+    b = mk()
+    assert b.stats()["sky_precompute_ms"] == 0.0  # came from the cache
+    for x, y in zip(a.get_sky_tables(), b.get_sky_tables()):
+        assert np.array_equal(x, y)
+    a.accumulate(2)
+    b.accumulate(2)
+    assert np.array_equal(a.fetch_hdr(), b.fetch_hdr())

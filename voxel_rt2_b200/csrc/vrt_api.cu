@@ -44,7 +44,7 @@ struct vrt_ctx {
   __half* d_trans_lut = nullptr;
   uint8_t* d_cloud_tex = nullptr;
   float* d_cloud_ambient = nullptr;
-  bool sky_valid = false, cloud_tex_set = false;
+  bool sky_valid = false, cloud_tex_set = false, lut_valid = false;
 
   // frame buffers
   float4* d_accum = nullptr;
@@ -432,6 +432,7 @@ int vrt_prepare(vrt_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.sky_precompute_ms, ctx->ev0, ctx->ev1));
     ctx->sky_valid = true;
+    ctx->lut_valid = true;
   }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->prepared = true;
@@ -477,7 +478,7 @@ int vrt_set_sky_tables(vrt_ctx* ctx, const float* scattering, const float* trans
 int vrt_get_trans_lut(vrt_ctx* ctx, uint16_t* lut) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(lut, "vrt_get_trans_lut: null pointer");
-  if (!ctx->d_trans_lut || !ctx->sky_valid) {
+  if (!ctx->d_trans_lut || !ctx->lut_valid) {
     ctx->err = "vrt_get_trans_lut: sky has not been computed";
     return VRT_ERR_NOT_PREPARED;
   }

@@ -43,7 +43,7 @@ HD float rayleigh_phase(float c) { return 3.0f / (16.0f * VRT_PI) * (1.0f + c * 
 // atmos.py:22-25; x^1.5 as x*sqrt(x): powf was ~40 % of the skybox kernel's instructions
 HD float mie_phase(float c, float g) {
   const float t = 1.0f + g * g - 2.0f * g * c;
-  return (1.0f - g * g) / (4.0f * VRT_PI * (t * sqrtf(t)));
+  return (1.0f - g * g) * frcp(4.0f * VRT_PI * (t * fsqrt(t)));
 }
 HD f3 get_unit_vec(float rx, float ry) {
   rx *= VRT_PI * 2.0f;
@@ -138,13 +138,16 @@ __device__ void atmospheric_scattering(const SkyBuild& B, f3 sbx, f3 sby, f3 ray
     const f3 step_T = saturate3(exp3(-step_od));
     const f3 visible = transmittance * saturate3((mk3(1.0f) - step_T) / step_od);
     const f3 npos = normalize(ray_pos);
+    // per-step factors of the two in-scatter terms hoisted out of the 8 sun samples (the
+    // reference multiplies left to right inside the loop; same product, different rounding order)
+    const f3 a_r = c_atm.rayleigh_coeff * B.sun_col * visible * (density.x * step_delta * 0.125f);
+    const f3 a_m = c_atm.mie_coeff * B.sun_col * visible * (density.y * step_delta * 0.125f);
     for (int j = 0; j < 8; j++) {
       f3 sample_dir = sun_basis_sample(B.cosmax, B.sun_dir, sbx, sby, rng);
       float cos_theta = dot(ray_dir, sample_dir);
       float ph_r = rayleigh_phase(cos_theta), ph_m = mie_phase(cos_theta, c_atm.mie_g);
       f3 sun_T = read_trans_lut(B.trans_lut, dot(npos, sample_dir), h);
-      in_scatter_col += c_atm.rayleigh_coeff * B.sun_col * sun_T * visible * ph_r * density.x * step_delta / 8.0f;
-      in_scatter_col += c_atm.mie_coeff * B.sun_col * sun_T * visible * ph_m * density.y * step_delta / 8.0f;
+      in_scatter_col += (a_r * ph_r + a_m * ph_m) * sun_T;
     }
     if (DEPTH == 0) {
       const float ms_energy = 5.3f;

@@ -46,6 +46,7 @@ class Renderer:
         self.max_depth = int(max_depth)
         self.sky_res = int(sky_res)
         self.up = tuple(float(x) for x in up)
+        self._cloud_passes, self._seed, self._cloud_tex_digest = int(cloud_passes), int(seed), ""
         self.current_spp = 0
         self.current_frame = 0
         self.sample_stride = 1   # sample sharding: this renderer draws indices offset, offset+stride, ...
@@ -136,6 +137,9 @@ class Renderer:
         tex = np.ascontiguousarray(tex, dtype=np.uint8)
         if tex.shape != (256, 256, 3):
             raise ValueError("cloud texture must be uint8 [256,256,3]")
+        import hashlib
+
+        self._cloud_tex_digest = hashlib.sha256(tex.tobytes()).hexdigest()[:16]
         self._check(self._lib.vrt_set_cloud_texture(self._h, tex.ctypes.data_as(C.c_void_p)))
 
     # ------------------------------------------------------------------ camera (pathtracer.py:246-281)
@@ -167,10 +171,35 @@ class Renderer:
             self.set_view_proj(self._camera_pos, view, proj)
 
     # ------------------------------------------------------------------ frame pipeline
+    def _sky_cache_path(self):
+        """Sky tables depend only on (sun direction, colour, cone, clouds, resolution, passes, seed,
+        cloud texture). VRT_SKY_CACHE=<dir> keeps them across runs: the 3840^2
+        precompute is seconds of GPU time, a cached pair is one 354 MB file read."""
+        d = os.environ.get("VRT_SKY_CACHE")
+        if not d or not self.use_physical_atmosphere:
+            return None
+        import hashlib
+
+        key = repr((self.light_direction, self.light_cone_angle, self.light_color, self.use_clouds, self.sky_res, self._cloud_passes,
+                    self._seed, self._cloud_tex_digest))
+        return os.path.join(d, "sky_%s.npy" % hashlib.sha256(key.encode()).hexdigest()[:24])
+
     def prepare_data(self):
         """pathtracer.py:314-323 + the sky start-up frames of Scene.finish (scene.py:243-253)."""
         self._sync_camera()
+        path = self._sky_cache_path()
+        if path and os.path.exists(path):
+            tabs = np.load(path, mmap_mode="r")
+            if tabs.shape == (2, self.sky_res, self.sky_res, 3):
+                self.set_sky_tables(np.ascontiguousarray(tabs[0]), np.ascontiguousarray(tabs[1]))
+                path = None  # tables installed: vrt_prepare skips the precompute
         self._check(self._lib.vrt_prepare(self._h))
+        if path:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            a, b = self.get_sky_tables()
+            tmp = path + ".tmp.npy"
+            np.save(tmp, np.stack([a, b]))
+            os.replace(tmp, path)
 
     def set_tile_shard(self, rank, n):
         self._check(self._lib.vrt_set_tile_shard(self._h, int(rank), int(n)))
