@@ -293,3 +293,86 @@ def test_sky_table_cache_round_trip(vrt, tmp_path, monkeypatch):
     a.accumulate(2)
     b.accumulate(2)
     assert np.array_equal(a.fetch_hdr(), b.fetch_hdr())
+
+
+# ------------------------------------------------------------------------------ edge cases
+def test_empty_and_full_grids(vrt, oracle):
+    """Empty grid: every primary ray misses the voxels (floor / sky only). Completely full grid:
+    every ray that enters the box hits on its first cell. Both bit-exact vs the oracle."""
+    for fill in (0, 1):
+        R = 32
+        g, o = make_pair(vrt, oracle, image_res=(64, 64), grid_res=R, jitter=False)
+        mat = np.full((R, R, R), fill, np.int8)
+        col = np.full((R, R, R, 3), 128, np.uint8)
+        both = (g, o)
+        apply_both(both, "set_voxels", mat, col)
+        apply_both(both, "set_floor", -1.2, (0.5, 0.5, 0.5))
+        apply_both(both, "prepare_data")
+        hg, ho = g.trace_primary(), o.trace_primary()
+        _hits_equal(hg, ho)
+        kinds = set(np.unique(hg["flags"] & 255).tolist())
+        assert (2 in kinds) == bool(fill)
+        g.accumulate(2)
+        o.accumulate(2)
+        assert rel_rmse(g.fetch_hdr(), o.fetch_hdr()) < 1e-3 or np.allclose(g.fetch_hdr(), o.fetch_hdr(), atol=1e-6)
+
+
+def test_largest_grid_512_and_small_grid_8(vrt, oracle):
+    """Grid-size limits of the C-ABI: 8^3 (all LODs inside one brick level) and 512^3 (upper
+    pyramid too large for shared memory -> read from global memory)."""
+    for R, occ in ((8, 0.3), (512, 0.002)):
+        g, o = make_pair(vrt, oracle, image_res=(128, 64), grid_res=R, jitter=False)
+        mat, col = scenes.random_grid(R, occ, 17)
+        both = (g, o)
+        apply_both(both, "set_voxels", mat, col)
+        apply_both(both, "set_floor", -1e5, (1.0, 1.0, 1.0))
+        apply_both(both, "prepare_data")
+        _hits_equal(g.trace_primary(), o.trace_primary())
+
+
+@pytest.mark.parametrize("depth", [1, 2, 8])
+def test_path_depth_parameter(vrt, oracle, depth):
+    """MAX_RAY_DEPTH (pathtracer.py:17) is a parameter here; depth 1 = direct light only."""
+    R = 32
+    g, o = make_pair(vrt, oracle, image_res=(64, 32), grid_res=R, max_depth=depth)
+    both = (g, o)
+    apply_both(both, "set_voxels", *scenes.random_grid(R, 0.3, 5, materials=(1, 50, 21)))
+    apply_both(both, "set_directional_light", (1, 1, 1), 0.1, (1, 1, 1))
+    apply_both(both, "set_background_color", (0.4, 0.5, 0.6))
+    apply_both(both, "prepare_data")
+    g.accumulate(8, stats=True)
+    o.accumulate(8, stats=True)
+    _check_radiance(g, o, tol_rmse=0.05, frac_close=0.93)
+    assert g.stats()["rays"] <= 2 * depth * g.stats()["paths"]
+
+
+def test_axis_parallel_camera_rays(vrt, oracle):
+    """Camera looking exactly down -z from the box centre line: the centre column of pixels has
+    d.x == 0 exactly (components with d == 0 never limit the step)."""
+    R = 32
+    g, o = make_pair(vrt, oracle, image_res=(64, 64), grid_res=R, jitter=False)
+    mat, col = scenes.random_grid(R, 0.1, 8)
+    both = (g, o)
+    apply_both(both, "set_voxels", mat, col)
+    apply_both(both, "set_camera_pos", 0.0, 0.0, 2.5)
+    apply_both(both, "set_look_at", 0.0, 0.0, 0.0)
+    apply_both(both, "set_floor", -1e5, (1.0, 1.0, 1.0))
+    apply_both(both, "prepare_data")
+    _hits_equal(g.trace_primary(), o.trace_primary())
+
+
+def test_c_abi_error_paths_on_device(vrt):
+    """Error behaviour through the C-ABI: accumulate before prepare, bad shard arguments."""
+    g = vrt.Renderer(dx=2.0 / 32, image_res=(64, 32), grid_res=32, sky_res=0)
+    with pytest.raises(RuntimeError, match="vrt_upload_voxels"):
+        g.prepare_data()
+    g.set_voxels(*scenes.empty(32))
+    with pytest.raises(RuntimeError, match="vrt_prepare"):
+        g.accumulate(1)
+    with pytest.raises(RuntimeError, match="rank"):
+        g.set_tile_shard(3, 2)
+    with pytest.raises(RuntimeError, match="sky_res = 0"):
+        g.set_use_physical_sky(True)
+    g.prepare_data()
+    g.accumulate(1)
+    assert g.fetch_hdr()[..., 3].min() == 1.0
