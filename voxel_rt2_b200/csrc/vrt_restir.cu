@@ -111,7 +111,10 @@ HD void load_reservoir(const uint2* __restrict__ base, size_t pidx, const float*
   decode_reservoir(w, unorm8, r);
 }
 
-__global__ void __launch_bounds__(128) k_gris(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int upper_in_smem, int fixed_words) {
+#ifndef VRT_GRIS_MIN_BLOCKS
+#define VRT_GRIS_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int upper_in_smem, int fixed_words) {
   extern __shared__ uint32_t smem[];
   // same staging layout as the render kernels: materials, UNORM8 table, upper pyramid
   float4* s_mats = reinterpret_cast<float4*>(smem);
