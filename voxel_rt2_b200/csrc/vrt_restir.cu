@@ -179,15 +179,26 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
       const int tu = u + ox, tv = v + oy;
       if (tu < 0 || tv < 0 || tu >= W || tv >= H) continue;
       const size_t ti = (size_t)tv * W + tu;
+      // issue every load of the tap up front (G-buffer record + 56-byte reservoir): one memory
+      // round trip per tap instead of three dependent ones
       const float4 ngp = __ldg(RB.gpos + ti);
-      if (ngp.w != 0.0f) continue;
       const uint2 nga = __ldg(RB.gattr + ti);
+      uint32_t nw[14];
+      {
+        const uint2* src = RB.reservoirs + ti * 7;
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+          const uint2 t = __ldg(src + q);
+          nw[2 * q] = t.x, nw[2 * q + 1] = t.y;
+        }
+      }
+      if (ngp.w != 0.0f) continue;
       const f3 neighbour_n1 = decode_unit_vector_3x16(h16val(nga.x), h16val(nga.x >> 16));
       const f3 neighbour_x1{ngp.x, ngp.y, ngp.z};
       const float neighbour_dist = length(neighbour_x1 - P.cam_pos);
       if (fabsf(neighbour_dist - center_dist) > 0.1f * center_dist || dot(center_n1, neighbour_n1) < 0.5f) continue;
       RReservoir nb;
-      load_reservoir(RB.reservoirs, ti, s_unorm, nb);
+      decode_reservoir(nw, s_unorm, nb);
       int neighbour_mat_id;
       const Mat neighbour_mat = decode_material(G, nga.y, neighbour_mat_id);
       f3 c_d, c_s, s_d, s_s;

@@ -44,23 +44,19 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
   if (STATS) tc->rays++;
 
   // ray_aabb_intersection against [0,R]^3 (axes with d == 0 are skipped, as in the reference).
-  // The three exit-side quotients are always needed (far_int). The three entry-side quotients
-  // only matter when the origin is outside the box: inside, each of them is <= 0, so near_int
-  // <= 0 < eps and max(near_int, eps) == eps whatever its value -> those divisions are skipped
-  // (same bits; never more than the original six divisions per ray even in a mixed warp).
+  // (Skipping the three entry-side divisions for origins inside the box is exact but was measured
+  // 6 % slower: primary and secondary rays share warps, so both variants execute.)
   float near_int = -VRT_INF, far_int = VRT_INF;
   {
     const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
-    const bool inside = o.x > 0.0f && o.x < Rf && o.y > 0.0f && o.y < Rf && o.z > 0.0f && o.z < Rf;
 #pragma unroll
-    for (int i = 0; i < 3; i++)
-      if (dd[i] != 0.0f) far_int = fminf(xdiv(xsub(dd[i] > 0.0f ? Rf : 0.0f, oo[i]), dd[i]), far_int);
-    if (inside) {
-      near_int = 0.0f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-        if (dd[i] != 0.0f) near_int = fmaxf(xdiv(xsub(dd[i] > 0.0f ? 0.0f : Rf, oo[i]), dd[i]), near_int);
+    for (int i = 0; i < 3; i++) {
+      if (dd[i] != 0.0f) {
+        float i1 = xdiv(xsub(0.0f, oo[i]), dd[i]);
+        float i2 = xdiv(xsub(Rf, oo[i]), dd[i]);
+        far_int = fminf(fmaxf(i1, i2), far_int);
+        near_int = fmaxf(fminf(i1, i2), near_int);
+      }
     }
   }
   if (!(near_int <= far_int && VRT_EPS < far_int && near_int < VRT_INF)) {
@@ -201,10 +197,8 @@ HD Hit next_hit(const Params& P, const uint32_t* __restrict__ upper, const float
   h.kind = 0;
   h.cx = h.cy = h.cz = -1;
   // floor: dist = (h - p.y)/d.y ; accept if eps < dist and |(x-y, 0, z-y)| < 10   
-  const float floor_dy = xsub(P.floor_height, pos.y);
-  // the quotient must exceed eps: skip the division unless numerator and denominator agree in sign
-  if ((floor_dy > 0.0f && d.y > 0.0f) || (floor_dy < 0.0f && d.y < 0.0f)) {
-    float dist = xdiv(floor_dy, d.y);
+  {
+    float dist = xdiv(xsub(P.floor_height, pos.y), d.y);
     if (dist > VRT_EPS && dist < h.closest) {
       float hx = xadd(pos.x, xmul(d.x, dist)), hy = xadd(pos.y, xmul(d.y, dist)), hz = xadd(pos.z, xmul(d.z, dist));
       float dn = xadd(xadd(xmul(hx, 0.0f), xmul(hy, 1.0f)), xmul(hz, 0.0f));
