@@ -376,3 +376,44 @@ def test_c_abi_error_paths_on_device(vrt):
     g.prepare_data()
     g.accumulate(1)
     assert g.fetch_hdr()[..., 3].min() == 1.0
+
+
+def test_scene_api_end_to_end_on_gpu(vrt, oracle, tmp_path, monkeypatch):
+    """The reference-facing path a user takes: Scene(...) -> set_* -> finish() (headless), on the
+    example6 fixture scene with the physical sky, checked against the oracle driven the same way."""
+    import os
+
+    from voxel_rt2_b200.scene import Scene
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example6_seed0.npz"))
+    monkeypatch.setenv("VRT_RES", "256x144")
+    monkeypatch.setenv("VRT_SKY_RES", "64")
+    monkeypatch.setenv("VRT_SEED", "3")
+    monkeypatch.delenv("VRT_SKY_CACHE", raising=False)
+    s = Scene(voxel_edges=0, exposure=2.0)                        # example6.py:7
+    s.voxel_material[:] = z["material"]
+    s.voxel_color[:] = z["color"]
+    s.set_floor(-0.85, (1.0, 1.0, 1.0))                           # example6.py:8
+    s.set_directional_light((1, 1, -1), 0.025, (1.3, 0.949 * 1.3, 0.937 * 1.3))
+    s.set_use_physical_sky(True)
+    s.set_use_clouds(True)
+    out = tmp_path / "example6.png"
+    img = s.finish(spp=8, out=str(out))
+    assert out.exists() and img.shape == (144, 256, 4)
+    assert 0.2 < float(img[..., :3].mean()) < 0.9
+    from voxel_rt2_b200.materials import material_table
+
+    tex = np.load(os.path.join(os.path.dirname(vrt.__file__), "assets", "cloud_texture.npz"))["tex"]
+    o = oracle.OracleRenderer(dx=2.0 / 128, image_res=(256, 144), grid_res=128, voxel_edges=0, exposure=2.0, sky_res=64, seed=3,
+                              materials=material_table(), cloud_tex=tex)
+    o.set_voxels(z["material"], z["color"])
+    o.set_floor(-0.85, (1.0, 1.0, 1.0))
+    o.set_directional_light((1, 1, -1), 0.025, (1.3, 0.949 * 1.3, 0.937 * 1.3))
+    o.set_use_physical_sky(True, True)
+    o.set_sky_tables(*s.renderer.get_sky_tables())
+    o.prepare_data()
+    o.accumulate(8)
+    ldr_o = o.fetch_image()
+    close = np.mean(np.abs(img[..., :3] - ldr_o[..., :3]).max(axis=-1) < 2e-3)
+    print("Scene.finish vs oracle: fraction of LDR pixels within 2e-3: %.4f" % close)
+    assert close > 0.97

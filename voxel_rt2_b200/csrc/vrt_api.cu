@@ -173,6 +173,7 @@ static void fill_params(const vrt_ctx* ctx, Params& P) {
   memcpy(P.inv_proj, ctx->inv_proj, sizeof P.inv_proj);
   memcpy(P.inv_view, ctx->inv_view, sizeof P.inv_view);
   P.W = c.width, P.H = c.height;
+  P.inv_w = 1.0f / (float)c.width, P.inv_h = 1.0f / (float)c.height;
   P.sky_scatter = ctx->d_sky_scatter, P.sky_trans = ctx->d_sky_trans, P.sky_res = c.sky_res;
   P.mats = ctx->d_mats;
   P.accum = ctx->d_accum;

@@ -150,6 +150,7 @@ struct Params {
   f3 cam_pos;
   float inv_proj[16], inv_view[16];
   int W, H;
+  float inv_w, inv_h;  // 1.0f / W, 1.0f / H (IEEE division on the host, same bits as on the device)
   // sky tables, float4 texels, [x][y] with y fastest
   const float4* sky_scatter;
   const float4* sky_trans;

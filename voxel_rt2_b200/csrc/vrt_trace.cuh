@@ -255,19 +255,19 @@ HD Hit next_hit(const Params& P, const uint32_t* __restrict__ upper, const float
 
 // pathtracer.py:293-312 + space_transformations.py:14-30, render_scale = 1, static camera.
 HD f3 get_cast_dir(const Params& P, float u, float v, float jx, float jy) {
-  float tx = xadd(xmul(xadd(u, 0.5f), xdiv(1.0f, (float)P.W)), xmul(jx, 0.5f));
-  float ty = xadd(xmul(xadd(v, 0.5f), xdiv(1.0f, (float)P.H)), xmul(jy, 0.5f));
-  float p[4] = {xsub(xmul(tx, 2.0f), 1.0f), xsub(xmul(ty, 2.0f), 1.0f), 1.0f, 1.0f};
+  float tx = xadd(xmul(xadd(u, 0.5f), P.inv_w), xmul(jx, 0.5f));
+  float ty = xadd(xmul(xadd(v, 0.5f), P.inv_h), xmul(jy, 0.5f));
+  const float px = xsub(xmul(tx, 2.0f), 1.0f), py = xsub(xmul(ty, 2.0f), 1.0f);
+  // inv_proj @ (px, py, 1, 1): the two products by 1.0f are exact and dropped (same bits)
   float q[4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
-    q[i] = xadd(xadd(xadd(xmul(P.inv_proj[i * 4 + 0], p[0]), xmul(P.inv_proj[i * 4 + 1], p[1])), xmul(P.inv_proj[i * 4 + 2], p[2])),
-                xmul(P.inv_proj[i * 4 + 3], p[3]));
+    q[i] = xadd(xadd(xadd(xmul(P.inv_proj[i * 4 + 0], px), xmul(P.inv_proj[i * 4 + 1], py)), P.inv_proj[i * 4 + 2]), P.inv_proj[i * 4 + 3]);
   f3 dv = xnormalize(f3{xdiv(q[0], q[3]), xdiv(q[1], q[3]), xdiv(q[2], q[3])});
+  // inv_view @ (dv, 0): the product by 0 contributes +-0 and is dropped
   float w[3];
 #pragma unroll
   for (int i = 0; i < 3; i++)
-    w[i] = xadd(xadd(xadd(xmul(P.inv_view[i * 4 + 0], dv.x), xmul(P.inv_view[i * 4 + 1], dv.y)), xmul(P.inv_view[i * 4 + 2], dv.z)),
-                xmul(P.inv_view[i * 4 + 3], 0.0f));
+    w[i] = xadd(xadd(xmul(P.inv_view[i * 4 + 0], dv.x), xmul(P.inv_view[i * 4 + 1], dv.y)), xmul(P.inv_view[i * 4 + 2], dv.z));
   return f3{w[0], w[1], w[2]};
 }
