@@ -47,20 +47,33 @@ def parse():
     ap.add_argument("--res", default="1920x1080")
     ap.add_argument("--sky-res", type=int, default=3840)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config3", choices=["config3", "config2", "config4"],
+                    help="config3 (default, the bench line): dense random grid; config2: example6 fixture scene, sky + clouds; "
+                         "config4: ReSTIR mode (render + spatial GRIS per frame) on the example6 scene")
     ap.add_argument("--cpu-spp", type=int, default=48, help="samples per pixel of the bounded CPU-baseline sample")
     return ap.parse_args()
+
+
+WORKLOAD = "config3"
 
 
 def build_scene(R):
     import scenes
 
-    return scenes.random_grid(R, 0.5, 1234)
+    if WORKLOAD == "config3":
+        return scenes.random_grid(R, 0.5, 1234)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "example6_seed0.npz"))  # example6.py run through the shim, seed 0
+    return z["material"], z["color"]
 
 
 def configure(r, R, mat, col, sky=True):
     r.set_voxels(mat, col)
-    r.set_floor(-1e5, (1.0, 1.0, 1.0))  # floor disabled as example9.py:4 does
-    r.set_directional_light(*SUN)
+    if WORKLOAD == "config3":
+        r.set_floor(-1e5, (1.0, 1.0, 1.0))  # floor disabled as example9.py:4 does
+        r.set_directional_light(*SUN)
+    else:
+        r.set_floor(-0.85, (1.0, 1.0, 1.0))                   # example6.py:8
+        r.set_directional_light((1, 1, -1), SUN[1], SUN[2])    # example6.py:10
     if sky:
         r.set_use_physical_sky(True, True)
 
@@ -180,7 +193,13 @@ def run_reference(args, rank, world):
 
 
 def main():
+    global WORKLOAD
     args = parse()
+    WORKLOAD = args.workload
+    if WORKLOAD != "config3":
+        args.grid = 128
+    if WORKLOAD == "config4":
+        args.spp = 1  # ReSTIR mode renders one sample per frame
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -224,7 +243,10 @@ def main():
         with torch.cuda.stream(stream):
             if world > 1:
                 r.reset_framebuffer()
-            r.accumulate(spp)
+            if WORKLOAD == "config4":
+                r.accumulate_restir(spp)
+            else:
+                r.accumulate(spp)
             if world > 1:
                 dist.all_reduce(accum)  # one NCCL all-reduce of the accumulation buffer per step
 
@@ -246,7 +268,7 @@ def main():
     for _ in range(args.steps):
         step()
         s = r.stats()
-        kernel_ms.append(s["last_render_ms"])
+        kernel_ms.append(s["last_render_ms"] + (s["last_gris_ms"] if WORKLOAD == "config4" else 0.0))
         launches += s["kernel_launches"]
     ev1.record(stream)
     barrier()
@@ -270,7 +292,10 @@ def main():
             r.set_view_proj(pos, view, proj)
             if world > 1:
                 r.reset_framebuffer()
-            r.accumulate(spp)
+            if WORKLOAD == "config4":
+                r.accumulate_restir(spp)
+            else:
+                r.accumulate(spp)
             if world > 1:
                 dist.all_reduce(accum)
             r._check(r._lib.vrt_fetch_ldr(r._h, host_img.ctypes.data_as(C.POINTER(C.c_float))))
@@ -309,7 +334,9 @@ def main():
             "metric": "paths_per_sec_depth4_1080p", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_frame": ms_total / args.steps / spp,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config3: dense random %d^3 (50%% occupancy), %dx%d, depth 4, physical sky + clouds, sun (1,1,1)" % (R, W, H),
+            "config": {"workload": {"config3": "config3: dense random %d^3 (50%% occupancy), %dx%d, depth 4, physical sky + clouds, sun (1,1,1)" % (R, W, H),
+                                    "config2": "config2: example6 scene (shim seed 0) %d^3, %dx%d, depth 4, physical sky + clouds" % (R, W, H),
+                                    "config4": "config4: ReSTIR mode (render + spatial GRIS 32 taps) on the example6 scene %d^3, %dx%d" % (R, W, H)}[WORKLOAD],
                        "spp_per_step_per_gpu": spp, "sky_res": args.sky_res, "parallelism": "sample-shard x%d + 1 all-reduce/step" % world,
                        "l2": "inputs>L2 (sky tables 2x%d MB + colour %d MB)" % (args.sky_res ** 2 * 16 // 2 ** 20, R ** 3 * 4 // 2 ** 20),
                        "sky_precompute_ms": sky_ms, "prepare_s": t_prep},
@@ -323,7 +350,10 @@ def main():
                     "ms_per_step": 1e3 * e2e_s / n_e2e, "call": "set_view_proj + accumulate(spp) + fetch_image -> pinned host"},
             "gpu_launches": launches,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if WORKLOAD == "config4":
+            line["roofline"]["kernel"] = "k_path<restir> + k_gris"
+            line["roofline"]["note"] = "bytes_per_path counts the path kernel only; GRIS adds 32 x 80 B of (L2-resident) tap reads per pixel"
+        if not args.no_cpu_baseline and world == 1 and WORKLOAD != "config4":
             try:
                 sky_tables = r.get_sky_tables()
                 cb = cpu_sample(args, W, H, R, mat, col, sky_tables, args.cpu_spp)

@@ -142,7 +142,7 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
     float tx = xmul(d.x > 0.0f ? xsub(cell_size, fx) : fx, ivx);
     float ty = xmul(d.y > 0.0f ? xsub(cell_size, fy) : fy, ivy);
     float tz = xmul(d.z > 0.0f ? xsub(cell_size, fz) : fz, ivz);
-    if (d.x == 0.0f) tx = VRT_INF;  // pinned, SURVEY A4
+    if (d.x == 0.0f) tx = VRT_INF;  // pinned, SURVEY A4 (also covers origins outside the slab of that axis)
     if (d.y == 0.0f) ty = VRT_INF;
     if (d.z == 0.0f) tz = VRT_INF;
     const float min_t = fminf(fminf(tx, ty), tz);
