@@ -129,6 +129,14 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
  * spatial_GRIS(0, 24.0, 32, 1) (pathtracer.py:815-989) resamples 32 neighbours; the frame is then
  * accumulated like a path-traced one. n_frames frames with sample indices first, first+stride... */
 int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, int32_t stride);
+/* Renderer.accumulate with camera_is_moving = 1 (scene.py:214-228, pathtracer.py:146-150): one
+ * frame rendered at render_scale (reference 0.5) with albedo-demodulated diffuse, then
+ * temporal_filter_prepass / temporal_filter / temporal_filter_specular (pathtracer.py:1020-1303)
+ * reprojecting the history of the previous moving frame with the previous camera matrices, then
+ * copy_prev_matrices (pathtracer.py:284-287). max_accum = set_max_samples (reference 50 while
+ * moving). vrt_fetch_hdr / vrt_fetch_ldr afterwards return this path's colour buffer, nearest
+ * up-sampled as _render_to_image does; vrt_reset (reset_framebuffer) drops the history. */
+int vrt_accumulate_moving(vrt_ctx* ctx, int32_t sample, float render_scale, float max_accum);
 /* Packed reservoirs of the last ReSTIR frame: 56 bytes per pixel, row-major (reservoir.py:8-19
  * field order; byte 55 carries the escape / last-vertex / NEE-visible flags). */
 int vrt_get_reservoirs(vrt_ctx* ctx, void* out56_per_pixel);

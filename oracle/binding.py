@@ -59,6 +59,9 @@ def load():
     lib.orc_oct_round_trip.argtypes = [C.c_int, fp, fp, fp]
     lib.orc_hash3.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
     lib.orc_hash3.restype = C.c_uint32
+    lib.orc_accumulate_moving.argtypes = [P, C.c_int, C.c_float, C.c_float]
+    lib.orc_fetch_hdr_moving.argtypes = [P, fp]
+    lib.orc_reset_moving.argtypes = [P]
     lib.orc_last_ms.argtypes = [P]
     lib.orc_last_ms.restype = C.c_double
     lib.orc_reset.argtypes = [P]
@@ -248,6 +251,18 @@ class OracleRenderer:
         self._lib.orc_accumulate_restir(self._h, first, int(frames), self.sample_stride, int(self.n_threads))
         self.current_spp += int(frames)
 
+    def accumulate_moving(self, render_scale=0.5, max_accum=50.0):
+        """One frame of accumulate() with camera_is_moving = 1 (scene.py:214-228): half-resolution
+        render, reprojected temporal filters, copy_prev_matrices."""
+        self._sync_camera()
+        self._lib.orc_accumulate_moving(self._h, self.sample_offset + self.current_spp * self.sample_stride, float(render_scale), float(max_accum))
+        self.current_spp += 1
+
+    def fetch_hdr_moving(self):
+        out = np.empty((self.image_res[1], self.image_res[0], 4), np.float32)
+        self._lib.orc_fetch_hdr_moving(self._h, _fp(out))
+        return out
+
     def get_reservoirs(self):
         out = np.empty((self.image_res[1], self.image_res[0], 56), np.uint8)
         self._lib.orc_get_reservoirs(self._h, out.ctypes.data_as(C.c_void_p))
@@ -259,6 +274,7 @@ class OracleRenderer:
     def reset_framebuffer(self):
         self.current_spp = 0
         self._lib.orc_reset(self._h)
+        self._lib.orc_reset_moving(self._h)
 
     def fetch_hdr(self):
         out = np.empty((self.image_res[1], self.image_res[0], 4), np.float32)

@@ -45,6 +45,17 @@ struct Ctx {
   std::vector<StorageReservoir> reservoirs;
   std::vector<GBufferPx> gbuf;
   std::vector<V3> col_d, col_s;
+  // moving-camera temporal path (pathtracer.py:993-1303): G-buffer, previous G-buffer, two
+  // history slots for diffuse / specular / reflection depth, previous matrices
+  struct Moving {
+    std::vector<V3> col_d, col_s, out;
+    std::vector<float> depth, refl, refl_blur, prev_depth, noct, prev_noct, hd[2], hs[2], hsd[2];
+    std::vector<uint32_t> mat;
+    float prev_view[16], prev_proj[16];
+    V3 prev_cam{0, 0, 0};
+    bool has_prev = false, active = false;
+    float scale = 1.0f;
+  } mv;
 };
 
 static const float RADIANCE_CLAMP = 300.0f;  // pathtracer.py:20
@@ -66,12 +77,19 @@ static inline const Mat& mat_at(const Ctx& c, int id) { return c.mats[id < 0 ? 0
 struct PathOut {
   V3 diffuse, specular;
 };
+struct GExtra {  // primary-vertex data the moving-camera temporal filters need (pathtracer.py:535-546)
+  V3 primary_pos{0, 0, 0}, primary_normal{0, 0, 0}, primary_albedo{1, 1, 1};
+  uint32_t mat_info = 0;
+  float first_bounce_reflection_dist = 0.0f;
+  bool sky = false;
+};
 
 // pathtracer.py:355-632 for one pixel sample, USE_RESTIR_PT = False, static camera.
-static void trace_path(const Ctx& c, int u, int v, uint32_t sample, Counters* cnt, PathOut& out) {
+static void trace_path(const Ctx& c, int u, int v, uint32_t sample, Counters* cnt, PathOut& out, GExtra* gx = nullptr,
+                       float render_scale = 1.0f) {
   const Scene& s = c.scene;
   const uint32_t key = path_key((uint32_t)(v * s.W + u), sample, c.seed);
-  V3 d = get_cast_dir(s, (float)u, (float)v);
+  V3 d = get_cast_dir(s, (float)u, (float)v, render_scale, gx != nullptr);
   V3 pos = s.cam_pos;
   V3 contrib{0, 0, 0}, throughput{1, 1, 1};
   uint32_t primary_mat_info = 0;
@@ -88,6 +106,13 @@ static void trace_path(const Ctx& c, int u, int v, uint32_t sample, Counters* cn
     Mat hit_mat = mat_at(c, h.mat_id);
     V3 hit_pos = pos + h.closest * d;
     if (depth == 0) primary_mat_info = encode_material(h.mat_id, h.albedo);
+    if (gx) {
+      if (depth == 0) {
+        gx->primary_pos = hit_pos, gx->primary_normal = h.normal, gx->primary_albedo = h.albedo, gx->mat_info = primary_mat_info;
+      } else if (depth == 1 && first_bounce_lobe_id != LOBE_DIFFUSE) {
+        gx->first_bounce_reflection_dist += h.closest;  // pathtracer.py:410-412
+      }
+    }
 
     if (!h.hit_light && h.closest < kInf) {
       if (cnt) cnt->vertices++;
@@ -154,7 +179,10 @@ static void trace_path(const Ctx& c, int u, int v, uint32_t sample, Counters* cn
         }
         V3 sky_emission = firefly_filter(sky_scattering + sky_T * s.light_weight * s.light_color * hit_sun);
         contrib += throughput * sky_emission;
-        if (depth == 0) is_sky_ray = true;
+        if (depth == 0) {
+          is_sky_ray = true;
+          if (gx) gx->primary_pos = V3{0, 0, 0}, gx->sky = true;
+        }
       } else {
         if (depth > 0) contrib += throughput * h.albedo;
       }
@@ -838,6 +866,229 @@ void orc_oct_round_trip(int n, const float* v, float* enc, float* dec) {
   }
 }
 uint32_t orc_hash3(uint32_t x, uint32_t y, uint32_t z) { return hash3(x, y, z); }
+// ------------------------------------------------------------------ moving-camera temporal path
+// Renderer.accumulate() with camera_is_moving = 1 (scene.py:214-228): render at render_scale with
+// albedo-demodulated diffuse (pathtracer.py:628-630), temporal_filter_prepass (:1020-1075),
+// temporal_filter (:1185-1230) and temporal_filter_specular (:1242-1303) with reprojection into the
+// previous frame, Catmull-Rom 4x4 history fetch (:1092-1183) and depth / normal rejection, then
+// copy_prev_matrices (:284-287). Pins: the prepass blur reads pre-blur reflection depths (the
+// reference reads and writes gbuff_depth_reflection in place: a race); non-finite reflection
+// distances count as "no reflection"; buffer reads are clamped to the image; sky pixels store a
+// zero normal code.
+static inline float catmullrom(float x) {  // pathtracer.py:1002-1013
+  float x2 = x * x, x3 = x * x * x, fx = 0.0f;
+  if (x < 1.0f)
+    fx = 1.5f * x3 - 2.5f * x2 + 1.0f;
+  else if (x < 2.0f)
+    fx = -0.5f * x3 + 2.5f * x2 - 4.0f * x + 2.0f;
+  return fx;
+}
+struct V4 {
+  float x, y, z, w;
+};
+static inline V4 ld4(const std::vector<float>& b, size_t i) { return V4{b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]}; }
+static inline void st4(std::vector<float>& b, size_t i, V4 v) { b[4 * i] = v.x, b[4 * i + 1] = v.y, b[4 * i + 2] = v.z, b[4 * i + 3] = v.w; }
+
+static V3 mv_bilinear(const Ctx& c, const std::vector<V3>& buf, float uvx, float uvy, int irx, int iry) {  // :1077-1090
+  const int W = c.scene.W, H = c.scene.H;
+  float fx = uvx * (float)irx - 0.5f, fy = uvy * (float)iry - 0.5f;
+  int ix = (int)fx, iy = (int)fy;
+  float wx = fractf(fx), wy = fractf(fy);
+  auto at = [&](int x, int y) {
+    x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
+    y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+    return buf[(size_t)y * W + x];
+  };
+  return mix3(mix3(at(ix, iy), at(ix + 1, iy), wx), mix3(at(ix, iy + 1), at(ix + 1, iy + 1), wx), wy);
+}
+static V3 mv_reproject(const Ctx& c, V3 world_pos) {  // :991-998
+  float a[4] = {world_pos.x, world_pos.y, world_pos.z, 1.0f}, b[4], q[4];
+  mat4_mul(c.mv.prev_view, a, b);
+  mat4_mul(c.mv.prev_proj, b, q);
+  return V3{q[0] / q[3] * 0.5f + 0.5f, q[1] / q[3] * 0.5f + 0.5f, q[2] / q[3] * 0.5f + 0.5f};
+}
+// history_filter (:1092-1130) and history_filter_specular (:1132-1183) in one routine
+static float mv_history(const Ctx& c, bool specular, float uvx, float uvy, float center_depth, V3 center_normal, int irx, int iry, V4& col_out,
+                        float& depth_out) {
+  const Scene& s = c.scene;
+  const auto& m = c.mv;
+  col_out = V4{0, 0, 0, 1};
+  depth_out = 0.0f;
+  if (!(std::isfinite(uvx) && std::isfinite(uvy)) || std::fabs(uvx) > 1e6f || std::fabs(uvy) > 1e6f) return 0.0f;
+  float fx = uvx * (float)irx - 0.5f, fy = uvy * (float)iry - 0.5f;
+  int ix = (int)fx, iy = (int)fy;
+  float ffx = fractf(fx), ffy = fractf(fy);
+  V4 sum{0, 0, 0, 0}, cmax{0, 0, 0, 0}, cmin{999999.0f, 999999.0f, 999999.0f, 999999.0f};
+  float dsum = 0.0f, dmax = 0.0f, dmin = 999999.0f, wsum = 0.0f;
+  for (int x = -1; x < 3; x++)
+    for (int y = -1; y < 3; y++) {
+      int tx = ix + x, ty = iy + y;
+      if (tx < 0 || ty < 0 || tx > irx - 1 || ty > iry - 1) continue;
+      size_t ti = (size_t)ty * s.W + tx;
+      float w = catmullrom(std::fabs((float)x - ffx)) * catmullrom(std::fabs((float)y - ffy));
+      V3 tap_normal = decode_unit_vector_3x16(m.prev_noct[2 * ti], m.prev_noct[2 * ti + 1]);
+      if (!specular) {
+        float tap_depth = linearize_depth(m.prev_depth[ti], s.inv_proj);
+        w *= std::fabs(tap_depth - center_depth) / center_depth < 0.05f ? 1.0f : 0.0f;
+      }
+      w *= dot(center_normal, tap_normal) > 0.642f ? 1.0f : 0.0f;
+      V4 col = ld4(specular ? m.hs[0] : m.hd[0], ti);
+      cmax = V4{fmaxf_(cmax.x, col.x), fmaxf_(cmax.y, col.y), fmaxf_(cmax.z, col.z), fmaxf_(cmax.w, col.w)};
+      cmin = V4{fminf_(cmin.x, col.x), fminf_(cmin.y, col.y), fminf_(cmin.z, col.z), fminf_(cmin.w, col.w)};
+      sum = V4{sum.x + col.x * w, sum.y + col.y * w, sum.z + col.z * w, sum.w + col.w * w};
+      if (specular) {
+        float rd = m.hsd[0][ti];
+        dmin = fminf_(dmin, rd), dmax = fmaxf_(dmax, rd);
+        dsum += rd * w;
+      }
+      wsum += w;
+    }
+  sum = V4{sum.x / wsum, sum.y / wsum, sum.z / wsum, sum.w / wsum};
+  dsum /= wsum;
+  col_out = V4{fmaxf_(clampf(sum.x, cmin.x, cmax.x), 0.0f), fmaxf_(clampf(sum.y, cmin.y, cmax.y), 0.0f), fmaxf_(clampf(sum.z, cmin.z, cmax.z), 0.0f),
+               fmaxf_(clampf(sum.w, cmin.w, cmax.w), 1.0f)};
+  depth_out = clampf(dsum, dmin, dmax);
+  return wsum;
+}
+
+void orc_accumulate_moving(void* p, int sample, float render_scale, float max_accum) {
+  Ctx* c = (Ctx*)p;
+  Scene& s = c->scene;
+  auto& m = c->mv;
+  const int W = s.W, H = s.H;
+  const size_t npx = (size_t)W * H;
+  if (m.depth.size() != npx) {
+    m.col_d.assign(npx, V3{0, 0, 0}), m.col_s.assign(npx, V3{0, 0, 0}), m.out.assign(npx, V3{0, 0, 0});
+    m.depth.assign(npx, 0.0f), m.refl.assign(npx, 0.0f), m.refl_blur.assign(npx, 0.0f), m.prev_depth.assign(npx, 0.0f);
+    m.noct.assign(2 * npx, 0.0f), m.prev_noct.assign(2 * npx, 0.0f), m.mat.assign(npx, 0u);
+    for (int k = 0; k < 2; k++) m.hd[k].assign(4 * npx, 0.0f), m.hs[k].assign(4 * npx, 0.0f), m.hsd[k].assign(npx, 0.0f);
+  }
+  if (!m.has_prev) {
+    std::copy(s.view, s.view + 16, m.prev_view), std::copy(s.proj, s.proj + 16, m.prev_proj);
+    m.prev_cam = s.cam_pos, m.has_prev = true;
+  }
+  m.scale = render_scale, m.active = true;
+  s.jitter[0] = s.jitter[1] = 0.0f;
+  const int irx = (int)((float)W * render_scale), iry = (int)((float)H * render_scale);
+  auto outside = [&](int u, int v) { return (float)u > render_scale * (float)W || (float)v > render_scale * (float)H; };  // :289-291
+  // ---- render
+#pragma omp parallel for schedule(dynamic, 2)
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      if (outside(u, v)) continue;
+      const size_t i = (size_t)v * W + u;
+      PathOut o;
+      GExtra g;
+      trace_path(*c, u, v, (uint32_t)sample, nullptr, o, &g, render_scale);
+      m.depth[i] = view_to_screen(xform_point(s.view, g.primary_pos, 1.0f), s.proj).z;
+      m.noct[2 * i] = m.noct[2 * i + 1] = 0.0f;
+      if (!g.sky) encode_unit_vector_3x16(g.primary_normal, m.noct[2 * i], m.noct[2 * i + 1]);
+      m.mat[i] = g.mat_info;
+      const float rd = g.first_bounce_reflection_dist;
+      float refl = 0.0f;
+      if (rd != 0.0f && std::isfinite(rd)) {
+        V3 primary_dir = normalize(g.primary_pos - s.cam_pos);
+        V3 virtual_point = g.primary_pos + primary_dir * rd;
+        refl = linearize_depth(view_to_screen(xform_point(s.view, virtual_point, 1.0f), s.proj).z, s.inv_proj);
+      }
+      m.refl[i] = refl;
+      V3 diffuse = o.diffuse / max3(g.primary_albedo, 1e-2f);  // de-modulate albedo (:628-630)
+      m.col_d[i] = diffuse, m.col_s[i] = o.specular;
+    }
+    // ---- temporal_filter_prepass
+#pragma omp parallel for schedule(static)
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      if (outside(u, v)) continue;
+      const size_t i = (size_t)v * W + u;
+      float sum = 0.0f, valid = 0.0f;
+      for (int x = -1; x < 3; x++)
+        for (int y = -1; y < 3; y++) {
+          int tx = u + x, ty = v + y;
+          if (tx < 0 || ty < 0 || tx > irx - 1 || ty > iry - 1) continue;
+          float r = m.refl[(size_t)ty * W + tx];
+          if (r != 0.0f) valid += 1.0f, sum += r;
+        }
+      m.refl_blur[i] = valid > 0.01f ? sum / valid : 0.0f;
+      if (bad3(m.col_d[i])) m.col_d[i] = V3{0, 0, 0};
+      if (bad3(m.col_s[i])) m.col_s[i] = V3{0, 0, 0};
+    }
+    // ---- temporal_filter + temporal_filter_specular
+#pragma omp parallel for schedule(dynamic, 2)
+  for (int v = 0; v < H; v++)
+    for (int u = 0; u < W; u++) {
+      if (outside(u, v)) continue;
+      const size_t i = (size_t)v * W + u;
+      m.out[i] = m.col_d[i];
+      const float tcx = ((float)u + 0.5f) * (1.0f / (float)W) / render_scale, tcy = ((float)v + 0.5f) * (1.0f / (float)H) / render_scale;
+      const float d_nl = m.depth[i];
+      const V3 center_n1 = decode_unit_vector_3x16(m.noct[2 * i], m.noct[2 * i + 1]);
+      const V3 center_x1 = xform_point(s.inv_view, screen_to_view(tcx, tcy, d_nl, s.inv_proj), 1.0f);
+      if (is_vec_zero(center_x1)) continue;
+      {  // diffuse
+        V3 current = mv_bilinear(*c, m.col_d, tcx, tcy, irx, iry);
+        V3 rp = mv_reproject(*c, center_x1);
+        V4 history;
+        float dummy;
+        float w_sum = mv_history(*c, false, rp.x, rp.y, linearize_depth(rp.z, s.inv_proj), center_n1, irx, iry, history, dummy);
+        if (w_sum > 1e-3f) {
+          history.w = fminf_(history.w + 1.0f, max_accum);
+          float t = 1.0f / history.w;
+          history.x = mixf(history.x, current.x, t), history.y = mixf(history.y, current.y, t), history.z = mixf(history.z, current.z, t);
+        } else {
+          history = V4{current.x, current.y, current.z, 1.0f};
+        }
+        st4(m.hd[1], i, history);
+        Mat cm;
+        int cid;
+        decode_material(*c, m.mat[i], cm, cid);
+        m.out[i] = V3{history.x, history.y, history.z} * cm.base_col;  // re-modulate albedo (:1227-1228)
+      }
+      {  // specular, reprojected through the virtual reflection point (:1251-1265)
+        const float center_refl_depth = m.refl_blur[i];
+        const float refl_nl = delinearize_depth(center_refl_depth, s.proj);
+        const V3 center_refl_pos = xform_point(s.inv_view, screen_to_view(tcx, tcy, refl_nl, s.inv_proj), 1.0f);
+        V3 current = mv_bilinear(*c, m.col_s, tcx, tcy, irx, iry);
+        V3 rp = mv_reproject(*c, center_refl_depth != 0.0f ? center_refl_pos : center_x1);
+        V4 history;
+        float refl_hist;
+        float w_sum = mv_history(*c, true, rp.x, rp.y, linearize_depth(rp.z, s.inv_proj), center_n1, irx, iry, history, refl_hist);
+        if (w_sum > 1e-3f) {
+          history.w = fminf_(history.w + 1.0f, max_accum);
+          float t = 1.0f / history.w;
+          history.x = mixf(history.x, current.x, t), history.y = mixf(history.y, current.y, t), history.z = mixf(history.z, current.z, t);
+          refl_hist = mixf(refl_hist, center_refl_depth, t);
+        } else {
+          history = V4{current.x, current.y, current.z, 1.0f};
+          refl_hist = center_refl_depth;
+        }
+        st4(m.hs[1], i, history);
+        m.hsd[1][i] = refl_hist;
+        m.out[i] += V3{history.x, history.y, history.z};
+      }
+    }
+  // ---- slot 1 -> slot 0, previous G-buffer (:1297-1303), copy_prev_matrices (:284-287)
+  m.hd[0] = m.hd[1], m.hs[0] = m.hs[1], m.hsd[0] = m.hsd[1];
+  m.prev_depth = m.depth, m.prev_noct = m.noct;
+  std::copy(s.view, s.view + 16, m.prev_view), std::copy(s.proj, s.proj + 16, m.prev_proj);
+  m.prev_cam = s.cam_pos;
+}
+// color_buffer of the moving path, nearest-upsampled as _render_to_image does (:643-644)
+void orc_fetch_hdr_moving(void* p, float* rgba) {
+  Ctx* c = (Ctx*)p;
+  const int W = c->scene.W, H = c->scene.H;
+  for (int j = 0; j < H; j++)
+    for (int i = 0; i < W; i++) {
+      int sx = (int)((float)i * c->mv.scale), sy = (int)((float)j * c->mv.scale);
+      V3 v = c->mv.out[(size_t)sy * W + sx];
+      float* o = rgba + ((size_t)j * W + i) * 4;
+      o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = 1.0f;
+    }
+}
+void orc_reset_moving(void* p) {
+  Ctx* c = (Ctx*)p;
+  c->mv = Ctx::Moving();
+}
 double orc_last_ms(void* p) { return ((Ctx*)p)->last_ms; }
 void orc_reset(void* p) {
   Ctx* c = (Ctx*)p;

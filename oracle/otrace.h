@@ -299,11 +299,19 @@ static inline void mat4_mul(const float* m, const float v[4], float out[4]) {
   for (int i = 0; i < 4; i++) out[i] = ((m[i * 4 + 0] * v[0] + m[i * 4 + 1] * v[1]) + m[i * 4 + 2] * v[2]) + m[i * 4 + 3] * v[3];
 }
 
-// pathtracer.py:293-312 get_cast_dir; space_transformations.py:14-30. render_scale = 1, static
-// camera => texcoord += 0.5 * taa_jitter.
-static inline V3 get_cast_dir(const Scene& s, float u, float v) {
-  float tx = (u + 0.5f) * (1.0f / (float)s.W) + s.jitter[0] * 0.5f;
-  float ty = (v + 0.5f) * (1.0f / (float)s.H) + s.jitter[1] * 0.5f;
+// pathtracer.py:293-312 get_cast_dir; space_transformations.py:14-30. Static camera:
+// render_scale = 1 and texcoord += 0.5 * taa_jitter; moving camera: texcoord / render_scale, no
+// jitter (pathtracer.py:307-309).
+static inline V3 get_cast_dir(const Scene& s, float u, float v, float render_scale = 1.0f, bool moving = false) {
+  float tx = (u + 0.5f) * (1.0f / (float)s.W);
+  float ty = (v + 0.5f) * (1.0f / (float)s.H);
+  if (moving) {
+    tx = tx / render_scale;
+    ty = ty / render_scale;
+  } else {
+    tx = tx + s.jitter[0] * 0.5f;
+    ty = ty + s.jitter[1] * 0.5f;
+  }
   float pos[4] = {tx * 2.0f - 1.0f, ty * 2.0f - 1.0f, 1.0f * 2.0f - 1.0f, 1.0f};
   float q[4];
   mat4_mul(s.inv_proj, pos, q);
@@ -312,6 +320,27 @@ static inline V3 get_cast_dir(const Scene& s, float u, float v) {
   float w[4];
   mat4_mul(s.inv_view, dv4, w);
   return V3{w[0], w[1], w[2]};
+}
+
+// space_transformations.py:6-34 (row-major matrices, M @ v)
+static inline float linearize_depth(float depth, const float* inv_proj) { return 1.0f / ((depth * 2.0f - 1.0f) * inv_proj[3 * 4 + 2] + inv_proj[3 * 4 + 3]); }
+static inline float delinearize_depth(float lindepth, const float* proj) {
+  return ((-lindepth * proj[2 * 4 + 2] + proj[2 * 4 + 3]) / -lindepth) * -0.5f + 0.5f;
+}
+static inline V3 screen_to_view(float ux, float uy, float depth, const float* inv_proj) {
+  float p[4] = {ux * 2.0f - 1.0f, uy * 2.0f - 1.0f, depth * 2.0f - 1.0f, 1.0f}, q[4];
+  mat4_mul(inv_proj, p, q);
+  return V3{q[0] / q[3], q[1] / q[3], q[2] / q[3]};
+}
+static inline V3 view_to_screen(V3 vp, const float* proj) {
+  float p[4] = {vp.x, vp.y, vp.z, 1.0f}, q[4];
+  mat4_mul(proj, p, q);
+  return V3{q[0] / q[3] * 0.5f + 0.5f, q[1] / q[3] * 0.5f + 0.5f, q[2] / q[3] * 0.5f + 0.5f};
+}
+static inline V3 xform_point(const float* m, V3 p, float w) {  // view_to_world / world_to_view
+  float a[4] = {p.x, p.y, p.z, w}, q[4];
+  mat4_mul(m, a, q);
+  return V3{q[0], q[1], q[2]};
 }
 
 }  // namespace orc

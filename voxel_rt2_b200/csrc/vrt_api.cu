@@ -55,6 +55,17 @@ struct vrt_ctx {
   unsigned int* d_work = nullptr;
   unsigned long long* d_stats = nullptr;
   RestirBuffers rb{nullptr, nullptr, nullptr, nullptr, nullptr};  // allocated on first ReSTIR frame
+  // moving-camera temporal path (allocated on the first moving frame)
+  struct {
+    float4 *col_d = nullptr, *col_s = nullptr, *hd[2] = {nullptr, nullptr}, *hs[2] = {nullptr, nullptr}, *out = nullptr, *full = nullptr;
+    float *depth[2] = {nullptr, nullptr}, *refl = nullptr, *refl_blur = nullptr, *hsd[2] = {nullptr, nullptr};
+    uint2* attr[2] = {nullptr, nullptr};
+    float prev_view[16], prev_proj[16];
+    int cur = 0;
+    bool has_prev = false, active = false;
+    float scale = 1.0f;
+  } mv;
+  float view[16], proj[16];
 
   int tile_rank = 0, tile_n = 1;
   vrt_stats stats;
@@ -172,6 +183,8 @@ static void fill_params(const vrt_ctx* ctx, Params& P) {
   P.cam_pos = f3{ctx->cam_pos[0], ctx->cam_pos[1], ctx->cam_pos[2]};
   memcpy(P.inv_proj, ctx->inv_proj, sizeof P.inv_proj);
   memcpy(P.inv_view, ctx->inv_view, sizeof P.inv_view);
+  memcpy(P.view, ctx->view, sizeof P.view);
+  memcpy(P.proj, ctx->proj, sizeof P.proj);
   P.W = c.width, P.H = c.height;
   P.inv_w = 1.0f / (float)c.width, P.inv_h = 1.0f / (float)c.height;
   P.sky_scatter = ctx->d_sky_scatter, P.sky_trans = ctx->d_sky_trans, P.sky_res = c.sky_res;
@@ -199,6 +212,8 @@ void vrt_destroy(vrt_ctx* ctx) {
   cudaFree(ctx->d_mats), cudaFree(ctx->d_sky_scatter), cudaFree(ctx->d_sky_trans), cudaFree(ctx->d_trans_lut);
   cudaFree(ctx->d_cloud_tex), cudaFree(ctx->d_cloud_ambient), cudaFree(ctx->d_accum), cudaFree(ctx->d_out), cudaFree(ctx->d_hits);
   cudaFree(ctx->d_jitter), cudaFree(ctx->d_work), cudaFree(ctx->d_stats);
+  cudaFree(ctx->mv.col_d), cudaFree(ctx->mv.col_s), cudaFree(ctx->mv.out), cudaFree(ctx->mv.full), cudaFree(ctx->mv.refl), cudaFree(ctx->mv.refl_blur);
+  for (int k = 0; k < 2; k++) cudaFree(ctx->mv.hd[k]), cudaFree(ctx->mv.hs[k]), cudaFree(ctx->mv.hsd[k]), cudaFree(ctx->mv.depth[k]), cudaFree(ctx->mv.attr[k]);
   cudaFree(ctx->rb.reservoirs), cudaFree(ctx->rb.gpos), cudaFree(ctx->rb.gattr), cudaFree(ctx->rb.col_d), cudaFree(ctx->rb.col_s);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -342,6 +357,8 @@ int vrt_set_camera(vrt_ctx* ctx, const float pos[3], const float view[16], const
   REQUIRE(invert4(v, vi) && invert4(p, pi), "vrt_set_camera: singular matrix");
   for (int i = 0; i < 16; i++) ctx->inv_view[i] = (float)vi[i], ctx->inv_proj[i] = (float)pi[i];
   memcpy(ctx->cam_pos, pos, sizeof ctx->cam_pos);
+  memcpy(ctx->view, view, sizeof ctx->view);
+  memcpy(ctx->proj, proj, sizeof ctx->proj);
   ctx->camera_set = true;
   return VRT_OK;
 }
@@ -545,6 +562,7 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
   CK(cudaMemcpyAsync(ctx->d_jitter, jit.data(), jit.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
   if (stats) CK(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  ctx->mv.active = false;
   Params P;
   fill_params(ctx, P);
   P.first_sample = first_sample, P.n_samples = n_samples, P.stride = stride;
@@ -625,6 +643,89 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
   return VRT_OK;
 }
 
+int vrt_accumulate_moving(vrt_ctx* ctx, int32_t sample, float render_scale, float max_accum) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(sample >= 0 && render_scale > 0.0f && render_scale <= 1.0f && max_accum >= 1.0f, "vrt_accumulate_moving: bad arguments");
+  REQUIRE(ctx->tile_n == 1, "vrt_accumulate_moving: tile sharding is not supported (history taps cross tiles)");
+  int rc = check_ready(ctx, "vrt_accumulate_moving");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t npx = (size_t)ctx->cfg.width * ctx->cfg.height;
+  auto& m = ctx->mv;
+  if (!m.col_d) {
+    CK(cudaMalloc(&m.col_d, npx * sizeof(float4)));
+    CK(cudaMalloc(&m.col_s, npx * sizeof(float4)));
+    CK(cudaMalloc(&m.out, npx * sizeof(float4)));
+    CK(cudaMalloc(&m.full, npx * sizeof(float4)));
+    CK(cudaMalloc(&m.refl, npx * sizeof(float)));
+    CK(cudaMalloc(&m.refl_blur, npx * sizeof(float)));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMalloc(&m.hd[k], npx * sizeof(float4)));
+      CK(cudaMalloc(&m.hs[k], npx * sizeof(float4)));
+      CK(cudaMalloc(&m.hsd[k], npx * sizeof(float)));
+      CK(cudaMalloc(&m.depth[k], npx * sizeof(float)));
+      CK(cudaMalloc(&m.attr[k], npx * sizeof(uint2)));
+    }
+    m.has_prev = false;
+  }
+  if (!m.has_prev) {
+    // reset_framebuffer semantics (pathtracer.py:664-668): empty history, previous matrices = current
+    CK(cudaMemsetAsync(m.col_d, 0, npx * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(m.col_s, 0, npx * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(m.out, 0, npx * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(m.refl, 0, npx * sizeof(float), ctx->stream));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMemsetAsync(m.hd[k], 0, npx * sizeof(float4), ctx->stream));
+      CK(cudaMemsetAsync(m.hs[k], 0, npx * sizeof(float4), ctx->stream));
+      CK(cudaMemsetAsync(m.hsd[k], 0, npx * sizeof(float), ctx->stream));
+      CK(cudaMemsetAsync(m.depth[k], 0, npx * sizeof(float), ctx->stream));
+      CK(cudaMemsetAsync(m.attr[k], 0, npx * sizeof(uint2), ctx->stream));
+    }
+    memcpy(m.prev_view, ctx->view, sizeof m.prev_view);
+    memcpy(m.prev_proj, ctx->proj, sizeof m.prev_proj);
+    m.has_prev = true;
+    m.cur = 0;
+  }
+  m.scale = render_scale;
+  m.active = true;
+  const int cur = m.cur, prev = cur ^ 1;
+  if (ctx->jitter_cap < 1) {
+    CK(cudaMalloc(&ctx->d_jitter, sizeof(float2)));
+    ctx->jitter_cap = 1;
+  }
+  CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
+  Params P;
+  fill_params(ctx, P);
+  P.first_sample = sample, P.n_samples = 1, P.stride = 1;
+  MovingOut MO{m.col_d, m.col_s, m.depth[cur], m.attr[cur], m.refl, render_scale};
+  MovingFrame F;
+  F.col_d = m.col_d, F.col_s = m.col_s, F.depth = m.depth[cur], F.attr = m.attr[cur], F.refl = m.refl, F.refl_blur = m.refl_blur;
+  F.depth_prev = m.depth[prev], F.attr_prev = m.attr[prev], F.hd_prev = m.hd[prev], F.hs_prev = m.hs[prev], F.hsd_prev = m.hsd[prev];
+  F.hd = m.hd[cur], F.hs = m.hs[cur], F.hsd = m.hsd[cur], F.out = m.out;
+  memcpy(F.prev_view, m.prev_view, sizeof F.prev_view);
+  memcpy(F.prev_proj, m.prev_proj, sizeof F.prev_proj);
+  F.scale = render_scale;
+  // pixels the filters skip keep their history (the reference copies slot 1 -> slot 0 for every
+  // pixel, :1297-1303): start this frame's slot from the previous one
+  CK(cudaMemcpyAsync(m.hd[cur], m.hd[prev], npx * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(m.hs[cur], m.hs[prev], npx * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(m.hsd[cur], m.hsd[prev], npx * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(m.depth[cur], m.depth[prev], npx * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(m.attr[cur], m.attr[prev], npx * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(vrt_launch_path_moving(P, MO, ctx->sm_count, ctx->stream));
+  CK(vrt_launch_moving_filters(P, F, max_accum, ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->stats.last_render_ms, ctx->ev0, ctx->ev1));
+  ctx->stats.kernel_launches = 3;
+  // copy_prev_matrices (pathtracer.py:284-287) and the slot swap
+  memcpy(m.prev_view, ctx->view, sizeof m.prev_view);
+  memcpy(m.prev_proj, ctx->proj, sizeof m.prev_proj);
+  m.cur = prev;
+  return VRT_OK;
+}
+
 int vrt_get_reservoirs(vrt_ctx* ctx, void* out) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(out, "vrt_get_reservoirs: null pointer");
@@ -649,6 +750,8 @@ int vrt_reset(vrt_ctx* ctx) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemsetAsync(ctx->d_accum, 0, (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4), ctx->stream));
+  ctx->mv.has_prev = false;
+  ctx->mv.active = false;
   return VRT_OK;
 }
 
@@ -664,7 +767,12 @@ static int resolve(vrt_ctx* ctx, bool ldr, float* host) {
   CK(cudaSetDevice(ctx->device));
   const int W = ctx->cfg.width, H = ctx->cfg.height;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  CK(vrt_launch_resolve(ctx->d_accum, ldr ? nullptr : ctx->d_out, ldr ? ctx->d_out : nullptr, W, H, ctx->cfg.exposure, ctx->stream));
+  const float4* src = ctx->d_accum;
+  if (ctx->mv.active) {  // the last frame came from the moving-camera path: show its colour buffer
+    CK(vrt_launch_moving_upsample(ctx->mv.out, ctx->mv.full, W, H, ctx->mv.scale, ctx->stream));
+    src = ctx->mv.full;
+  }
+  CK(vrt_launch_resolve(src, ldr ? nullptr : ctx->d_out, ldr ? ctx->d_out : nullptr, W, H, ctx->cfg.exposure, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   if (host) CK(cudaMemcpyAsync(host, ctx->d_out, (size_t)W * H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

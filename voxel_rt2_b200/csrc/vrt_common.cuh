@@ -149,6 +149,7 @@ struct Params {
   // camera
   f3 cam_pos;
   float inv_proj[16], inv_view[16];
+  float view[16], proj[16];  // moving-camera temporal path only
   int W, H;
   float inv_w, inv_h;  // 1.0f / W, 1.0f / H (IEEE division on the host, same bits as on the device)
   // sky tables, float4 texels, [x][y] with y fastest

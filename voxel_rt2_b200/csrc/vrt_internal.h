@@ -13,6 +13,10 @@ cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStrea
 // vrt_pool.cu — shared-memory wavefront version of the path kernel (default for path tracing)
 cudaError_t vrt_launch_path_pool(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out);
 cudaError_t vrt_launch_path_restir(const Params& P, const RestirBuffers& RB, int sm_count, cudaStream_t st);
+cudaError_t vrt_launch_path_moving(const Params& P, const MovingOut& MO, int sm_count, cudaStream_t st);
+// vrt_temporal.cu — moving-camera temporal filters (pathtracer.py:993-1303)
+cudaError_t vrt_launch_moving_filters(const Params& P, const MovingFrame& F, float max_accum, cudaStream_t st);
+cudaError_t vrt_launch_moving_upsample(const float4* out, float4* full, int W, int H, float scale, cudaStream_t st);
 size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem);
 // vrt_restir.cu — spatial_GRIS (pathtracer.py:815-989); adds the frame's colour into P.accum
 cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t frame, cudaStream_t st);

@@ -95,8 +95,14 @@ enum { PIX_IDLE = -1, PIX_DONE = -2 };
 // packed reservoir, merges the primary-vertex NEE sample into it (reservoir.py:64-74) and writes
 // the G-buffer the spatial pass needs. It runs one sample per launch and never retires
 // zero-throughput paths early (their reconnection data is still used by the shift).
-template <bool STATS, bool RESTIR>
-__global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem, RestirBuffers RB) {
+// MODE 2 is render with camera_is_moving = 1 (pathtracer.py:146,628-630): the frame is rendered at
+// render_scale into the lower-left corner, the diffuse part is divided by the primary albedo, and
+// the G-buffer the reprojecting temporal filters need (NDC depth, octahedral normal, material,
+// virtual reflection depth; pathtracer.py:535-546) is written next to the two colour buffers.
+template <bool STATS, int MODE>
+__global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem, RestirBuffers RB, MovingOut MO) {
+  constexpr bool RESTIR = MODE == 1;
+  constexpr bool MOVING = MODE == 2;
   extern __shared__ uint32_t smem[];
   const uint32_t* upper = stage_shared(P, smem, upper_in_smem);
   const float4* s_mats = reinterpret_cast<const float4*>(smem);
@@ -134,6 +140,9 @@ __global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(
   uint32_t primary_noct = 0u;
   int rc_lobe = 0;
   bool sky_ray = false;
+  // moving-camera bookkeeping (dead code unless MOVING)
+  f3 primary_albedo = mk3(1.0f);
+  float refl_dist = 0.0f;
 
   bool finished = false, restart = false;
 
@@ -149,7 +158,22 @@ __global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(
       f3 diffuse, specular;
       const int u = pix & 0xffff, v = pix >> 16;
       const size_t pidx = (size_t)v * P.W + u;
-      if (!RESTIR) {
+      if (MOVING) {
+        diffuse = fnee_d, specular = fnee_s;
+        if (f_lobe == LOBE_DIFFUSE) diffuse += contrib * f_invpdf + emission;
+        if (f_lobe == LOBE_SPEC_REFL) specular += contrib * f_invpdf;
+        diffuse = diffuse / f3{fmaxf(primary_albedo.x, 1e-2f), fmaxf(primary_albedo.y, 1e-2f), fmaxf(primary_albedo.z, 1e-2f)};
+        MO.col_d[pidx] = make_float4(diffuse.x, diffuse.y, diffuse.z, 0.0f);
+        MO.col_s[pidx] = make_float4(specular.x, specular.y, specular.z, 0.0f);
+        MO.depth[pidx] = view_to_screen_z(P, primary_pos);
+        MO.attr[pidx] = make_uint2(primary_noct, pm_info);
+        float refl = 0.0f;
+        if (refl_dist != 0.0f && !isbad(refl_dist)) {
+          const f3 virtual_point = primary_pos + normalize(primary_pos - P.cam_pos) * refl_dist;
+          refl = linearize_depth(P, view_to_screen_z(P, virtual_point));
+        }
+        MO.refl[pidx] = refl;
+      } else if (!RESTIR) {
         diffuse = fnee_d, specular = fnee_s;
         if (f_lobe == LOBE_DIFFUSE) diffuse += contrib * f_invpdf + emission;
         if (f_lobe == LOBE_SPEC_REFL) specular += contrib * f_invpdf;
@@ -212,10 +236,10 @@ __global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(
         RB.col_s[pidx] = make_float4(specular.x, specular.y, specular.z, 0.0f);
       }
       s_i++;
-      if (s_i < P.n_samples && !RESTIR) {
+      if (s_i < P.n_samples && MODE == 0) {
         restart = true;
       } else {
-        if (!RESTIR) {
+        if (MODE == 0) {
           float4* dst = P.accum + pidx;
           float4 a = *dst;
           a.x += acc.x, a.y += acc.y, a.z += acc.z, a.w += (float)P.n_samples;
@@ -258,11 +282,18 @@ __global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(
       const int u = pix & 0xffff, v = pix >> 16;
       const uint32_t sample = (uint32_t)(P.first_sample + s_i * P.stride);
       key = path_key((uint32_t)(v * P.W + u), sample, P.seed);
-      const float2 j = P.jitter[s_i];
-      d = get_cast_dir(P, (float)u, (float)v, j.x, j.y);
+      if (MOVING) {
+        // is_outside_render_area (pathtracer.py:289-291): such pixels are not rendered this frame
+        if ((float)u > MO.scale * (float)P.W || (float)v > MO.scale * (float)P.H) pix = PIX_IDLE;
+        d = get_cast_dir_scaled(P, (float)u, (float)v, MO.scale);
+      } else {
+        const float2 j = P.jitter[s_i];
+        d = get_cast_dir(P, (float)u, (float)v, j.x, j.y);
+      }
       pos = P.cam_pos;
       thr = mk3(1.0f), contrib = mk3(0.0f), fnee_d = mk3(0.0f), fnee_s = mk3(0.0f);
       f_invpdf = 1.0f, f_lobe = 0, pm_info = 0, depth = 0, state = ST_SEGMENT;
+      if (MOVING) primary_albedo = mk3(1.0f), refl_dist = 0.0f, primary_pos = mk3(0.0f), primary_noct = 0u, sky_ray = false;
       if (RESTIR) {
         rz.F = rz.rc_pos = rz.rc_normal = rz.rc_incident_dir = rz.rc_incident_L = rz.rc_NEE_dir = mk3(0.0f);
         rz.rc_mat_info = 0u, rz.cached_jacobian_term = 1.0f, rz.lobes = 0;
@@ -286,6 +317,18 @@ __global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(
     if (active) {
       if (state == ST_SEGMENT) {
         const uint32_t base = 8u * (uint32_t)depth;
+        if (MOVING) {  // pathtracer.py:402-412
+          if (depth == 0) {
+            primary_pos = pos + h.closest * d;
+            primary_albedo = h.albedo;
+            pm_info = encode_material(h.mat_id, h.albedo);
+            float ex = 0.0f, ey = 0.0f;
+            if (h.closest < VRT_INF) encode_unit_vector_3x16(f3{h.nx, h.ny, h.nz}, ex, ey);
+            primary_noct = h16bits(ex) | (h16bits(ey) << 16);
+          } else if (depth == 1 && f_lobe != LOBE_DIFFUSE) {
+            refl_dist += h.closest;
+          }
+        }
         if (RESTIR) {  // pathtracer.py:402-417
           const f3 hit_pos = pos + h.closest * d;
           if (depth == 0) {
@@ -316,6 +359,7 @@ __global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(
           }
           f3 sky_emission = firefly_filter(sky_scattering + sky_T * sun_rad * hit_sun);
           contrib += thr * sky_emission;
+          if (MOVING && depth == 0) primary_pos = mk3(0.0f), sky_ray = true;
           if (RESTIR) {  // pathtracer.py:509-517
             if (depth == 0) {
               primary_pos = mk3(0.0f);
@@ -412,7 +456,7 @@ __global__ void __launch_bounds__(128, RESTIR ? 3 : VRT_PATH_MIN_BLOCKS) k_path(
       d = nd;
       depth++;
       // The reference keeps tracing zero-throughput paths; they add exact zeros, so stop here.
-      const bool dead = !RESTIR && thr.x == 0.0f && thr.y == 0.0f && thr.z == 0.0f;
+      const bool dead = MODE == 0 && thr.x == 0.0f && thr.y == 0.0f && thr.z == 0.0f;
       if (depth >= P.max_depth || dead) finished = true;
     }
   }
@@ -480,29 +524,36 @@ cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <bool STATS, bool RESTIR>
-static cudaError_t launch_path_t(const Params& P, int sm_count, cudaStream_t st, int* blocks_out, const RestirBuffers& RB) {
+template <bool STATS, int MODE>
+static cudaError_t launch_path_t(const Params& P, int sm_count, cudaStream_t st, int* blocks_out, const RestirBuffers& RB, const MovingOut& MO) {
   int uis;
   size_t sm = smem_bytes(P, &uis);
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<STATS, RESTIR>, 128, sm);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<STATS, MODE>, 128, sm);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   int blocks = sm_count * per_sm;  // persistent: one wave, a multiple of the SM count
   int max_useful = (P.n_tiles + 3) / 4;
   if (blocks > max_useful) blocks = max_useful > 0 ? max_useful : 1;
   if (blocks_out) *blocks_out = blocks;
-  k_path<STATS, RESTIR><<<blocks, 128, sm, st>>>(P, uis, RB);
+  k_path<STATS, MODE><<<blocks, 128, sm, st>>>(P, uis, RB, MO);
   return cudaGetLastError();
 }
 
 cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out) {
   RestirBuffers none{nullptr, nullptr, nullptr, nullptr, nullptr};
-  return stats ? launch_path_t<true, false>(P, sm_count, st, blocks_out, none) : launch_path_t<false, false>(P, sm_count, st, blocks_out, none);
+  MovingOut mo{nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f};
+  return stats ? launch_path_t<true, 0>(P, sm_count, st, blocks_out, none, mo) : launch_path_t<false, 0>(P, sm_count, st, blocks_out, none, mo);
 }
 
 cudaError_t vrt_launch_path_restir(const Params& P, const RestirBuffers& RB, int sm_count, cudaStream_t st) {
-  return launch_path_t<false, true>(P, sm_count, st, nullptr, RB);
+  MovingOut mo{nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f};
+  return launch_path_t<false, 1>(P, sm_count, st, nullptr, RB, mo);
+}
+
+cudaError_t vrt_launch_path_moving(const Params& P, const MovingOut& MO, int sm_count, cudaStream_t st) {
+  RestirBuffers none{nullptr, nullptr, nullptr, nullptr, nullptr};
+  return launch_path_t<false, 2>(P, sm_count, st, nullptr, none, MO);
 }
 
 size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem) { return smem_bytes(P, upper_in_smem); }

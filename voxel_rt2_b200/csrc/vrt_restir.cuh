@@ -103,3 +103,35 @@ struct RestirBuffers {
   float4* col_d;
   float4* col_s;
 };
+
+// Outputs of the moving-camera variant of the path kernel (pathtracer.py:535-546,628-632).
+struct MovingOut {
+  float4* col_d;  // albedo-demodulated diffuse of the frame
+  float4* col_s;
+  float* depth;   // gbuff_depth (NDC z in [0,1])
+  uint2* attr;    // octahedral f16x2 normal, packed material + albedo
+  float* refl;    // gbuff_depth_reflection (linear), 0 = none
+  float scale;    // render_scale
+};
+
+// One frame of the moving-camera temporal filters: current G-buffer / colours, previous frame's
+// G-buffer and history slot (read), this frame's history slot and colour (written).
+struct MovingFrame {
+  float4* col_d;
+  float4* col_s;
+  const float* depth;
+  const uint2* attr;
+  const float* refl;
+  float* refl_blur;
+  const float* depth_prev;
+  const uint2* attr_prev;
+  const float4* hd_prev;
+  const float4* hs_prev;
+  const float* hsd_prev;
+  float4* hd;
+  float4* hs;
+  float* hsd;
+  float4* out;
+  float prev_view[16], prev_proj[16];
+  float scale;
+};

@@ -271,3 +271,44 @@ HD f3 get_cast_dir(const Params& P, float u, float v, float jx, float jy) {
     w[i] = xadd(xadd(xmul(P.inv_view[i * 4 + 0], dv.x), xmul(P.inv_view[i * 4 + 1], dv.y)), xmul(P.inv_view[i * 4 + 2], dv.z));
   return f3{w[0], w[1], w[2]};
 }
+
+// Moving camera (pathtracer.py:307-309): texcoord / render_scale, no TAA jitter.
+HD f3 get_cast_dir_scaled(const Params& P, float u, float v, float scale) {
+  const float tx = xdiv(xmul(xadd(u, 0.5f), P.inv_w), scale);
+  const float ty = xdiv(xmul(xadd(v, 0.5f), P.inv_h), scale);
+  const float px = xsub(xmul(tx, 2.0f), 1.0f), py = xsub(xmul(ty, 2.0f), 1.0f);
+  float q[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    q[i] = xadd(xadd(xadd(xmul(P.inv_proj[i * 4 + 0], px), xmul(P.inv_proj[i * 4 + 1], py)), P.inv_proj[i * 4 + 2]), P.inv_proj[i * 4 + 3]);
+  f3 dv = xnormalize(f3{xdiv(q[0], q[3]), xdiv(q[1], q[3]), xdiv(q[2], q[3])});
+  float w[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    w[i] = xadd(xadd(xmul(P.inv_view[i * 4 + 0], dv.x), xmul(P.inv_view[i * 4 + 1], dv.y)), xmul(P.inv_view[i * 4 + 2], dv.z));
+  return f3{w[0], w[1], w[2]};
+}
+
+// renderer/space_transformations.py:6-34 (row-major matrices, M @ v)
+HD void mat4_mul(const float* m, float x, float y, float z, float w, float q[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) q[i] = ((m[i * 4 + 0] * x + m[i * 4 + 1] * y) + m[i * 4 + 2] * z) + m[i * 4 + 3] * w;
+}
+HD float linearize_depth(const Params& P, float depth) { return 1.0f / ((depth * 2.0f - 1.0f) * P.inv_proj[3 * 4 + 2] + P.inv_proj[3 * 4 + 3]); }
+HD float delinearize_depth(const Params& P, float lindepth) { return ((-lindepth * P.proj[2 * 4 + 2] + P.proj[2 * 4 + 3]) / -lindepth) * -0.5f + 0.5f; }
+HD f3 screen_to_view(const Params& P, float ux, float uy, float depth) {
+  float q[4];
+  mat4_mul(P.inv_proj, ux * 2.0f - 1.0f, uy * 2.0f - 1.0f, depth * 2.0f - 1.0f, 1.0f, q);
+  return f3{q[0] / q[3], q[1] / q[3], q[2] / q[3]};
+}
+HD f3 view_to_world(const Params& P, f3 v) {
+  float q[4];
+  mat4_mul(P.inv_view, v.x, v.y, v.z, 1.0f, q);
+  return f3{q[0], q[1], q[2]};
+}
+HD float view_to_screen_z(const Params& P, f3 world_pos) {  // view_to_screen(world_to_view(p)).z
+  float a[4], q[4];
+  mat4_mul(P.view, world_pos.x, world_pos.y, world_pos.z, 1.0f, a);
+  mat4_mul(P.proj, a[0], a[1], a[2], 1.0f, q);
+  return q[2] / q[3] * 0.5f + 0.5f;
+}

@@ -225,6 +225,20 @@ class Renderer:
         self.current_spp += int(frames)
         self.current_frame += int(frames)
 
+    def accumulate_moving(self, render_scale=0.5, max_accum=50.0):
+        """One frame of accumulate() while the camera moves (scene.py:214-228): set_render_scale(0.5),
+        set_max_samples(50), set_camera_is_moving(True); reprojected temporal filters; the previous
+        matrices are updated afterwards (copy_prev_matrices). fetch_image()/fetch_hdr() then show
+        this path's colour buffer."""
+        self._sync_camera()
+        sample = self.sample_offset + self.current_spp * self.sample_stride
+        self._check(self._lib.vrt_accumulate_moving(self._h, sample, C.c_float(render_scale), C.c_float(max_accum)))
+        self.current_spp += 1
+        self.current_frame += 1
+
+    def fetch_hdr_moving(self):
+        return self.fetch_hdr()
+
     def get_reservoirs(self):
         """Packed 56-byte reservoirs of the last ReSTIR frame, uint8 [H, W, 56]."""
         out = np.empty((self.image_res[1], self.image_res[0], 56), np.uint8)
