@@ -59,8 +59,8 @@ enum {
   F_NDR, F_NDG, F_NDB, F_NSR, F_NSG, F_NSB,  // first-vertex NEE, diffuse / specular
   F_AR, F_AG, F_AB,                          // per-pixel accumulator of this launch
   F_INVPDF, F_PIX, F_MISC, F_PMINFO,
-  F_HIT_T,     // T: voxel-space t of the pending ray (inf = miss); C overwrites with world distance
-  F_HIT_CELL,  // T: cell x | y<<10 | z<<20 | normal code << 30.. (see pack_cell)
+  F_HIT_T,     // T: voxel-space t of the pending ray (inf = miss)
+  F_HIT_CELL,  // T: cell x | y<<10 | z<<20 | in-grid flag << 30 (the face normal goes into F_MISC)
   F_HIT_COL,   // C: RGBA8 colour word of the surface (kept while the shadow ray flies)
   F_VX, F_VY, F_VZ,  // view vector at the surface (= -segment direction)
 };

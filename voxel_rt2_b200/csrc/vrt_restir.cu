@@ -50,54 +50,80 @@ HD Mat decode_material(const GrisCtx& G, uint32_t enc, int& mat_id) {  // math_u
   return m;
 }
 
-// pathtracer.py:672-812
-HD void shift_sample(const GrisCtx& G, f3 dst_pos, f3 dst_normal, const Mat& dst_material, const RReservoir& src, f3& diffuse, f3& specular,
-                     float& jacobian_out) {
-  const RSample& z = src.z;
-  const bool esc = is_vec_zero(z.rc_normal), last = is_vec_zero(z.rc_incident_dir), nee = !is_vec_zero(z.rc_NEE_dir);
-  const f3 dir = esc ? z.rc_pos : normalize(z.rc_pos - dst_pos);
-  float passed_checks = 1.0f;
-  if (dot(dst_normal, dir) < 1e-5f || (!esc && dot(z.rc_normal, -dir) < 1e-5f)) passed_checks = 0.0f;
-  f3 rc_tang, rc_bitang;
-  make_orthonormal_basis(z.rc_normal, rc_tang, rc_bitang);
+// Per-sample and per-destination terms of shift() that do not depend on the other end of the
+// reconnection: hoisted so the 32-tap loop computes them once for the centre pixel.
+struct RcPre {   // reconnection vertex of a sample (pathtracer.py:676-689)
+  Mat rc_mat;
   int rc_mat_id;
-  const Mat rc_mat = decode_material(G, z.rc_mat_info, rc_mat_id);
-  f3 contrib = mk3(0.0f);
-  if (!last && !esc) {
-    f3 rc_brdf = disney_evaluate_lobewise(rc_mat, -dir, z.rc_normal, z.rc_incident_dir, rc_tang, rc_bitang, z.lobes / 10);
-    rc_brdf *= saturate(dot(z.rc_normal, z.rc_incident_dir));
-    const float dst_rc_pdf = pdf_disney_lobewise(rc_mat, -dir, z.rc_normal, z.rc_incident_dir, rc_tang, rc_bitang, z.lobes / 10);
-    const float lp = cone_sample_pdf(G.light_cos_max, dot(G.light_dir, z.rc_incident_dir));
-    const float w = power_heuristic(dst_rc_pdf, lp * (nee ? 1.0f : 0.0f));
-    contrib += firefly_filter((w * rc_brdf) * frcp(dst_rc_pdf) * z.rc_incident_L);
-  }
-  if (esc) contrib += firefly_filter(z.rc_incident_L);
-  if (nee && !esc) {
-    f3 bd, bs;
-    float lpdf;
-    eval_and_pdf(rc_mat, -dir, z.rc_normal, z.rc_NEE_dir, rc_tang, rc_bitang, bd, bs, lpdf);
-    const f3 rc_nee_brdf = (bd + bs) * saturate(dot(z.rc_normal, z.rc_NEE_dir));
-    const float w = power_heuristic(G.light_pdf_axis, lpdf);
-    f3 sky_T = mk3(1.0f);
-    if (G.use_sky) sky_T = sky_fetch(G.sky_trans, sky_tap(G.sky_res, project_sky(z.rc_NEE_dir, 1.0f / (float)G.sky_res)));
-    contrib += firefly_filter((w * rc_nee_brdf) * sky_T * G.sun_rad);
-  }
-  if (rc_mat_id == 2) contrib += rc_mat.base_col;
-  f3 dst_tang, dst_bitang;
-  make_orthonormal_basis(dst_normal, dst_tang, dst_bitang);
-  const f3 view = normalize(G.cam_pos - dst_pos);
-  f3 pd, ps;
-  disney_evaluate_lobewise_split(dst_material, view, dst_normal, dir, dst_tang, dst_bitang, z.lobes % 10, pd, ps);
-  const float cosd = saturate(dot(dst_normal, dir));
-  diffuse = (pd * cosd) * contrib;
-  specular = (ps * cosd) * contrib;
+  f3 tang, bitang, sky_T;
+  bool esc, last, nee, sky_ready;
+};
+struct DstPre {  // primary vertex the sample is shifted to (pathtracer.py:731-733)
+  f3 tang, bitang, view;
+};
+HD f3 rc_sky_T(const GrisCtx& G, const RSample& z) {
+  return sky_fetch(G.sky_trans, sky_tap(G.sky_res, project_sky(z.rc_NEE_dir, 1.0f / (float)G.sky_res)));
+}
+HD RcPre prep_rc(const GrisCtx& G, const RSample& z, bool fetch_sky) {
+  RcPre r;
+  r.esc = is_vec_zero(z.rc_normal), r.last = is_vec_zero(z.rc_incident_dir), r.nee = !is_vec_zero(z.rc_NEE_dir);
+  make_orthonormal_basis(z.rc_normal, r.tang, r.bitang);
+  r.rc_mat = decode_material(G, z.rc_mat_info, r.rc_mat_id);
+  r.sky_T = mk3(1.0f);
+  r.sky_ready = fetch_sky || !(r.nee && !r.esc && G.use_sky);
+  if (fetch_sky && r.nee && !r.esc && G.use_sky) r.sky_T = rc_sky_T(G, z);
+  return r;
+}
+HD DstPre prep_dst(const GrisCtx& G, f3 dst_pos, f3 dst_normal) {
+  DstPre d;
+  make_orthonormal_basis(dst_normal, d.tang, d.bitang);
+  d.view = normalize(G.cam_pos - dst_pos);
+  return d;
+}
+
+// pathtracer.py:672-812. The geometric terms (N.L tests, Jacobian) are evaluated first: when
+// their product is zero every use of the shifted integrand is multiplied by it (p_hat * jacobian
+// in the merge weight, center_p_hat in the canonical weight), so the BSDF work is skipped.
+HD void shift_sample(const GrisCtx& G, f3 dst_pos, f3 dst_normal, const Mat& dst_material, const DstPre& D, const RReservoir& src, const RcPre& R,
+                     f3& diffuse, f3& specular, float& jacobian_out) {
+  const RSample& z = src.z;
+  const f3 dir = R.esc ? z.rc_pos : normalize(z.rc_pos - dst_pos);
+  float passed_checks = 1.0f;
+  if (dot(dst_normal, dir) < 1e-5f || (!R.esc && dot(z.rc_normal, -dir) < 1e-5f)) passed_checks = 0.0f;
   float jacobian = 1.0f;
-  if (!esc) {
+  if (!R.esc) {
     const f3 y = z.rc_pos - dst_pos;
     jacobian = z.cached_jacobian_term * fdiv(fabsf(dot(normalize(y), z.rc_normal)), dot(y, y));
   }
   if (jacobian < 0.0f || isbad(jacobian)) jacobian = 0.0f;
   jacobian_out = jacobian * passed_checks;
+  diffuse = mk3(0.0f), specular = mk3(0.0f);
+  if (jacobian_out == 0.0f) return;
+  f3 contrib = mk3(0.0f);
+  if (!R.last && !R.esc) {
+    f3 rc_brdf = disney_evaluate_lobewise(R.rc_mat, -dir, z.rc_normal, z.rc_incident_dir, R.tang, R.bitang, z.lobes / 10);
+    rc_brdf *= saturate(dot(z.rc_normal, z.rc_incident_dir));
+    const float dst_rc_pdf = pdf_disney_lobewise(R.rc_mat, -dir, z.rc_normal, z.rc_incident_dir, R.tang, R.bitang, z.lobes / 10);
+    const float lp = cone_sample_pdf(G.light_cos_max, dot(G.light_dir, z.rc_incident_dir));
+    const float w = power_heuristic(dst_rc_pdf, lp * (R.nee ? 1.0f : 0.0f));
+    contrib += firefly_filter((w * rc_brdf) * frcp(dst_rc_pdf) * z.rc_incident_L);
+  }
+  if (R.esc) contrib += firefly_filter(z.rc_incident_L);
+  if (R.nee && !R.esc) {
+    f3 bd, bs;
+    float lpdf;
+    eval_and_pdf(R.rc_mat, -dir, z.rc_normal, z.rc_NEE_dir, R.tang, R.bitang, bd, bs, lpdf);
+    const f3 rc_nee_brdf = (bd + bs) * saturate(dot(z.rc_normal, z.rc_NEE_dir));
+    const float w = power_heuristic(G.light_pdf_axis, lpdf);
+    const f3 sky_T = R.sky_ready ? R.sky_T : rc_sky_T(G, z);  // neighbours: fetched only if the shift survives the early-out
+    contrib += firefly_filter((w * rc_nee_brdf) * sky_T * G.sun_rad);
+  }
+  if (R.rc_mat_id == 2) contrib += R.rc_mat.base_col;
+  f3 pd, ps;
+  disney_evaluate_lobewise_split(dst_material, D.view, dst_normal, dir, D.tang, D.bitang, z.lobes % 10, pd, ps);
+  const float cosd = saturate(dot(dst_normal, dir));
+  diffuse = (pd * cosd) * contrib;
+  specular = (ps * cosd) * contrib;
 }
 
 HD void load_reservoir(const uint2* __restrict__ base, size_t pidx, const float* unorm8, RReservoir& r) {
@@ -168,6 +194,8 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
     float canonical_mis_weight = 1.0f;
     f3 chosen_F_d = mk3(0.0f), chosen_F_s = mk3(0.0f);
     const float center_F_lum = luminance(center.z.F);
+    const RcPre center_rc = prep_rc(G, center.z, true);
+    const DstPre center_dst = prep_dst(G, center_x1, center_n1);
     for (int i = 0; i < max_taps; i++) {
       const float golden_angle = 2.399963229728f;
       const float angle = ((float)i + angle_shift) * golden_angle;
@@ -203,8 +231,8 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
       const Mat neighbour_mat = decode_material(G, nga.y, neighbour_mat_id);
       f3 c_d, c_s, s_d, s_s;
       float c_jacobian, jacobian;
-      shift_sample(G, neighbour_x1, neighbour_n1, neighbour_mat, center, c_d, c_s, c_jacobian);
-      shift_sample(G, center_x1, center_n1, center_mat, nb, s_d, s_s, jacobian);
+      shift_sample(G, neighbour_x1, neighbour_n1, neighbour_mat, prep_dst(G, neighbour_x1, neighbour_n1), center, center_rc, c_d, c_s, c_jacobian);
+      shift_sample(G, center_x1, center_n1, center_mat, center_dst, nb, prep_rc(G, nb.z, false), s_d, s_s, jacobian);
       const float center_p_hat = luminance(c_d + c_s) * c_jacobian;
       float canonical_weight = center_p_hat * nb.M;
       canonical_weight = canonical_weight / (center_p_hat * nb.M + center_F_lum * center.M / (float)max_taps);

@@ -84,7 +84,6 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
   int last_b = -1;
   unsigned long long w = 0ull;
   int iters = 0;
-  bool found = false;
   while (iters < 512) {
     if (hit_distance > far) {
       hit_distance = VRT_INF;
@@ -128,10 +127,7 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
         occ = (w >> ((pz & 3) * 16 + (py & 3) * 4 + (px & 3))) & 1ull;
       }
     }
-    if (occ) {
-      found = true;
-      break;
-    }
+    if (occ) break;
     // --- step to the exit face of the empty LOD-`lod` cell (raytracer.py:124-147)
     const float cell_size = (float)(1 << lod);
     const int cxi = px >> lod, cyi = py >> lod, czi = pz >> lod;
@@ -160,7 +156,6 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
     iters++;
     if (STATS) tc->steps++;
   }
-  (void)found;
   h.t = hit_distance;
   h.cx = px, h.cy = py, h.cz = pz;
   h.iters = iters;
