@@ -119,6 +119,16 @@ def main():
     o.prepare_data()
     o.accumulate(1024)
     np.savez_compressed(os.path.join(HERE, "radiance_example6_bg_96x64_1024spp.npz"), hdr=o.fetch_hdr().astype(np.float32), seed=np.int32(12))
+    # example6 as authored (physical sky + clouds), sky tables precomputed BY THE ORACLE at 64^2 with
+    # 4 cloud passes: end-to-end pin of precompute + lookups + path tracing
+    import os as _os
+
+    tex = np.load(_os.path.join(ROOT, "voxel_rt2_b200", "assets", "cloud_texture.npz"))["tex"]
+    o = oracle_for(sc, (96, 64), sky_res=64, cloud_passes=4, jitter=True, seed=13, cloud_tex=tex)
+    o.set_use_physical_sky(True, True)
+    o.prepare_data()
+    o.accumulate(1024)
+    np.savez_compressed(os.path.join(HERE, "radiance_example6_sky64_96x64_1024spp.npz"), hdr=o.fetch_hdr().astype(np.float32), seed=np.int32(13))
     print("done")
 
 
