@@ -74,7 +74,11 @@ HD float sqr(float x) { return x * x; }
 HD float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 HD f3 mix3(f3 a, f3 b, float t) { return a * (1.0f - t) + b * t; }
 HD float fractf(float x) { return x - floorf(x); }
-HD float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+// sign(x) in {-1, 0, +1}: copy the sign bit onto 1.0f, zero (and NaN) map to 0 like the comparisons did
+HD float signf(float x) {
+  const float s = __uint_as_float((__float_as_uint(x) & 0x80000000u) | 0x3f800000u);
+  return (x > 0.0f || x < 0.0f) ? s : 0.0f;
+}
 HD f3 reflect(f3 i, f3 n) { return i - (2.0f * dot(i, n)) * n; }
 HD f3 exp3(f3 a) { return f3{expf(a.x), expf(a.y), expf(a.z)}; }
 HD float luminance(f3 c) { return dot(f3{0.2125f, 0.7154f, 0.0721f}, c); }
