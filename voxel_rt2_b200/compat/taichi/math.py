@@ -14,6 +14,10 @@ def _is_vec(x):
     return isinstance(x, Vec)
 
 
+_set = object.__setattr__
+_SCALARS = (_b.int, _b.float, _b.bool)
+
+
 class Vec:
     """Small fixed-size numeric vector with GLSL-style swizzles and element-wise operators."""
 
@@ -21,7 +25,7 @@ class Vec:
     _SW = {"x": 0, "y": 1, "z": 2, "w": 3, "r": 0, "g": 1, "b": 2, "a": 3}
 
     def __init__(self, vals):
-        self.v = list(vals)
+        _set(self, "v", vals if type(vals) is list else list(vals))
 
     # --- container protocol
     def __len__(self):
@@ -74,13 +78,37 @@ class Vec:
             return Vec([f(b, a) for a, b in zip(self.v, o)])
         return Vec([f(o, a) for a in self.v])
 
-    def __add__(self, o): return self._bin(o, lambda a, b: a + b)
+    def __add__(self, o):
+        a = self.v
+        if type(o) is Vec:
+            return Vec([x + y for x, y in zip(a, o.v)])
+        if type(o) in _SCALARS:
+            return Vec([x + o for x in a])
+        return self._bin(o, lambda a, b: a + b)
     def __radd__(self, o): return self._rbin(o, lambda a, b: a + b)
-    def __sub__(self, o): return self._bin(o, lambda a, b: a - b)
+    def __sub__(self, o):
+        a = self.v
+        if type(o) is Vec:
+            return Vec([x - y for x, y in zip(a, o.v)])
+        if type(o) in _SCALARS:
+            return Vec([x - o for x in a])
+        return self._bin(o, lambda a, b: a - b)
     def __rsub__(self, o): return self._rbin(o, lambda a, b: a - b)
-    def __mul__(self, o): return self._bin(o, lambda a, b: a * b)
-    def __rmul__(self, o): return self._rbin(o, lambda a, b: a * b)
-    def __truediv__(self, o): return self._bin(o, lambda a, b: a / b)
+    def __mul__(self, o):
+        a = self.v
+        if type(o) is Vec:
+            return Vec([x * y for x, y in zip(a, o.v)])
+        if type(o) in _SCALARS:
+            return Vec([x * o for x in a])
+        return self._bin(o, lambda a, b: a * b)
+    def __rmul__(self, o):
+        if type(o) in _SCALARS:
+            return Vec([o * x for x in self.v])
+        return self._rbin(o, lambda a, b: a * b)
+    def __truediv__(self, o):
+        if type(o) in _SCALARS:
+            return Vec([x / o for x in self.v])
+        return self._bin(o, lambda a, b: a / b)
     def __rtruediv__(self, o): return self._rbin(o, lambda a, b: a / b)
     def __floordiv__(self, o): return self._bin(o, lambda a, b: a // b)
     def __rfloordiv__(self, o): return self._rbin(o, lambda a, b: a // b)
@@ -108,10 +136,16 @@ class Vec:
 
     # --- methods used by the examples
     def dot(self, o):
-        return _b.sum(a * b for a, b in zip(self.v, o))
+        a, b = self.v, (o.v if type(o) is Vec else o)
+        if len(a) == 3:
+            return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+        return _b.sum(x * y for x, y in zip(a, b))
 
     def norm(self, eps=0.0):
-        return _m.sqrt(_b.sum(a * a for a in self.v) + eps)
+        a = self.v
+        if len(a) == 3:
+            return _m.sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + eps)
+        return _m.sqrt(_b.sum(x * x for x in a) + eps)
 
     def norm_sqr(self):
         return _b.sum(a * a for a in self.v)
@@ -152,6 +186,13 @@ def _flatten(args):
 
 def _make_ctor(n, conv):
     def ctor(*args):
+        # fast path: n plain scalars (by far the most common call in scene scripts)
+        if len(args) == n:
+            for a in args:
+                if type(a) not in _SCALARS:
+                    break
+            else:
+                return Vec([conv(a) for a in args])
         vals = _flatten(args)
         if len(vals) == 1:
             vals = vals * n

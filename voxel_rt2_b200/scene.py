@@ -13,6 +13,8 @@ unchanged:
 Voxels live in host NumPy arrays (material int8[R,R,R], colour uint8[R,R,R,3], index + R/2)
 until finish() uploads them once (voxel_world.py:6-25 semantics: colour clamp + u8 truncation,
 material cast to int8)."""
+import ctypes
+import math
 import os
 import time
 from datetime import datetime
@@ -31,6 +33,17 @@ voxel_rt2_b200 headless renderer (no window):
 * VRT_SPP samples per pixel, image written to VRT_OUT or screenshot/
 ====================================================
 """
+
+
+def _f32(x):
+    """Round a Python number to float32 (Taichi's default_fp)."""
+    return ctypes.c_float(x).value
+
+
+def _u8(c):
+    x = _f32(c)
+    x = 0.0 if x < 0.0 else (1.0 if x > 1.0 else x)
+    return int(_f32(x * 255.0))  # x has 24 significant bits: the double product is exact, then one f32 rounding
 
 
 def _env_res():
@@ -82,8 +95,11 @@ class Scene:
     def round_idx(idx_):  # scene.py:131-137: f32 cast, ti.round, i32
         out = []
         for c in idx_:
-            f = float(np.float32(c))
-            out.append(int(np.floor(f + 0.5)) if f >= 0 else int(np.ceil(f - 0.5)))
+            if type(c) is int:
+                out.append(c)  # exact in float32 for every index that can address the grid
+                continue
+            f = _f32(c)
+            out.append(int(math.floor(f + 0.5)) if f >= 0 else int(math.ceil(f - 0.5)))
         return out
 
     def set_voxel(self, idx, mat, color):  # scene.py:139-141 -> pathtracer.py:1325-1328
@@ -97,11 +113,9 @@ class Scene:
             return  # the reference writes out of bounds silently; ignored here
         m = int(mat)
         self.voxel_material[i, j, k] = ((m + 128) % 256) - 128  # ti.cast(mat, ti.i8) wraps
-        c = self.voxel_color[i, j, k]
-        for q in range(3):  # rgb32f_to_rgb8: clamp, u8(c*255) truncation (math_utils.py:86-92)
-            x = float(np.float32(color[q]))
-            x = 0.0 if x < 0.0 else (1.0 if x > 1.0 else x)
-            c[q] = int(np.float32(x) * np.float32(255.0))
+        # rgb32f_to_rgb8: clamp, u8(c * 255) truncation in float32 (math_utils.py:86-92)
+        r, g, b = color
+        self.voxel_color[i, j, k] = (_u8(r), _u8(g), _u8(b))
 
     def get_voxel(self, idx):  # scene.py:143-146 -> pathtracer.py:1330-1334
         from taichi.math import vec3
