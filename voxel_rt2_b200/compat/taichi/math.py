@@ -211,8 +211,43 @@ def _to_i(x):
     return _b.int(x)  # truncation toward zero, like a Taichi i32 cast
 
 
-vec2, vec3, vec4 = _make_ctor(2, _to_f), _make_ctor(3, _to_f), _make_ctor(4, _to_f)
-ivec2, ivec3, ivec4 = _make_ctor(2, _to_i), _make_ctor(3, _to_i), _make_ctor(4, _to_i)
+_vec2g, _vec3g, _vec4g = _make_ctor(2, _to_f), _make_ctor(3, _to_f), _make_ctor(4, _to_f)
+_ivec3g = _make_ctor(3, _to_i)
+_new = object.__new__
+
+
+def vec3(*args):
+    if len(args) == 3:
+        a, b, c = args
+        if type(a) in _SCALARS and type(b) in _SCALARS and type(c) in _SCALARS:
+            r = _new(Vec)
+            _set(r, "v", [_b.float(a), _b.float(b), _b.float(c)])
+            return r
+    return _vec3g(*args)
+
+
+def vec2(*args):
+    if len(args) == 2:
+        a, b = args
+        if type(a) in _SCALARS and type(b) in _SCALARS:
+            r = _new(Vec)
+            _set(r, "v", [_b.float(a), _b.float(b)])
+            return r
+    return _vec2g(*args)
+
+
+def ivec3(*args):
+    if len(args) == 3:
+        a, b, c = args
+        if type(a) in _SCALARS and type(b) in _SCALARS and type(c) in _SCALARS:
+            r = _new(Vec)
+            _set(r, "v", [_b.int(a), _b.int(b), _b.int(c)])
+            return r
+    return _ivec3g(*args)
+
+
+vec4 = _vec4g
+ivec2, ivec4 = _make_ctor(2, _to_i), _make_ctor(4, _to_i)
 uvec2, uvec3, uvec4 = ivec2, ivec3, ivec4
 
 
