@@ -151,6 +151,17 @@ int vrt_reset(vrt_ctx* ctx);
  * for device-side collectives (NCCL all-reduce through torch.distributed). */
 int vrt_accum_device_ptr(vrt_ctx* ctx, void** ptr, uint64_t* bytes);
 
+/* Multi-GPU merge without a separate collective (one process per GPU on one NVLink box): every
+ * rank exports its accumulation buffer (cudaIpcMemHandle_t, 64 bytes), the displaying rank opens
+ * the peers' buffers and ONE kernel reads all partial sums over NVLink peer mappings, adds them to
+ * its own and applies _render_to_image (pathtracer.py:634-662) — reduce + tonemap fused. The caller
+ * orders the ranks (a barrier after the peers' vrt_accumulate and another before they touch the
+ * buffer again). ldr_rgba may be NULL (result stays on the device, see vrt_resolve_ldr_device). */
+int vrt_accum_ipc_handle(vrt_ctx* ctx, void* handle64);
+int vrt_open_peer_accum(vrt_ctx* ctx, const void* handle64, void** peer_ptr);
+int vrt_close_peer_accum(vrt_ctx* ctx, void* peer_ptr);
+int vrt_fetch_ldr_merged(vrt_ctx* ctx, const void* const* peer_ptrs, int32_t n_peers, float* ldr_rgba);
+
 /* Renderer.color_buffer after accumulate: mean linear radiance, float4 [height][width]. */
 int vrt_fetch_hdr(vrt_ctx* ctx, float* rgba);
 /* Renderer.fetch_image / _render_to_image (pathtracer.py:634-662,1321-1323) */

@@ -538,3 +538,16 @@ def test_full_size_properties_1080p_256(vrt):
     assert cells.min() >= 0 and cells.max() < R
     n = hits["normal"][kinds == 2]
     assert (np.abs(n).sum(axis=-1) >= 1).all()
+
+
+def test_merged_resolve_without_peers_equals_fetch_image(vrt):
+    """vrt_fetch_ldr_merged with zero peers is the plain tonemap pass (the N-GPU behaviour is checked
+    by tools/peer_merge_check.py under torchrun)."""
+    R = 32
+    g = vrt.Renderer(dx=2.0 / R, image_res=(64, 32), grid_res=R, sky_res=0, seed=1)
+    g.set_voxels(*scenes.random_grid(R, 0.3, 2))
+    g.set_background_color((0.2, 0.3, 0.4))
+    g.prepare_data()
+    g.accumulate(4)
+    assert np.array_equal(g.fetch_image_merged([]), g.fetch_image())
+    assert len(g.accum_ipc_handle()) == 64

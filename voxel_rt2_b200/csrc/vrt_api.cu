@@ -798,6 +798,51 @@ int vrt_resolve_ldr_device(vrt_ctx* ctx, void** ptr) {
   return rc;
 }
 
+int vrt_accum_ipc_handle(vrt_ctx* ctx, void* handle64) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(handle64, "vrt_accum_ipc_handle: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->d_accum));
+  memcpy(handle64, &h, sizeof h);
+  return VRT_OK;
+}
+
+int vrt_open_peer_accum(vrt_ctx* ctx, const void* handle64, void** peer_ptr) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(handle64 && peer_ptr, "vrt_open_peer_accum: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof h);
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *peer_ptr = p;
+  return VRT_OK;
+}
+
+int vrt_close_peer_accum(vrt_ctx* ctx, void* peer_ptr) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (peer_ptr) CK(cudaIpcCloseMemHandle(peer_ptr));
+  return VRT_OK;
+}
+
+int vrt_fetch_ldr_merged(vrt_ctx* ctx, const void* const* peer_ptrs, int32_t n_peers, float* ldr_rgba) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_ptrs), "vrt_fetch_ldr_merged: 0..8 peers");
+  CK(cudaSetDevice(ctx->device));
+  const int W = ctx->cfg.width, H = ctx->cfg.height;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(vrt_launch_resolve_merged(ctx->d_accum, reinterpret_cast<const float4* const*>(peer_ptrs), n_peers, ctx->d_out, W, H, ctx->cfg.exposure, ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (ldr_rgba) CK(cudaMemcpyAsync(ldr_rgba, ctx->d_out, (size_t)W * H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->stats.last_resolve_ms, ctx->ev0, ctx->ev1));
+  return VRT_OK;
+}
+
 int vrt_get_stats(vrt_ctx* ctx, vrt_stats* out) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(out, "vrt_get_stats: null pointer");

@@ -20,6 +20,8 @@ cudaError_t vrt_launch_moving_upsample(const float4* out, float4* full, int W, i
 size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem);
 // vrt_restir.cu — spatial_GRIS (pathtracer.py:815-989); adds the frame's colour into P.accum
 cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t frame, cudaStream_t st);
+cudaError_t vrt_launch_resolve_merged(const float4* accum, const float4* const* peers, int n_peers, float4* ldr, int W, int H, float exposure,
+                                      cudaStream_t st);
 cudaError_t vrt_launch_resolve(const float4* accum, float4* hdr, float4* ldr, int W, int H, float exposure, cudaStream_t st);
 
 // vrt_build.cu — voxel arrays ([x][y][z], z fastest) -> bricks, colour SoA, upper pyramid

@@ -508,6 +508,41 @@ __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accu
   }
 }
 
+// Fused multi-GPU merge + tonemap: rank-local sums plus up to 7 peers' partial sums read through
+// NVLink peer mappings (ld.global on cudaIpc-mapped pointers), then the same tonemap as k_resolve.
+// 16-byte loads, one pixel per thread: each peer contributes one coalesced 512-byte request per warp.
+struct PeerPtrs {
+  const float4* p[8];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_resolve_merged(const float4* __restrict__ accum, PeerPtrs peers, float4* __restrict__ ldr, int W, int H,
+                                                        float exposure) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= W * H) return;
+  float4 a = accum[idx];
+#pragma unroll 1
+  for (int k = 0; k < peers.n; k++) {
+    const float4 b = peers.p[k][idx];
+    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+  }
+  const int i = idx % W, j = idx / W;
+  const float inv = a.w > 0.0f ? 1.0f / a.w : 0.0f;
+  const float ux = (float)i / (float)W - 0.5f, uy = (float)j / (float)H - 0.5f;
+  const float s = (1.0f - 0.9f * fmaxf(sqrtf(ux * ux + uy * uy), 0.0f)) * exposure;
+  ldr[idx] = make_float4(saturate(powf(uchimura1(a.x * inv * s), 1.0f / 2.2f)), saturate(powf(uchimura1(a.y * inv * s), 1.0f / 2.2f)),
+                         saturate(powf(uchimura1(a.z * inv * s), 1.0f / 2.2f)), 1.0f);
+}
+
+cudaError_t vrt_launch_resolve_merged(const float4* accum, const float4* const* peers, int n_peers, float4* ldr, int W, int H, float exposure,
+                                      cudaStream_t st) {
+  PeerPtrs pp;
+  pp.n = n_peers;
+  for (int k = 0; k < 8; k++) pp.p[k] = k < n_peers ? peers[k] : nullptr;
+  const int n = W * H;
+  k_resolve_merged<<<(n + 255) / 256, 256, 0, st>>>(accum, pp, ldr, W, H, exposure);
+  return cudaGetLastError();
+}
+
 // -------------------------------------------------------------------------------- launchers
 static size_t smem_bytes(const Params& P, int* upper_in_smem) {
   size_t need = (size_t)SMEM_FIXED_WORDS * 4 + (size_t)P.upper_words * 4;

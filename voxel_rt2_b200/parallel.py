@@ -43,3 +43,40 @@ def mean_from_accumulation(accum):
     out = accum.clone()
     out[..., :3] = torch.where(w > 0, accum[..., :3] / w.clamp_min(1.0), torch.zeros_like(accum[..., :3]))
     return out
+
+
+class PeerMerge:
+    """Fused alternative to merge_accumulation + fetch_image for the displaying rank: rank 0 maps
+    the other ranks' accumulation buffers (CUDA IPC over NVLink) and sums them inside the tonemap
+    kernel (`vrt_fetch_ldr_merged`). Usage per frame batch, on every rank:
+
+        r.accumulate(spp); pm.ready()          # barrier: all partial sums are complete
+        if rank == 0: img = pm.fetch_image()   # one kernel: peer reads + reduce + tonemap
+        pm.release()                           # barrier: peers may reset / continue
+    """
+
+    def __init__(self, renderer, group=None):
+        import torch.distributed as dist
+
+        self.r, self.group = renderer, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, renderer.accum_ipc_handle(), group=group)
+        self.peers = []
+        if self.rank == 0:
+            self.peers = [renderer.open_peer_accum(h) for k, h in enumerate(handles) if k != 0]
+
+    def ready(self):
+        import torch.distributed as dist
+
+        dist.barrier(group=self.group)
+
+    release = ready
+
+    def fetch_image(self, out=None):
+        return self.r.fetch_image_merged(self.peers, out)
+
+    def close(self):
+        for p in self.peers:
+            self.r.close_peer_accum(p)
+        self.peers = []

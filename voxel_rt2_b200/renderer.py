@@ -278,6 +278,30 @@ class Renderer:
         self._check(self._lib.vrt_accum_device_ptr(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    # ---- fused peer-read merge + tonemap (one process per GPU, NVLink peer mappings)
+    def accum_ipc_handle(self):
+        """64-byte cudaIpcMemHandle_t of the accumulation buffer (bytes), to hand to another rank."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.vrt_accum_ipc_handle(self._h, buf))
+        return bytes(buf.raw)
+
+    def open_peer_accum(self, handle):
+        p = C.c_void_p()
+        self._check(self._lib.vrt_open_peer_accum(self._h, C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+        return p.value
+
+    def close_peer_accum(self, ptr):
+        self._check(self._lib.vrt_close_peer_accum(self._h, C.c_void_p(ptr)))
+
+    def fetch_image_merged(self, peer_ptrs, out=None):
+        """Tonemapped image of (own + peers') accumulation buffers, summed inside the tonemap kernel."""
+        n = len(peer_ptrs)
+        arr = (C.c_void_p * max(n, 1))(*peer_ptrs)
+        if out is None:
+            out = np.empty((self.image_res[1], self.image_res[0], 4), np.float32)
+        self._check(self._lib.vrt_fetch_ldr_merged(self._h, arr, n, _fp(out)))
+        return out
+
     def accum_tensor(self):
         """The float4 accumulation buffer as a torch CUDA tensor [H, W, 4] sharing memory with the
         library (for torch.distributed collectives)."""
