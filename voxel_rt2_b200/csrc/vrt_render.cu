@@ -311,9 +311,9 @@ __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_pa
     if (active) h = next_hit<STATS>(P, upper, unorm8, pos, d, state == ST_SHADOW, &tc, &c_hits);
 
     // ---- (3) classify
-    bool do_shade = false;
+    bool do_shade = false, escaped = false, sky_need = false;
     float visible = 0.0f;
-    f3 light_dir = d;
+    f3 light_dir = d, sky_dir = d;
     if (active) {
       if (state == ST_SEGMENT) {
         const uint32_t base = 8u * (uint32_t)depth;
@@ -347,29 +347,13 @@ __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_pa
           }
         }
         if (h.closest == VRT_INF) {
-          // escaped: background or sky tables + sun disk (pathtracer.py:499-511)
-          const float hit_sun = dot(P.light_dir, d) >= P.light_cos_max ? 1.0f : 0.0f;
-          f3 sky_scattering = P.background, sky_T = mk3(1.0f);
+          // escaped: background or sky tables + sun disk (pathtracer.py:499-511); the table
+          // lookup happens at the merged sky site (3b) below
+          escaped = true;
           if (P.use_sky) {
-            f3 dj = normalize(d + f3{rnd(key, base + 5), rnd(key, base + 6), rnd(key, base + 7)} * 0.0015f);
-            SkyTap t = sky_tap(P.sky_res, project_sky(dj, sky_fres));
-            sky_scattering = sky_fetch(P.sky_scatter, t);
-            sky_T = sky_fetch(P.sky_trans, t);
+            sky_dir = normalize(d + f3{rnd(key, base + 5), rnd(key, base + 6), rnd(key, base + 7)} * 0.0015f);
+            sky_need = true;
             if (STATS) c_escapes++;
-          }
-          f3 sky_emission = firefly_filter(sky_scattering + sky_T * sun_rad * hit_sun);
-          contrib += thr * sky_emission;
-          if (MOVING && depth == 0) primary_pos = mk3(0.0f), sky_ray = true;
-          if (RESTIR) {  // pathtracer.py:509-517
-            if (depth == 0) {
-              primary_pos = mk3(0.0f);
-              sky_ray = true;
-            } else if (depth == 1) {
-              rz.rc_pos = d;
-              rz.rc_incident_L = sky_emission;
-            } else {
-              rz.rc_incident_L += firefly_filter(thr_after_rc * sky_emission);
-            }
           }
           finished = true;
         } else if (h.hit_light) {
@@ -397,6 +381,37 @@ __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_pa
         visible = h.closest >= VRT_INF ? 1.0f : 0.0f;
         state = ST_SEGMENT;
         do_shade = true;
+        if (visible != 0.0f && P.use_sky) {
+          sky_need = true;  // sky_dir == d == the sun sample the shadow ray was traced along
+          if (STATS) c_nee++;
+        }
+      }
+    }
+
+    // ---- (3b) merged sky site: one projection + bilinear footprint per lane for both users of
+    // the tables, escaped segments (scattering + transmittance, atmos.py:94-115) and visible sun
+    // samples (transmittance only, atmos.py:117-131)
+    f3 sky_T = mk3(1.0f), sky_scattering = P.background;
+    if (sky_need) {
+      const SkyTap t = sky_tap(P.sky_res, project_sky(sky_dir, sky_fres));
+      sky_T = sky_fetch(P.sky_trans, t);
+      if (escaped) sky_scattering = sky_fetch(P.sky_scatter, t);
+    }
+    if (escaped) {
+      const float hit_sun = dot(P.light_dir, d) >= P.light_cos_max ? 1.0f : 0.0f;
+      f3 sky_emission = firefly_filter(sky_scattering + sky_T * sun_rad * hit_sun);
+      contrib += thr * sky_emission;
+      if (MOVING && depth == 0) primary_pos = mk3(0.0f), sky_ray = true;
+      if (RESTIR) {  // pathtracer.py:509-517
+        if (depth == 0) {
+          primary_pos = mk3(0.0f);
+          sky_ray = true;
+        } else if (depth == 1) {
+          rz.rc_pos = d;
+          rz.rc_incident_L = sky_emission;
+        } else {
+          rz.rc_incident_L += firefly_filter(thr_after_rc * sky_emission);
+        }
       }
     }
 
@@ -412,12 +427,6 @@ __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_pa
         float lpdf;
         eval_and_pdf(m, s_view, s_n, light_dir, tang, bitang, bd, bs, lpdf);
         const float mis = power_heuristic(light_pdf_axis, lpdf);
-        f3 sky_T = mk3(1.0f);
-        if (P.use_sky) {
-          SkyTap t = sky_tap(P.sky_res, project_sky(light_dir, sky_fres));
-          sky_T = sky_fetch(P.sky_trans, t);
-          if (STATS) c_nee++;
-        }
         const float ndl = dot(light_dir, s_n);
         const f3 lr = sky_T * sun_rad * ndl;
         if (depth == 0) {
