@@ -1,0 +1,246 @@
+"""Golden vectors computed by the REFERENCE'S OWN SOURCE (/root/reference/renderer/*.py), executed
+here through the float32 Taichi emulator in oracle/ti_emu (Taichi itself cannot be installed in
+this container). Run in the authoring container:
+
+    python tests/golden/make_ref_vectors.py [section ...]
+
+Output: tests/golden/ref_*.npz (committed; /root/reference is not needed to run the tests).
+tests/test_reference_vectors.py checks the CPU oracle against them.
+
+Deviations from "the reference exactly as shipped", each a documented quirk:
+  A1  the occupancy field is allocated 2 R^3 bits so the reference's LOD base offsets stay inside
+      the field (as shipped they overrun the allocation; the intended bits are the same);
+  A3  a query for a cell outside the grid (the reference reads an aliased / out-of-range word there)
+      is answered "empty" and the ray is recorded with flag 1: only its hit distance is compared
+      (the oracle's pin is "leaving the grid is a miss");
+  A4  directions with an exactly-zero component are not generated (0 * inf in the reference).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ti_emu"))
+sys.path.insert(0, REF)
+os.chdir(REF)  # the reference opens default_material_set.csv / textures by relative path
+
+import taichi as ti  # noqa: E402  (the emulator)
+
+F = np.float32
+
+
+def vec(a):
+    return ti.Matrix(np.asarray(a, dtype=np.float32), _noconv=True)
+
+
+def unit(rng, n):
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return v.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------- traversal
+def grids():
+    rng = np.random.default_rng(20260101)
+    g = {}
+    g["rand16_15"] = (rng.random((16, 16, 16)) < 0.15).astype(np.int8)
+    g["rand32_40"] = (rng.random((32, 32, 32)) < 0.40).astype(np.int8)
+    s = np.zeros((32, 32, 32), np.int8)  # sparse structured: a slab, a column and isolated voxels
+    s[4:28, 3, 4:28] = 1
+    s[16, 4:30, 16] = 1
+    s[29, 29, 29] = s[0, 0, 0] = s[31, 31, 0] = s[7, 20, 9] = 1
+    g["struct32"] = s
+    return g
+
+
+def section_raytrace():
+    from renderer.math_utils import eps, inf
+    from renderer.raytracer import VoxelOctreeRaytracer
+
+    out = {}
+    for name, occ in grids().items():
+        R = occ.shape[0]
+        rt = VoxelOctreeRaytracer(R)
+        rt.occupancy = ti.field(ti.i32, shape=(2 * R ** 3 // 32 + 1,))  # A1
+        vox = ti.field(ti.i8, shape=(R, R, R))
+        vox.from_numpy(occ)
+        rt._update_lods(vox, ti.Vector([0, 0, 0]))
+        # occupancy bits of every LOD, through the reference's own query function
+        bits = []
+        for lod in range(rt.n_lods):
+            r = R >> lod
+            b = np.zeros((r, r, r), np.uint8)
+            for x in range(r):
+                for y in range(r):
+                    for z in range(r):
+                        b[x, y, z] = 1 if rt.query_occupancy(ti.Vector([x, y, z], ti.i32), np.int32(lod)) else 0
+            bits.append(b.reshape(-1))
+        out[name + "_grid"] = occ
+        out[name + "_lodbits"] = np.concatenate(bits)
+
+        inner = VoxelOctreeRaytracer.query_occupancy
+
+        oob = [0]
+
+        def checked(ipos, lod, _rt=rt, _R=R):
+            r = _R >> int(lod)
+            if int(ipos.a.min()) < 0 or int(ipos.a.max()) >= r:
+                oob[0] = 1  # A3: the cell is outside the grid; read it as empty (robust-buffer behaviour)
+                return False
+            return inner(_rt, ipos, lod)
+
+        rt.query_occupancy = checked
+        rng = np.random.default_rng(R * 1000 + len(name))
+        n = 300
+        o = np.empty((n, 3), np.float32)
+        d = unit(rng, n)
+        third = n // 3
+        # outside origins aimed at the box, origins inside the box, origins on / near cell boundaries
+        o[:third] = (R / 2 + unit(rng, third) * R * rng.uniform(0.9, 2.0, (third, 1))).astype(np.float32)
+        tgt = rng.uniform(0, R, (third, 3))
+        dd = tgt - o[:third]
+        d[:third] = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32)
+        o[third:2 * third] = rng.uniform(0, R, (third, 3)).astype(np.float32)
+        o[2 * third:] = (np.floor(rng.uniform(0, R, (n - 2 * third, 3))) + rng.choice([0.0, 1e-6, 0.5, 0.999999], (n - 2 * third, 3))).astype(np.float32)
+        t = np.zeros(n, np.float32)
+        cell = np.zeros((n, 3), np.int32)
+        nrm = np.zeros((n, 3), np.float32)
+        iters = np.zeros(n, np.int32)
+        flag = np.zeros(n, np.int32)
+        for i in range(n):
+            oob[0] = 0
+            ht, hc, hn, hi = rt.raytrace(vec(o[i]), vec(d[i]), eps, inf)
+            t[i], cell[i], nrm[i], iters[i], flag[i] = ht, hc.a, hn.a, hi, oob[0]
+        out[name + "_o"], out[name + "_d"], out[name + "_t"] = o, d, t
+        out[name + "_cell"], out[name + "_normal"], out[name + "_iters"], out[name + "_flag"] = cell, nrm, iters, flag
+        print("raytrace %s: %d rays, %d hits, %d out-of-grid (A3)" % (name, n, int(np.isfinite(t).sum()), int(flag.sum())))
+    np.savez_compressed(os.path.join(HERE, "ref_raytrace.npz"), **out)
+
+
+# ------------------------------------------------------------------------------ math helpers
+def section_math():
+    import renderer.math_utils as mu
+
+    rng = np.random.default_rng(7)
+    out = {}
+    n = 64
+    v = unit(rng, n)
+    bx, by = np.zeros((n, 3), F), np.zeros((n, 3), F)
+    for i in range(n):
+        x, y = mu.make_orthonormal_basis(vec(v[i]))
+        bx[i], by[i] = x.a, y.a
+    out["onb_n"], out["onb_x"], out["onb_y"] = v, bx, by
+    # octahedral 2 x f16 round trip (math_utils.py:201-215)
+    enc, dec = np.zeros((n, 2), np.float16), np.zeros((n, 3), F)
+    for i in range(n):
+        e = mu.encode_unit_vector_3x16(vec(v[i]))
+        enc[i] = e.a
+        dec[i] = mu.decode_unit_vector_3x16(e).a
+    out["oct_v"], out["oct_enc"], out["oct_dec"] = v, enc, dec
+    # hash3 (math_utils.py:217-229)
+    hx = rng.integers(0, 2 ** 32, (n, 3), dtype=np.uint64).astype(np.uint32)
+    out["hash3_in"] = hx
+    out["hash3_out"] = np.array([mu.hash3(np.uint32(a), np.uint32(b), np.uint32(c)) for a, b, c in hx], np.uint32)
+    # encode_material / decode (math_utils.py:231-247): mat id + albedo -> u32
+    mid = rng.integers(0, 128, n).astype(np.int32)
+    alb = rng.random((n, 3)).astype(F)
+    out["encmat_id"], out["encmat_albedo"] = mid, alb
+    out["encmat_out"] = np.array([mu.encode_material(np.int32(m), vec(a)) for m, a in zip(mid, alb)], np.uint32)
+    # u8 colour conversions (math_utils.py:86-100)
+    c = np.concatenate([rng.random((n - 4, 3)), [[0, 0, 0], [1, 1, 1], [1.5, -0.2, 0.5], [0.999, 0.001, 0.5]]]).astype(F)
+    out["rgb_in"] = c
+    out["rgb_u8"] = np.array([mu.rgb32f_to_rgb8(vec(x)).a for x in c], np.uint8)
+    out["rgb_back"] = np.array([mu.rgb8_to_rgb32f(ti.Matrix(u, _noconv=True)).a for u in out["rgb_u8"]], F)
+    # uchimura tonemap (math_utils.py:160-186) and luminance
+    x = np.concatenate([rng.random((n, 3)) * 4.0, [[0, 0, 0], [0.22, 0.22, 0.22], [0.532, 0.1, 10.0]]]).astype(F)
+    out["uchi_in"] = x
+    out["uchi_out"] = np.array([mu.uchimura(vec(a)).a for a in x], F)
+    out["lum_out"] = np.array([mu.luminance(vec(a)) for a in x], F)
+    # cone pdf / samples with supplied random numbers (math_utils.py:44-63)
+    u = rng.random((n, 2)).astype(F)
+    cm = np.cos(rng.uniform(0.005, 0.3, n)).astype(F)
+    samples = np.zeros((n, 3), F)
+    hemi = np.zeros((n, 3), F)
+    for i in range(n):
+        q = list(u[i])
+        ti.set_random_source(lambda name: q.pop(0))
+        samples[i] = mu.sample_cone_oriented(cm[i], vec(v[i])).a
+        q = list(u[i])
+        hemi[i] = mu.sample_cosine_weighted_hemisphere(vec(v[i])).a
+    ti.set_random_source(None)
+    out["cone_u"], out["cone_cosmax"], out["cone_n"], out["cone_dir"], out["hemi_dir"] = u, cm, v, samples, hemi
+    np.savez_compressed(os.path.join(HERE, "ref_math.npz"), **out)
+    print("math: %d vectors per helper" % n)
+
+
+# -------------------------------------------------------------------------------------- BSDF
+def section_bsdf():
+    from renderer.materials import MaterialList
+    from renderer.math_utils import make_orthonormal_basis
+
+    mats = MaterialList()
+    bsdf = mats.bsdf
+    rng = np.random.default_rng(11)
+    ids = [0, 1, 2, 10, 11, 20, 21, 22, 30, 31, 32, 40, 41, 50, 51, 52, 53, 54, 80, 81, 82]
+    per = 12
+    n = len(ids) * per
+    mat_id = np.repeat(np.array(ids, np.int32), per)
+    albedo = rng.uniform(0.05, 1.0, (n, 3)).astype(F)
+    nrm = unit(rng, n)
+    # view / light directions in the upper hemisphere of n (plus a few below it)
+    def hemi(k):
+        w = unit(rng, n)
+        s = np.sign((w * nrm).sum(1, keepdims=True))
+        s[s == 0] = 1
+        w = w * s
+        flip = rng.random(n) < k
+        w[flip] = -w[flip]
+        return w.astype(F)
+
+    v, l = hemi(0.0), hemi(0.1)
+    u3 = rng.random((n, 3)).astype(F)
+    ev_d, ev_s = np.zeros((n, 3), F), np.zeros((n, 3), F)
+    pdf = np.zeros(n, F)
+    sdir, sbrdf = np.zeros((n, 3), F), np.zeros((n, 3), F)
+    spdf, slobe = np.zeros(n, F), np.zeros(n, np.int32)
+    lw = np.zeros((n, 3), F)
+    lobe_d, lobe_s, lobe_pdf = np.zeros((n, 3, 3), F), np.zeros((n, 3, 3), F), np.zeros((n, 3), F)
+    table = np.zeros((128, 14), F)
+    names = ["subsurface", "metallic", "specular", "specular_tint", "roughness", "anisotropic", "sheen", "sheen_tint", "clearcoat",
+             "clearcoat_gloss", "ior_minus_one"]
+    for m in range(128):
+        s = mats.mat_list[m]
+        table[m, :3] = s.base_col.a
+        table[m, 3:] = [getattr(s, k) for k in names]
+    for i in range(n):
+        m = mats.mat_list[int(mat_id[i])]
+        m.base_col = vec(albedo[i])
+        N, V, L = vec(nrm[i]), vec(v[i]), vec(l[i])
+        tang, bitang = make_orthonormal_basis(N)
+        d, s = bsdf.disney_evaluate_split(m, V, N, L, tang, bitang)
+        ev_d[i], ev_s[i] = d.a, s.a
+        pdf[i] = bsdf.pdf_disney(m, V, N, L, tang, bitang)
+        lw[i] = [float(x) for x in bsdf.disney_get_lobe_probabilities(m)]
+        q = list(u3[i])
+        ti.set_random_source(lambda name: q.pop(0))
+        sd, sb, sp, sl = bsdf.sample_disney(m, V, N, tang, bitang)
+        ti.set_random_source(None)
+        sdir[i], sbrdf[i], spdf[i], slobe[i] = sd.a, sb.a, sp, sl
+        for lobe in range(3):
+            a, b = bsdf.disney_evaluate_lobewise_split(m, V, N, L, tang, bitang, np.int32(lobe))
+            lobe_d[i, lobe], lobe_s[i, lobe] = a.a, b.a
+            lobe_pdf[i, lobe] = bsdf.pdf_disney_lobewise(m, V, N, L, tang, bitang, np.int32(lobe))
+    np.savez_compressed(os.path.join(HERE, "ref_bsdf.npz"), material_table=table, mat_id=mat_id, albedo=albedo, n=nrm, v=v, l=l, u3=u3,
+                        eval_d=ev_d, eval_s=ev_s, pdf=pdf, lobe_w=lw, sample_dir=sdir, sample_brdf=sbrdf, sample_pdf=spdf, sample_lobe=slobe,
+                        lobe_d=lobe_d, lobe_s=lobe_s, lobe_pdf=lobe_pdf)
+    print("bsdf: %d probes over %d materials" % (n, len(ids)))
+
+
+SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf}
+
+if __name__ == "__main__":
+    for s in (sys.argv[1:] or list(SECTIONS)):
+        SECTIONS[s]()
