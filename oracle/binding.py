@@ -59,6 +59,8 @@ def load():
     lib.orc_oct_round_trip.argtypes = [C.c_int, fp, fp, fp]
     lib.orc_hash3.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
     lib.orc_hash3.restype = C.c_uint32
+    lib.orc_math_probe.argtypes = [C.c_int, C.c_int, fp, fp, fp]
+    lib.orc_bsdf_lobewise_probe.argtypes = [P, C.c_int, ip, fp, fp, fp, fp, fp, fp]
     lib.orc_accumulate_moving.argtypes = [P, C.c_int, C.c_float, C.c_float]
     lib.orc_fetch_hdr_moving.argtypes = [P, fp]
     lib.orc_reset_moving.argtypes = [P]
@@ -317,6 +319,13 @@ class OracleRenderer:
     def occupancy(self, x, y, z, lod):
         return self._lib.orc_occupancy(self._h, int(x), int(y), int(z), int(lod))
 
+    def bsdf_lobewise_probe(self, mat_id, albedo, v, n, l):
+        mat_id = np.ascontiguousarray(mat_id, np.int32)
+        k = mat_id.size
+        out, lw = np.empty((k, 3, 7), np.float32), np.empty((k, 3), np.float32)
+        self._lib.orc_bsdf_lobewise_probe(self._h, k, _ip(mat_id), _fp(_f32(albedo)), _fp(_f32(v)), _fp(_f32(n)), _fp(_f32(l)), _fp(out), _fp(lw))
+        return out, lw
+
     def bsdf_probe(self, mat_id, albedo, v, n, l, u3):
         mat_id = np.ascontiguousarray(mat_id, np.int32)
         k = mat_id.size
@@ -324,3 +333,14 @@ class OracleRenderer:
         self._lib.orc_bsdf_probe(self._h, k, _ip(mat_id), _fp(_f32(albedo)), _fp(_f32(v)), _fp(_f32(n)), _fp(_f32(l)), _fp(_f32(u3)),
                                  _fp(out))
         return out
+
+
+def math_probe(kind, a, b=None, out_per=3):
+    """orc_math_probe: see oracle.cpp for the kinds."""
+    lib = load()
+    a = np.ascontiguousarray(a, np.float32)
+    n = a.shape[0]
+    b = np.ascontiguousarray(b if b is not None else np.zeros((n, 3)), np.float32)
+    out = np.zeros((n, out_per) if out_per > 1 else (n,), np.float32)
+    lib.orc_math_probe(int(kind), n, _fp(a), _fp(b), _fp(out))
+    return out

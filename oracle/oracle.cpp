@@ -866,6 +866,52 @@ void orc_oct_round_trip(int n, const float* v, float* enc, float* dec) {
   }
 }
 uint32_t orc_hash3(uint32_t x, uint32_t y, uint32_t z) { return hash3(x, y, z); }
+// probes of the small helpers, checked against vectors computed by the reference's own math_utils.py
+// kind: 0 make_orthonormal_basis (in: n; out: x, y)   1 sample_cone_oriented (in: n, cosmax, u0, u1; out: dir)
+//       2 sample_cosine_weighted_hemisphere (in: n, -, u0, u1; out: dir)   3 uchimura (in: rgb; out: rgb)
+//       4 luminance (in: rgb; out: 1)   5 encode_material (in: albedo, mat id as float; out: u32 bits)
+void orc_math_probe(int kind, int n, const float* a, const float* b, float* out) {
+  for (int i = 0; i < n; i++) {
+    V3 v{a[3 * i], a[3 * i + 1], a[3 * i + 2]};
+    if (kind == 0) {
+      V3 x, y;
+      make_orthonormal_basis(v, x, y);
+      float* o = out + 6 * i;
+      o[0] = x.x, o[1] = x.y, o[2] = x.z, o[3] = y.x, o[4] = y.y, o[5] = y.z;
+    } else if (kind == 1 || kind == 2) {
+      V3 d = kind == 1 ? sample_cone_oriented(b[3 * i], v, b[3 * i + 1], b[3 * i + 2]) : sample_cosine_weighted_hemisphere(v, b[3 * i + 1], b[3 * i + 2]);
+      out[3 * i] = d.x, out[3 * i + 1] = d.y, out[3 * i + 2] = d.z;
+    } else if (kind == 3) {
+      V3 d = uchimura(v);
+      out[3 * i] = d.x, out[3 * i + 1] = d.y, out[3 * i + 2] = d.z;
+    } else if (kind == 4) {
+      out[i] = luminance(v);
+    } else if (kind == 5) {
+      uint32_t e = encode_material((int)b[i], v);
+      std::memcpy(out + i, &e, 4);
+    }
+  }
+}
+// lobe-wise BSDF probes (bsdf.py:306-380): out[n][3 lobes][7] = {diffuse rgb, specular rgb, pdf}; lobe_w[n][3]
+void orc_bsdf_lobewise_probe(void* p, int n, const int* mat_id, const float* albedo, const float* v, const float* nrm, const float* l,
+                             float* out, float* lobe_w) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < n; i++) {
+    Mat m = mat_at(*c, mat_id[i]);
+    m.base_col = V3{albedo[3 * i], albedo[3 * i + 1], albedo[3 * i + 2]};
+    V3 vv{v[3 * i], v[3 * i + 1], v[3 * i + 2]}, nn{nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]}, ll{l[3 * i], l[3 * i + 1], l[3 * i + 2]};
+    V3 tang, bitang;
+    make_orthonormal_basis(nn, tang, bitang);
+    lobe_probabilities(m, lobe_w[3 * i], lobe_w[3 * i + 1], lobe_w[3 * i + 2]);
+    for (int lobe = 0; lobe < 3; lobe++) {
+      V3 d, s;
+      disney_evaluate_lobewise_split(m, vv, nn, ll, tang, bitang, lobe, d, s);
+      float* o = out + (3 * i + lobe) * 7;
+      o[0] = d.x, o[1] = d.y, o[2] = d.z, o[3] = s.x, o[4] = s.y, o[5] = s.z;
+      o[6] = pdf_disney_lobewise(m, vv, nn, ll, tang, bitang, lobe);
+    }
+  }
+}
 // ------------------------------------------------------------------ moving-camera temporal path
 // Renderer.accumulate() with camera_is_moving = 1 (scene.py:214-228): render at render_scale with
 // albedo-demodulated diffuse (pathtracer.py:628-630), temporal_filter_prepass (:1020-1075),

@@ -651,7 +651,7 @@ def ti_iter(x):
     """Iterable of a (non-static) Taichi for loop: loop variables are i32."""
     if isinstance(x, range):
         return (np.int32(i) for i in x)
-    if isinstance(x, (Field, StructField)):
+    if isinstance(x, (Field, StructField, _NdArg)):
         return x._struct_for()
     if isinstance(x, np.ndarray):
         return (np.int32(i) for i in range(x.shape[0]))

@@ -51,3 +51,79 @@ def test_traversal_matches_reference_raytrace_bit_for_bit(oracle, grid):
     # rays that step out of the grid before `hit_distance > far` fires — the reference
     # (reading the out-of-range cell as empty) and the oracle's pin both report a miss
     assert np.isinf(rt[~ok]).all() and np.isinf(t[~ok]).all()
+
+
+def _close(a, b, rtol, atol=0.0):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b) <= atol + rtol * np.abs(b)
+
+
+def test_math_helpers_match_reference(oracle):
+    """renderer/math_utils.py helpers: orthonormal basis, cone and cosine-hemisphere samplers fed the
+    same random numbers, Uchimura tonemap, luminance, material packing, octahedral coding, hash3."""
+    z = np.load(os.path.join(G, "ref_math.npz"))
+    lib = oracle.load()
+    onb = oracle.math_probe(0, z["onb_n"], out_per=6)
+    assert _close(onb[:, :3], z["onb_x"], 1e-6, 1e-7).all() and _close(onb[:, 3:], z["onb_y"], 1e-6, 1e-7).all()
+    b = np.concatenate([z["cone_cosmax"][:, None], z["cone_u"]], axis=1)
+    assert _close(oracle.math_probe(1, z["cone_n"], b), z["cone_dir"], 2e-6, 2e-7).all()
+    assert _close(oracle.math_probe(2, z["cone_n"], b), z["hemi_dir"], 2e-6, 2e-7).all()
+    assert _close(oracle.math_probe(3, z["uchi_in"]), z["uchi_out"], 2e-6, 1e-7).all()
+    assert _close(oracle.math_probe(4, z["uchi_in"], out_per=1), z["lum_out"], 1e-6, 1e-7).all()
+    enc = oracle.math_probe(5, z["encmat_albedo"], z["encmat_id"].astype(np.float32), out_per=1).view(np.uint32)
+    assert np.array_equal(enc, z["encmat_out"])
+    for (x, y, w), h in zip(z["hash3_in"], z["hash3_out"]):
+        assert lib.orc_hash3(int(x), int(y), int(w)) == int(h)
+    # octahedral 2 x f16 coding of unit vectors (math_utils.py:201-215)
+    import ctypes as C
+
+    v = np.ascontiguousarray(z["oct_v"], np.float32)
+    enc = np.zeros((len(v), 2), np.float32)
+    dec = np.zeros((len(v), 3), np.float32)
+    fp = C.POINTER(C.c_float)
+    lib.orc_oct_round_trip(len(v), v.ctypes.data_as(fp), enc.ctypes.data_as(fp), dec.ctypes.data_as(fp))
+    assert np.array_equal(enc.astype(np.float16).view(np.uint16), z["oct_enc"].view(np.uint16))
+    assert _close(dec, z["oct_dec"], 1e-6, 1e-7).all()
+
+
+def test_host_colour_quantisation_matches_reference():
+    """rgb32f_to_rgb8 / rgb8_to_rgb32f (math_utils.py:86-100) vs the colour conversion of the host's
+    Scene.set_voxel / get_voxel."""
+    from voxel_rt2_b200.scene import _f32, _u8
+
+    z = np.load(os.path.join(G, "ref_math.npz"))
+    for c, u, back in zip(z["rgb_in"], z["rgb_u8"], z["rgb_back"]):
+        assert [_u8(float(x)) for x in c] == [int(x) for x in u]
+        assert [np.float32(_f32(int(x) / 255.0)) for x in u] == [x for x in back]
+
+
+def test_material_table_matches_reference_material_list():
+    """MaterialList (materials.py:47-112 + default_material_set.csv) read back field by field."""
+    from voxel_rt2_b200.materials import material_table
+
+    z = np.load(os.path.join(G, "ref_bsdf.npz"))
+    assert np.array_equal(np.asarray(material_table(), np.float32).reshape(128, 14), z["material_table"])
+
+
+def test_disney_bsdf_matches_reference(oracle):
+    """bsdf.py evaluated by the reference source for 252 (material, albedo, v, n, l, u) probes over all
+    21 material rows: disney_evaluate_split, pdf_disney, lobe probabilities, the lobe-wise variants and
+    sample_disney (direction, brdf, pdf, lobe) with the same three random numbers."""
+    z = np.load(os.path.join(G, "ref_bsdf.npz"))
+    o = _orc(oracle, 16)
+    out = o.bsdf_probe(z["mat_id"], z["albedo"], z["v"], z["n"], z["l"], z["u3"])
+    rt, at = 2e-6, 1e-7  # measured 1.5e-7: libm vs numpy float32 pow / sqrt / log differ by an ulp
+    assert _close(out[:, 0:3], z["eval_d"], rt, at).all()
+    assert _close(out[:, 3:6], z["eval_s"], rt, at).all()
+    assert _close(out[:, 6], z["pdf"], rt, at).all()
+    assert np.array_equal(out[:, 11].astype(np.int32), z["sample_lobe"])
+    assert _close(out[:, 7:10], z["sample_dir"], 1e-5, 2e-6).all()
+    good = np.isfinite(z["sample_pdf"]) & (np.abs(z["sample_pdf"]) < 1e6)
+    assert good.sum() > 200
+    assert _close(out[good, 10], z["sample_pdf"][good], 1e-4, 1e-6)  # sharp GGX lobes amplify the ulp of the sampled half vector.all()
+    assert _close(out[good, 12:15], z["sample_brdf"][good], 1e-4, 1e-6).all()
+    lw_out, lw = o.bsdf_lobewise_probe(z["mat_id"], z["albedo"], z["v"], z["n"], z["l"])
+    assert _close(lw, z["lobe_w"], 1e-6, 1e-7).all()
+    assert _close(lw_out[:, :, 0:3], z["lobe_d"], rt, at).all()
+    assert _close(lw_out[:, :, 3:6], z["lobe_s"], rt, at).all()
+    assert _close(lw_out[:, :, 6], z["lobe_pdf"], rt, at).all()
