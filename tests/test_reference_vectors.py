@@ -120,7 +120,7 @@ def test_disney_bsdf_matches_reference(oracle):
     assert _close(out[:, 7:10], z["sample_dir"], 1e-5, 2e-6).all()
     good = np.isfinite(z["sample_pdf"]) & (np.abs(z["sample_pdf"]) < 1e6)
     assert good.sum() > 200
-    assert _close(out[good, 10], z["sample_pdf"][good], 1e-4, 1e-6)  # sharp GGX lobes amplify the ulp of the sampled half vector.all()
+    assert _close(out[good, 10], z["sample_pdf"][good], 1e-4, 1e-6).all()  # sharp GGX lobes amplify the ulp of the sampled half vector
     assert _close(out[good, 12:15], z["sample_brdf"][good], 1e-4, 1e-6).all()
     lw_out, lw = o.bsdf_lobewise_probe(z["mat_id"], z["albedo"], z["v"], z["n"], z["l"])
     assert _close(lw, z["lobe_w"], 1e-6, 1e-7).all()
