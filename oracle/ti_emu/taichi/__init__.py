@@ -78,7 +78,7 @@ def _as_dtype(dt):
 def _kind(x):
     """Type of an operand: a numpy dtype for typed values, _WF / _WI for weak Python constants."""
     if isinstance(x, Matrix):
-        d = x.a.dtype
+        d = x.data.dtype
         return _WF if d == _F64 else (_WI if d == _I64 else d)
     if isinstance(x, (bool, np.bool_, int)):
         return _WI
@@ -127,7 +127,7 @@ def _np_dtype(k):
 
 def _raw(x, dt):
     if isinstance(x, Matrix):
-        return x.a if x.a.dtype == dt else x.a.astype(dt)
+        return x.data if x.data.dtype == dt else x.data.astype(dt)
     if isinstance(x, (list, tuple)):
         return _raw(Matrix(x), dt)
     if type(x) is int and np.issubdtype(dt, np.integer):  # wrap-around conversion of Python integers
@@ -171,6 +171,10 @@ def binop(op, a, b):
     if op == "@":
         return matmul(a, b)
     if isinstance(a, (Struct, np.ndarray)) or isinstance(b, (Struct, np.ndarray)) or a is None or b is None:
+        if isinstance(a, Matrix) and isinstance(b, np.ndarray):
+            return binop(op, a, Matrix(b))
+        if isinstance(b, Matrix) and isinstance(a, np.ndarray):
+            return binop(op, Matrix(a), b)
         if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
             return _PY_BIN[op](a, b)  # Python-scope numpy code of the reference (np_rotate_matrix, ...)
         raise TypeError("taichi emulator: bad operands for %s: %r, %r" % (op, type(a), type(b)))
@@ -247,14 +251,15 @@ _SWZ = {c: i for s in ("xyzw", "rgba", "stpq") for i, c in enumerate(s)}
 class Matrix:
     """Vector (1-D) or matrix (2-D). dtype float64 / int64 == Python-scope ("weak") values."""
 
-    __slots__ = ("a",)
+    __slots__ = ("data",)
+    __array_ufunc__ = None  # numpy scalars defer to our reflected operators instead of iterating us
 
     def __init__(self, vals, dt=None, _noconv=False):
         if _noconv:
-            object.__setattr__(self, "a", vals)
+            object.__setattr__(self, "data", vals)
             return
         if isinstance(vals, Matrix):
-            arr = vals.a.copy()
+            arr = vals.data.copy()
         elif isinstance(vals, np.ndarray):
             arr = vals.copy()
         else:
@@ -276,39 +281,39 @@ class Matrix:
             arr = arr.astype(_as_dtype(dt))
         elif in_taichi_scope():
             arr = _typed_arr(arr)
-        object.__setattr__(self, "a", arr)
+        object.__setattr__(self, "data", arr)
 
     # --- structure
     @property
     def n(self):
-        return self.a.shape[0]
+        return self.data.shape[0]
 
     @property
     def m(self):
-        return self.a.shape[1] if self.a.ndim > 1 else 1
+        return self.data.shape[1] if self.data.ndim > 1 else 1
 
     @property
     def shape(self):
-        return self.a.shape
+        return self.data.shape
 
     def __len__(self):
-        return self.a.shape[0]
+        return self.data.shape[0]
 
     def __iter__(self):
-        for i in range(self.a.shape[0]):
+        for i in range(self.data.shape[0]):
             yield self[i]
 
     def copy(self):
-        return Matrix(self.a.copy(), _noconv=True)
+        return Matrix(self.data.copy(), _noconv=True)
 
     def get_shape(self):
-        return self.a.shape
+        return self.data.shape
 
     def to_numpy(self):
-        return self.a.copy()
+        return self.data.copy()
 
     def to_list(self):
-        return self.a.tolist()
+        return self.data.tolist()
 
     # --- element access
     def _elem(self, v):
@@ -320,17 +325,17 @@ class Matrix:
         if isinstance(k, tuple):
             k = tuple(int(i) for i in k)
         elif isinstance(k, Matrix):
-            k = tuple(int(i) for i in k.a)
+            k = tuple(int(i) for i in k.data)
         else:
             k = int(k)
-        return self._elem(self.a[k])
+        return self._elem(self.data[k])
 
     def __setitem__(self, k, v):
         if isinstance(k, tuple):
             k = tuple(int(i) for i in k)
         else:
             k = int(k)
-        self.a[k] = _raw(v, self.a.dtype)
+        self.data[k] = _raw(v, self.data.dtype)
 
     def __getattr__(self, name):
         try:
@@ -338,15 +343,15 @@ class Matrix:
         except KeyError:
             raise AttributeError(name)
         if len(idx) == 1:
-            return _wrap(self.a[idx[0]])
-        return Matrix(self.a[idx], _noconv=True)  # fancy indexing copies
+            return _wrap(self.data[idx[0]])
+        return Matrix(self.data[idx], _noconv=True)  # fancy indexing copies
 
     def __setattr__(self, name, v):
         try:
             idx = [_SWZ[c] for c in name]
         except KeyError:
             raise AttributeError(name)
-        self.a[idx] = _raw(v, self.a.dtype)
+        self.data[idx] = _raw(v, self.data.dtype)
 
     # --- arithmetic (Python-scope code and un-rewritten expressions)
     def __add__(self, o): return binop("+", self, o)
@@ -382,7 +387,7 @@ class Matrix:
         return cast(self, dt)
 
     def sum(self):
-        r = self.a.reshape(-1)
+        r = self.data.reshape(-1)
         acc = r[0]
         for v in r[1:]:
             acc = acc + v
@@ -406,22 +411,22 @@ class Matrix:
         return Matrix([a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x])
 
     def transpose(self):
-        return Matrix(self.a.T.copy(), _noconv=True)
+        return Matrix(self.data.T.copy(), _noconv=True)
 
     def min(self):
-        return _wrap(self.a.min())
+        return _wrap(self.data.min())
 
     def max(self):
-        return _wrap(self.a.max())
+        return _wrap(self.data.max())
 
     def inverse(self):
-        return Matrix(np.linalg.inv(self.a.astype(np.float64)).astype(self.a.dtype if self.a.dtype != _I64 else _F64), _noconv=True)
+        return Matrix(np.linalg.inv(self.data.astype(np.float64)).astype(self.data.dtype if self.data.dtype != _I64 else _F64), _noconv=True)
 
     def fill(self, v):
-        self.a[...] = _raw(v, self.a.dtype)
+        self.data[...] = _raw(v, self.data.dtype)
 
     def __repr__(self):
-        return "Matrix(%r)" % (self.a,)
+        return "Matrix(%r)" % (self.data,)
 
     # ti.Vector.field / ti.Matrix.field
     @staticmethod
@@ -441,8 +446,8 @@ def _typed_arr(arr):
 
 def _typed(x):
     """A Python-scope (weak) vector entering Taichi scope becomes an f32 / i32 vector."""
-    if isinstance(x, Matrix) and x.a.dtype in (_F64, _I64):
-        return Matrix(_typed_arr(x.a), _noconv=True)
+    if isinstance(x, Matrix) and x.data.dtype in (_F64, _I64):
+        return Matrix(_typed_arr(x.data), _noconv=True)
     return x
 
 
@@ -455,21 +460,21 @@ Vector.field = lambda n, dtype=f32, shape=None, **kw: Field(dtype, shape, (n,))
 
 def matmul(a, b):
     a, b = (Matrix(a) if not isinstance(a, Matrix) else a), (Matrix(b) if not isinstance(b, Matrix) else b)
-    if a.a.ndim != 2:
+    if a.data.ndim != 2:
         raise TypeError("matmul: left operand must be a matrix")
     rows = []
-    if b.a.ndim == 1:
-        for i in range(a.a.shape[0]):
+    if b.data.ndim == 1:
+        for i in range(a.data.shape[0]):
             acc = binop("*", a[i, 0], b[0])
-            for k in range(1, a.a.shape[1]):
+            for k in range(1, a.data.shape[1]):
                 acc = binop("+", acc, binop("*", a[i, k], b[k]))
             rows.append(acc)
         return Matrix(rows)
-    for i in range(a.a.shape[0]):
+    for i in range(a.data.shape[0]):
         row = []
-        for j in range(b.a.shape[1]):
+        for j in range(b.data.shape[1]):
             acc = binop("*", a[i, 0], b[0, j])
-            for k in range(1, a.a.shape[1]):
+            for k in range(1, a.data.shape[1]):
                 acc = binop("+", acc, binop("*", a[i, k], b[k, j]))
             row.append(acc)
         rows.append(row)
@@ -549,7 +554,7 @@ pow = power
 def _minmax(fn):
     def g(*xs):
         if len(xs) == 1 and isinstance(xs[0], Matrix):
-            return _wrap(fn.reduce(xs[0].a))
+            return _wrap(fn.reduce(xs[0].data))
         acc = xs[0]
         for x in xs[1:]:
             if type(acc) in _PYNUM and type(x) in _PYNUM:
@@ -568,7 +573,7 @@ min = _minmax(np.minimum)
 def select(c, a, b):
     if isinstance(c, Matrix):
         dt = _np_dtype(_promote(_kind(a), _kind(b)))
-        return _wrap(np.where(c.a != 0, _raw(a, dt), _raw(b, dt)))
+        return _wrap(np.where(c.data != 0, _raw(a, dt), _raw(b, dt)))
     r = a if truth(c) else b
     o = b if truth(c) else a
     if isinstance(r, Matrix):
@@ -583,7 +588,7 @@ def cast(x, dt):
         return Matrix(x, dt.dtype)
     d = _as_dtype(dt)
     if isinstance(x, Matrix):
-        src = x.a
+        src = x.data
     else:
         src = np.asarray(x)
     if np.issubdtype(d, np.integer) and np.issubdtype(src.dtype, np.floating):
@@ -670,10 +675,15 @@ def init(*a, **kw):
 _random_source = None
 
 
-def set_random_source(fn):
-    """fn(caller_function_name) -> float in [0, 1). None restores the default generator."""
-    global _random_source
-    _random_source = fn
+def set_random_source(fn, with_frame=False):
+    """fn(caller_function_name[, caller_frame]) -> float in [0, 1). None restores the default
+    generator. With the frame a harness can walk f_back to the kernel and read its loop variables
+    (pixel, depth), i.e. map each draw to a dimension of a counter-based sampler."""
+    global _random_source, _random_with_frame
+    _random_source, _random_with_frame = fn, with_frame
+
+
+_random_with_frame = False
 
 
 _default_rng = np.random.default_rng(0)
@@ -681,8 +691,8 @@ _default_rng = np.random.default_rng(0)
 
 def random(dtype=float):
     if _random_source is not None:
-        name = sys._getframe(1).f_code.co_name
-        return np.float32(_random_source(name))
+        fr = sys._getframe(1)
+        return np.float32(_random_source(fr.f_code.co_name, fr) if _random_with_frame else _random_source(fr.f_code.co_name))
     return np.float32(_default_rng.random(dtype=np.float32))
 
 
@@ -714,7 +724,7 @@ class Field:
         if k is None:
             return ()
         if isinstance(k, Matrix):
-            k = tuple(int(i) for i in k.a)
+            k = tuple(int(i) for i in k.data)
         elif isinstance(k, (tuple, list)):
             k = tuple(int(i) for i in k)
         else:
@@ -856,8 +866,8 @@ class VectorType:
         if not in_taichi_scope():
             dt = _F64 if np.issubdtype(dt, np.floating) else _I64  # Python-scope vectors hold Python numbers
         m = Matrix(vals, dt)
-        if m.a.shape[0] != self.n:
-            raise TypeError("vec%d built from %d components" % (self.n, m.a.shape[0]))
+        if m.data.shape[0] != self.n:
+            raise TypeError("vec%d built from %d components" % (self.n, m.data.shape[0]))
         return m
 
 
@@ -950,7 +960,7 @@ class Texture:
         self.arr = np.zeros(self.shape + (4,), dtype=np.float32)
 
     def _key(self, c):
-        return tuple(int(v) for v in (c.a if isinstance(c, Matrix) else c))
+        return tuple(int(v) for v in (c.data if isinstance(c, Matrix) else c))
 
     def store(self, coord, value):
         v = _raw(value, _F32)
@@ -1084,8 +1094,8 @@ _ATOMICS = ("atomic_or", "atomic_min", "atomic_max", "atomic_add")
 def store(old, new):
     """Type-stable assignment to a local variable."""
     if isinstance(new, (Matrix, Struct)):
-        if isinstance(old, Matrix) and isinstance(new, Matrix) and old.a.shape == new.a.shape and old.a.dtype not in (_F64, _I64):
-            return Matrix(_raw(new, old.a.dtype).copy(), _noconv=True)
+        if isinstance(old, Matrix) and isinstance(new, Matrix) and old.data.shape == new.data.shape and old.data.dtype not in (_F64, _I64):
+            return Matrix(_raw(new, old.data.dtype).copy(), _noconv=True)
         return _typed(new).copy() if isinstance(new, Matrix) else new.copy()
     if isinstance(new, (tuple, list, Field, StructField, Texture, _NdArg, np.ndarray, str, _pytypes.FunctionType)) or new is None:
         return new
@@ -1103,7 +1113,7 @@ def store(old, new):
 
 def getattr_(obj, name):
     v = getattr(obj, name)
-    if isinstance(v, Matrix) and v.a.dtype in (_F64, _I64) and in_taichi_scope():
+    if isinstance(v, Matrix) and v.data.dtype in (_F64, _I64) and in_taichi_scope():
         return _typed(v)
     return v
 
@@ -1126,8 +1136,9 @@ def call_wb(f, args, kwargs):
 
 
 class _Rewriter(ast.NodeTransformer):
-    def __init__(self, params):
+    def __init__(self, params, local_names=()):
         self.params = params
+        self.locals = set(params) | set(local_names)
         self.tmp = 0
 
     def _call(self, fn, *args):
@@ -1196,7 +1207,7 @@ class _Rewriter(ast.NodeTransformer):
                             value=self._call("__ti_callwb", call.func, ast.Tuple(elts=call.args, ctx=ast.Load()), kw))]
         fin = ast.Subscript(value=ast.Name(id=tmp, ctx=ast.Load()), slice=ast.Constant(1), ctx=ast.Load())
         for i, a in enumerate(call.args):
-            if isinstance(a, ast.Name) and a.id != "self":
+            if isinstance(a, ast.Name) and a.id != "self" and a.id in self.locals:
                 stmts.append(ast.Assign(targets=[ast.Name(id=a.id, ctx=ast.Store())],
                                         value=self._call("__ti_wb", ast.Name(id=a.id, ctx=ast.Load()), fin, ast.Constant(i))))
         return stmts, ast.Subscript(value=ast.Name(id=tmp, ctx=ast.Load()), slice=ast.Constant(0), ctx=ast.Load())
@@ -1207,7 +1218,7 @@ class _Rewriter(ast.NodeTransformer):
         f = v.func
         if isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "ti":
             return False
-        return any(isinstance(a, ast.Name) for a in v.args)
+        return any(isinstance(a, ast.Name) and a.id in self.locals for a in v.args)
 
     def visit_Assign(self, n):
         if self._is_plain_call(n.value):
@@ -1311,7 +1322,7 @@ def _compile(fn):
         a.annotation = None
     fdef.returns = None
     local_names = [n for n in _assigned_names(fdef) if n not in params]
-    rw = _Rewriter(params)
+    rw = _Rewriter(params, local_names)
     fdef.args.defaults = [rw.visit(d) for d in fdef.args.defaults]
     body = rw._body(fdef.body)
     init = [ast.Assign(targets=[ast.Name(id=n, ctx=ast.Store())], value=ast.Name(id="__ti_UNDEF", ctx=ast.Load())) for n in local_names]

@@ -87,7 +87,7 @@ def section_raytrace():
 
         def checked(ipos, lod, _rt=rt, _R=R):
             r = _R >> int(lod)
-            if int(ipos.a.min()) < 0 or int(ipos.a.max()) >= r:
+            if int(ipos.data.min()) < 0 or int(ipos.data.max()) >= r:
                 oob[0] = 1  # A3: the cell is outside the grid; read it as empty (robust-buffer behaviour)
                 return False
             return inner(_rt, ipos, lod)
@@ -113,7 +113,7 @@ def section_raytrace():
         for i in range(n):
             oob[0] = 0
             ht, hc, hn, hi = rt.raytrace(vec(o[i]), vec(d[i]), eps, inf)
-            t[i], cell[i], nrm[i], iters[i], flag[i] = ht, hc.a, hn.a, hi, oob[0]
+            t[i], cell[i], nrm[i], iters[i], flag[i] = ht, hc.data, hn.data, hi, oob[0]
         out[name + "_o"], out[name + "_d"], out[name + "_t"] = o, d, t
         out[name + "_cell"], out[name + "_normal"], out[name + "_iters"], out[name + "_flag"] = cell, nrm, iters, flag
         print("raytrace %s: %d rays, %d hits, %d out-of-grid (A3)" % (name, n, int(np.isfinite(t).sum()), int(flag.sum())))
@@ -131,14 +131,14 @@ def section_math():
     bx, by = np.zeros((n, 3), F), np.zeros((n, 3), F)
     for i in range(n):
         x, y = mu.make_orthonormal_basis(vec(v[i]))
-        bx[i], by[i] = x.a, y.a
+        bx[i], by[i] = x.data, y.data
     out["onb_n"], out["onb_x"], out["onb_y"] = v, bx, by
     # octahedral 2 x f16 round trip (math_utils.py:201-215)
     enc, dec = np.zeros((n, 2), np.float16), np.zeros((n, 3), F)
     for i in range(n):
         e = mu.encode_unit_vector_3x16(vec(v[i]))
-        enc[i] = e.a
-        dec[i] = mu.decode_unit_vector_3x16(e).a
+        enc[i] = e.data
+        dec[i] = mu.decode_unit_vector_3x16(e).data
     out["oct_v"], out["oct_enc"], out["oct_dec"] = v, enc, dec
     # hash3 (math_utils.py:217-229)
     hx = rng.integers(0, 2 ** 32, (n, 3), dtype=np.uint64).astype(np.uint32)
@@ -152,12 +152,12 @@ def section_math():
     # u8 colour conversions (math_utils.py:86-100)
     c = np.concatenate([rng.random((n - 4, 3)), [[0, 0, 0], [1, 1, 1], [1.5, -0.2, 0.5], [0.999, 0.001, 0.5]]]).astype(F)
     out["rgb_in"] = c
-    out["rgb_u8"] = np.array([mu.rgb32f_to_rgb8(vec(x)).a for x in c], np.uint8)
-    out["rgb_back"] = np.array([mu.rgb8_to_rgb32f(ti.Matrix(u, _noconv=True)).a for u in out["rgb_u8"]], F)
+    out["rgb_u8"] = np.array([mu.rgb32f_to_rgb8(vec(x)).data for x in c], np.uint8)
+    out["rgb_back"] = np.array([mu.rgb8_to_rgb32f(ti.Matrix(u, _noconv=True)).data for u in out["rgb_u8"]], F)
     # uchimura tonemap (math_utils.py:160-186) and luminance
     x = np.concatenate([rng.random((n, 3)) * 4.0, [[0, 0, 0], [0.22, 0.22, 0.22], [0.532, 0.1, 10.0]]]).astype(F)
     out["uchi_in"] = x
-    out["uchi_out"] = np.array([mu.uchimura(vec(a)).a for a in x], F)
+    out["uchi_out"] = np.array([mu.uchimura(vec(a)).data for a in x], F)
     out["lum_out"] = np.array([mu.luminance(vec(a)) for a in x], F)
     # cone pdf / samples with supplied random numbers (math_utils.py:44-63)
     u = rng.random((n, 2)).astype(F)
@@ -167,9 +167,9 @@ def section_math():
     for i in range(n):
         q = list(u[i])
         ti.set_random_source(lambda name: q.pop(0))
-        samples[i] = mu.sample_cone_oriented(cm[i], vec(v[i])).a
+        samples[i] = mu.sample_cone_oriented(cm[i], vec(v[i])).data
         q = list(u[i])
-        hemi[i] = mu.sample_cosine_weighted_hemisphere(vec(v[i])).a
+        hemi[i] = mu.sample_cosine_weighted_hemisphere(vec(v[i])).data
     ti.set_random_source(None)
     out["cone_u"], out["cone_cosmax"], out["cone_n"], out["cone_dir"], out["hemi_dir"] = u, cm, v, samples, hemi
     np.savez_compressed(os.path.join(HERE, "ref_math.npz"), **out)
@@ -213,7 +213,7 @@ def section_bsdf():
              "clearcoat_gloss", "ior_minus_one"]
     for m in range(128):
         s = mats.mat_list[m]
-        table[m, :3] = s.base_col.a
+        table[m, :3] = s.base_col.data
         table[m, 3:] = [getattr(s, k) for k in names]
     for i in range(n):
         m = mats.mat_list[int(mat_id[i])]
@@ -221,17 +221,17 @@ def section_bsdf():
         N, V, L = vec(nrm[i]), vec(v[i]), vec(l[i])
         tang, bitang = make_orthonormal_basis(N)
         d, s = bsdf.disney_evaluate_split(m, V, N, L, tang, bitang)
-        ev_d[i], ev_s[i] = d.a, s.a
+        ev_d[i], ev_s[i] = d.data, s.data
         pdf[i] = bsdf.pdf_disney(m, V, N, L, tang, bitang)
         lw[i] = [float(x) for x in bsdf.disney_get_lobe_probabilities(m)]
         q = list(u3[i])
         ti.set_random_source(lambda name: q.pop(0))
         sd, sb, sp, sl = bsdf.sample_disney(m, V, N, tang, bitang)
         ti.set_random_source(None)
-        sdir[i], sbrdf[i], spdf[i], slobe[i] = sd.a, sb.a, sp, sl
+        sdir[i], sbrdf[i], spdf[i], slobe[i] = sd.data, sb.data, sp, sl
         for lobe in range(3):
             a, b = bsdf.disney_evaluate_lobewise_split(m, V, N, L, tang, bitang, np.int32(lobe))
-            lobe_d[i, lobe], lobe_s[i, lobe] = a.a, b.a
+            lobe_d[i, lobe], lobe_s[i, lobe] = a.data, b.data
             lobe_pdf[i, lobe] = bsdf.pdf_disney_lobewise(m, V, N, L, tang, bitang, np.int32(lobe))
     np.savez_compressed(os.path.join(HERE, "ref_bsdf.npz"), material_table=table, mat_id=mat_id, albedo=albedo, n=nrm, v=v, l=l, u3=u3,
                         eval_d=ev_d, eval_s=ev_s, pdf=pdf, lobe_w=lw, sample_dir=sdir, sample_brdf=sbrdf, sample_pdf=spdf, sample_lobe=slobe,
@@ -239,7 +239,160 @@ def section_bsdf():
     print("bsdf: %d probes over %d materials" % (n, len(ids)))
 
 
-SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf}
+# ------------------------------------------------------------------- Renderer: hits + render()
+def mix32(x):
+    x &= 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+def sampler_rnd(pixel, sample, seed, dim):
+    """The counter-based sampler shared by oracle and CUDA (DESIGN.md "Sampler")."""
+    key = mix32((mix32(pixel ^ ((0x9E3779B9 * (sample + 1)) & 0xFFFFFFFF)) + seed) & 0xFFFFFFFF)
+    h = mix32((key + 0x9E3779B9 * (dim + 1)) & 0xFFFFFFFF)
+    return np.float32(h >> 8) * np.float32(1.0 / 16777216.0)
+
+
+DIMS = {"sample_cone": (0, 2), "sample_disney": (2, 1), "sample_cosine_weighted_hemisphere": (3, 2), "GGX_VNDF_aniso": (3, 2),
+        "sample_clearcoat": (3, 2), "sample_skybox": (5, 3)}
+
+
+def render_scene(R, seed):
+    rng = np.random.default_rng(seed)
+    mat = np.zeros((R, R, R), np.int8)
+    occ = rng.random((R, R, R)) < 0.08
+    occ[R // 4: 3 * R // 4, : R // 3, R // 4: 3 * R // 4] |= rng.random((R // 2, R // 3, R // 2)) < 0.6
+    ids = np.array([1, 1, 1, 11, 21, 32, 40, 50, 52, 54, 2], np.int8)
+    mat[occ] = rng.choice(ids, int(occ.sum()))
+    col = rng.integers(40, 250, (R, R, R, 3)).astype(np.uint8)
+    return mat, col
+
+
+def make_reference_renderer(W, H, R, mat, col, cfg):
+    from renderer.pathtracer import Renderer
+    from renderer.raytracer import VoxelOctreeRaytracer
+    from renderer.voxel_world import VoxelWorld
+
+    r = Renderer(dx=2.0 / R, image_res=(W, H), up=(0, 1, 0), voxel_edges=cfg["voxel_edges"], exposure=3)
+    # the shipped Renderer hard-codes a 128^3 grid (pathtracer.py:80); same classes at R^3
+    r.voxel_grid_res = R
+    r.world = VoxelWorld(2.0 / R, R, cfg["voxel_edges"])
+    r.voxel_raytracer = VoxelOctreeRaytracer(R)
+    r.voxel_raytracer.occupancy = ti.field(ti.i32, shape=(2 * R ** 3 // 32 + 1,))  # A1
+    r.world.voxel_material.arr[...] = mat
+    r.world.voxel_color.arr[...] = col
+    r.set_directional_light(cfg["light_dir"], cfg["light_cone"], cfg["light_color"])
+    r.floor_height[None] = cfg["floor_height"]
+    r.floor_color[None] = cfg["floor_color"]
+    r.floor_material[None] = cfg["floor_material"]
+    r.background_color[None] = cfg["background"]
+    r.use_physical_atmosphere[None] = 0
+    r.camera_is_moving[None] = 0
+    r.render_scale[None] = 1.0
+    r.world.update_data()
+    r.voxel_raytracer._update_lods(r.world.voxel_material, ti.Vector(r.world.voxel_grid_offset))
+    inner = VoxelOctreeRaytracer.query_occupancy
+
+    def checked(ipos, lod, _rt=r.voxel_raytracer):  # A3
+        n = R >> int(lod)
+        if int(ipos.data.min()) < 0 or int(ipos.data.max()) >= n:
+            return False
+        return inner(_rt, ipos, lod)
+
+    r.voxel_raytracer.query_occupancy = checked
+    return r
+
+
+def set_reference_camera(r, pos, view, proj):
+    ti.set_random_source(lambda name: 0.5)
+    r.set_camera_pos(*[float(x) for x in pos])
+    r.set_view_mat(np.ascontiguousarray(view.T))  # the kernels transpose what GGUI hands them (pathtracer.py:262-281)
+    r.set_proj_mat(np.ascontiguousarray(proj.T))
+    ti.set_random_source(None)
+    r.taa_jitter[None] = (0.0, 0.0)
+
+
+def section_render():
+    """Renderer.next_hit on every primary ray + sun shadow ray (hit buffer) and Renderer.render()
+    (pathtracer.py:355-632) for a few samples per pixel, with ti.random() answering from the
+    oracle's counter-based sampler: dimension 8*depth + {0,1 cone; 2 lobe; 3,4 direction; 5..7 sky
+    jitter} of the path (pixel, sample), read from the calling frames. TAA jitter is zero."""
+    sys.path.insert(0, ROOT)
+    from renderer.math_utils import eps, inf
+    from voxel_rt2_b200.camera import default_camera_matrices
+
+    W, H, R, seed, n_samples = 32, 16, 32, 77, 4
+    cfg = dict(voxel_edges=0.06, light_dir=(1.0, 1.0, 0.4), light_cone=0.06, light_color=(1.2, 1.1, 0.9), floor_height=-0.55,
+               floor_color=(0.8, 0.75, 0.7), floor_material=1, background=(0.25, 0.35, 0.55))
+    mat, col = render_scene(R, 5)
+    r = make_reference_renderer(W, H, R, mat, col, cfg)
+    pos, view, proj = default_camera_matrices(W, H, pos=(0.9, 0.8, 1.9))
+    set_reference_camera(r, pos, view, proj)
+    tex = r.world.voxel_color_texture
+    out = dict(material=mat, color=col, cam_pos=pos, view=view, proj=proj, seed=np.int32(seed), W=np.int32(W), H=np.int32(H))
+    for k, v in cfg.items():
+        out["cfg_" + k] = np.asarray(v, np.float32)
+    # ---- hit buffer: primary ray + shadow ray on the cone axis (the oracle's / CUDA's trace_primary)
+    hit_t = np.zeros((H, W), np.float32)
+    hit_n = np.zeros((H, W, 3), np.float32)
+    hit_alb = np.zeros((H, W, 3), np.float32)
+    hit_mat = np.zeros((H, W), np.int32)
+    hit_light = np.zeros((H, W), np.int32)
+    shadow = np.full((H, W), 3, np.int32)
+    dirs = np.zeros((H, W, 3), np.float32)
+    cam = r.camera_pos[None].copy()
+    ldir = r.light_direction[None].copy()
+    for v in range(H):
+        for u in range(W):
+            d = r.get_cast_dir(np.int32(u), np.int32(v))
+            closest, normal, albedo, hl, iters, mid = r.next_hit(cam, d, inf, tex, shadow_ray=False)
+            dirs[v, u], hit_t[v, u], hit_n[v, u], hit_alb[v, u], hit_mat[v, u], hit_light[v, u] = d.data, closest, normal.data, albedo.data, mid, hl
+            if not hl and closest < inf:
+                p = cam + closest * d + normal * eps
+                if ldir.dot(normal) > 0:
+                    dist = r.next_hit(p, ldir, inf, tex, shadow_ray=True)[0]
+                    shadow[v, u] = 0 if dist >= inf else 1
+                else:
+                    shadow[v, u] = 2
+    out.update(hit_dir=dirs, hit_t=hit_t, hit_normal=hit_n, hit_albedo=hit_alb, hit_mat=hit_mat, hit_light=hit_light, hit_shadow=shadow)
+    print("hit buffer: %d voxel/floor hits of %d pixels" % (int(np.isfinite(hit_t).sum()), W * H))
+
+    # ---- render(): per-pixel radiance of single samples
+    state = {"sample": 0, "count": {}}
+
+    def source(name, frame):
+        f = frame
+        while f is not None and f.f_code.co_name != "render":
+            f = f.f_back
+        if f is None or name not in DIMS:
+            return 0.5  # set_proj_mat jitter, Reservoir.input_sample: not part of the non-ReSTIR pixel value
+        u, v, depth = int(f.f_locals["u"]), int(f.f_locals["v"]), int(f.f_locals["depth"])
+        base, n = DIMS[name]
+        key = (u, v, depth, name)
+        i = state["count"].get(key, 0)
+        state["count"][key] = i + 1
+        assert i < n, key
+        return sampler_rnd(v * W + u, state["sample"], seed, 8 * depth + base + i)
+
+    ti.set_random_source(source, with_frame=True)
+    diff = np.zeros((n_samples, H, W, 3), np.float32)
+    spec = np.zeros((n_samples, H, W, 3), np.float32)
+    for s in range(n_samples):
+        state["sample"], state["count"] = s, {}
+        r.render(tex)
+        diff[s] = np.transpose(r.color_buffer.arr, (1, 0, 2))
+        spec[s] = np.transpose(r.color_buffer_specular.arr, (1, 0, 2))
+        print("render sample %d: mean %.4f" % (s, float((diff[s] + spec[s]).mean())))
+    ti.set_random_source(None)
+    out.update(render_diffuse=diff, render_specular=spec)
+    np.savez_compressed(os.path.join(HERE, "ref_render.npz"), **out)
+
+
+SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render}
 
 if __name__ == "__main__":
     for s in (sys.argv[1:] or list(SECTIONS)):

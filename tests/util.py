@@ -27,3 +27,37 @@ def rel_rmse(a, b):
     a = np.asarray(a, np.float64)[..., :3]
     b = np.asarray(b, np.float64)[..., :3]
     return float(np.sqrt(np.mean((a - b) ** 2)) / max(np.mean(b), 1e-12))
+
+
+def renderer_from_reference_fixture(factory, z, **kw):
+    """A Renderer / OracleRenderer configured like the reference Renderer that produced
+    tests/golden/ref_render*.npz (tests/golden/make_ref_vectors.py section_render)."""
+    W, H = int(z["W"]), int(z["H"])
+    R = z["material"].shape[0]
+    sky_res = int(z["sky_res"]) if "sky_res" in z else 0
+    r = factory(dx=2.0 / R, image_res=(W, H), grid_res=R, sky_res=sky_res, seed=int(z["seed"]), jitter=False,
+                voxel_edges=float(z["cfg_voxel_edges"]), **kw)
+    r.set_voxels(z["material"], z["color"])
+    r.set_floor(float(z["cfg_floor_height"]), z["cfg_floor_color"], int(z["cfg_floor_material"]))
+    r.set_directional_light(z["cfg_light_dir"], float(z["cfg_light_cone"]), z["cfg_light_color"])
+    r.set_background_color(z["cfg_background"])
+    r.set_view_proj(z["cam_pos"], z["view"], z["proj"])
+    return r
+
+
+def reference_hit_fields(h):
+    """trace_primary() records -> the arrays the reference-derived fixture stores."""
+    kind = h["flags"] & 255
+    t = np.where(kind > 0, h["t"], np.inf).astype(np.float32)
+    return dict(t=t, normal=h["normal"] + 0.0, mat=(h["flags"] >> 16) & 255, light=(h["flags"] >> 24) & 255, shadow=(h["flags"] >> 8) & 255)
+
+
+def reference_radiance(z, s):
+    """Sample s of the reference render(): diffuse + specular with the NaN / negative scrub the
+    reference applies in its temporal filter (pathtracer.py:1068-1075)."""
+    def scrub(c):
+        bad = ~np.isfinite(c).all(-1) | (c < 0).any(-1)
+        c = c.copy()
+        c[bad] = 0
+        return c
+    return scrub(z["render_diffuse"][s]) + scrub(z["render_specular"][s])
