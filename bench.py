@@ -151,6 +151,16 @@ def cpu_sample(args, W, H, R, mat, col, sky_tables, cpu_spp):
             "spp": cpu_spp}
 
 
+def _upsample_table(tab, S):
+    """Bilinear resampling (wrap-around, texel centres) of an s x s x 3 sky table to S x S x 3."""
+    s = tab.shape[0]
+    x = (np.arange(S) + 0.5) * s / S - 0.5
+    i0 = np.floor(x).astype(np.int64)
+    f = (x - i0).astype(np.float32)
+    a = tab[i0 % s] * (1.0 - f)[:, None, None] + tab[(i0 + 1) % s] * f[:, None, None]
+    return np.ascontiguousarray(a[:, i0 % s] * (1.0 - f)[None, :, None] + a[:, (i0 + 1) % s] * f[None, :, None], dtype=np.float32)
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle restatement (the reference itself is Taichi/Vulkan and cannot run here)."""
     if rank != 0:
@@ -163,12 +173,17 @@ def run_reference(args, rank, world):
 
     lib = load()
     cores = int(lib.orc_num_threads())
-    # sky tables: the CPU cannot run the 3840^2 precompute in bounded time (~1e12 inner iterations);
-    # the reference arm uses a 64^2 table computed by the oracle itself (same code path per lookup).
+    # sky tables: the CPU cannot run the 3840^2 precompute in bounded time (~1e12 inner iterations), so
+    # the oracle computes a 64^2 table itself and it is resampled to the GPU arm's table size: every
+    # lookup then walks the same 2 x 177 MB footprint (same cache behaviour) through the same code.
     S = 64
     o = OracleRenderer(dx=2.0 / R, image_res=(W, H), grid_res=R, sky_res=S, cloud_passes=2, exposure=2.0, seed=1, materials=material_table())
     configure(o, R, mat, col, sky=True)
     o.prepare_data()
+    if args.sky_res > S:
+        tabs = [_upsample_table(t, args.sky_res) for t in o.get_sky_tables()]
+        S = o.sky_res = args.sky_res
+        o.set_sky_tables(*tabs)
     # each step = 1 spp over every 4th 8x4 tile (1/4 of the frame) so K+W steps end in minutes
     n = 4
     o.set_tile_shard(0, n)

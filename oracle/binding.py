@@ -51,6 +51,7 @@ def load():
     lib.orc_get_sky_tables.argtypes = [P, fp, fp]
     lib.orc_get_trans_lut.argtypes = [P, P]
     lib.orc_get_cloud_ambient.argtypes = [P, fp]
+    lib.orc_sample_skybox.argtypes = [P, C.c_int, fp, fp, fp, fp]
     lib.orc_set_tile_shard.argtypes = [P, C.c_int, C.c_int]
     lib.orc_trace_primary.argtypes = [P, P]
     lib.orc_accumulate.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -234,6 +235,23 @@ class OracleRenderer:
         self._lib.orc_get_trans_lut(self._h, a.ctypes.data_as(C.c_void_p))
         return a
 
+    def get_cloud_ambient(self):
+        a = np.empty(3, np.float32)
+        self._lib.orc_get_cloud_ambient(self._h, _fp(a))
+        return a
+
+    def sample_sky_trans(self, dirs):
+        d = _f32(dirs)
+        out = np.empty((d.size // 3, 3), np.float32)
+        self._lib.orc_sample_sky_trans(self._h, d.size // 3, _fp(d), _fp(out))
+        return out
+
+    def sample_skybox(self, dirs, jitter):
+        d, j = _f32(dirs), _f32(jitter)
+        sc, tr = np.empty((d.size // 3, 3), np.float32), np.empty((d.size // 3, 3), np.float32)
+        self._lib.orc_sample_skybox(self._h, d.size // 3, _fp(d), _fp(j), _fp(sc), _fp(tr))
+        return sc, tr
+
     def set_tile_shard(self, rank, n):
         self._lib.orc_set_tile_shard(self._h, int(rank), int(n))
 
@@ -343,4 +361,20 @@ def math_probe(kind, a, b=None, out_per=3):
     b = np.ascontiguousarray(b if b is not None else np.zeros((n, 3)), np.float32)
     out = np.zeros((n, out_per) if out_per > 1 else (n,), np.float32)
     lib.orc_math_probe(int(kind), n, _fp(a), _fp(b), _fp(out))
+    return out
+
+
+def project_sky(dirs, S):
+    lib = load()
+    d = _f32(dirs)
+    out = np.empty((d.size // 3, 2), np.float32)
+    lib.orc_project_sky(d.size // 3, int(S), _fp(d), _fp(out))
+    return out
+
+
+def unproject_sky(uv, S):
+    lib = load()
+    u = _f32(uv)
+    out = np.empty((u.size // 2, 3), np.float32)
+    lib.orc_unproject_sky(u.size // 2, int(S), _fp(u), _fp(out))
     return out

@@ -1248,6 +1248,17 @@ void orc_sample_sky_trans(void* p, int n, const float* d, float* out) {
     out[3 * i] = r.x, out[3 * i + 1] = r.y, out[3 * i + 2] = r.z;
   }
 }
+// sample_skybox (atmos.py:94-115) with the three jitter numbers supplied
+void orc_sample_skybox(void* p, int n, const float* d, const float* jitter, float* scat, float* trans) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < n; i++) {
+    V3 sc, tr;
+    sample_skybox(c->scene.sky_scatter, c->scene.sky_trans, c->scene.sky_res, V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]}, jitter[3 * i],
+                  jitter[3 * i + 1], jitter[3 * i + 2], sc, tr);
+    scat[3 * i] = sc.x, scat[3 * i + 1] = sc.y, scat[3 * i + 2] = sc.z;
+    trans[3 * i] = tr.x, trans[3 * i + 1] = tr.y, trans[3 * i + 2] = tr.z;
+  }
+}
 float orc_rnd(uint32_t pixel, uint32_t sample, uint32_t seed, uint32_t dim) { return rnd(path_key(pixel, sample, seed), dim); }
 uint16_t orc_f32_to_f16(float f) { return f32_to_f16_bits(f); }
 float orc_f16_to_f32(uint16_t h) { return f16_bits_to_f32(h); }

@@ -711,6 +711,7 @@ class Field:
         self.elem_shape = tuple(elem_shape)
         self.offset = None
         self.arr = None
+        self.oob_zero = False
         shape = _norm_shape(shape)
         if shape is not None:
             self._alloc(shape)
@@ -733,11 +734,16 @@ class Field:
             k = tuple(i - o for i, o in zip(k, self.offset))
         for i, n in zip(k, self.shape):
             if i < 0 or i >= n:
+                if self.oob_zero:
+                    return None
                 raise IndexError("field index %r out of range %r" % (k, self.shape))
         return k
 
     def __getitem__(self, k):
-        v = self.arr[self._key(k)]
+        k = self._key(k)
+        if k is None:  # harness opt-in (Field.oob_zero): out-of-range reads return zeros
+            return Matrix(np.zeros(self.elem_shape, self.dtype), _noconv=True) if self.elem_shape else self.dtype.type(0)
+        v = self.arr[k]
         if self.elem_shape:
             return Matrix(v, _noconv=True)  # view into the field storage
         return _wrap(v)

@@ -392,7 +392,190 @@ def section_render():
     np.savez_compressed(os.path.join(HERE, "ref_render.npz"), **out)
 
 
-SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render}
+def path_random_source(W, seed, state):
+    """ti.random() of Renderer.render answered from the shared counter-based sampler (see section_render)."""
+    def source(name, frame):
+        f = frame
+        while f is not None and f.f_code.co_name != "render":
+            f = f.f_back
+        if f is None or name not in DIMS:
+            return 0.5  # set_proj_mat jitter, Reservoir.input_sample: not part of the non-ReSTIR pixel value
+        u, v, depth = int(f.f_locals["u"]), int(f.f_locals["v"]), int(f.f_locals["depth"])
+        base, n = DIMS[name]
+        key = (u, v, depth, name)
+        i = state["count"].get(key, 0)
+        state["count"][key] = i + 1
+        assert i < n, key
+        return sampler_rnd(v * W + u, state["sample"], seed, 8 * depth + base + i)
+    return source
+
+
+def synthetic_sky_tables(S):
+    """Smooth positive tables (the lookups, not the atmosphere model, are under test here)."""
+    x, y = np.meshgrid((np.arange(S) + 0.5) / S, (np.arange(S) + 0.5) / S, indexing="ij")
+    sc = np.stack([0.25 + 0.2 * np.sin(6.283 * x) * y, 0.3 + 0.25 * y, 0.45 + 0.3 * y * np.cos(6.283 * x) ** 2], -1)
+    tr = np.stack([0.3 + 0.6 * y, 0.35 + 0.5 * y * (0.5 + 0.5 * np.cos(6.283 * x)), 0.2 + 0.7 * y ** 2], -1)
+    return sc.astype(np.float32), tr.astype(np.float32)
+
+
+def section_frame():
+    """The static-camera frame loop of Scene.finish (scene.py:206-262) for 4 frames with the physical
+    sky on (synthetic 16 x 16 tables): set_proj_mat / set_view_mat, accumulate() = render +
+    temporal_filter_prepass + temporal_filter + temporal_filter_specular (pathtracer.py:1310-1319),
+    fetch_image() = _render_to_image (:634-662), copy_prev_matrices. Stored: the accumulated HDR
+    buffer and the tonemapped image after the last frame."""
+    sys.path.insert(0, ROOT)
+    from voxel_rt2_b200.camera import default_camera_matrices
+
+    W, H, R, seed, n_frames, S = 32, 16, 32, 123, 4, 16
+    cfg = dict(voxel_edges=0.06, light_dir=(0.5, 0.8, 0.6), light_cone=0.025, light_color=(1.3, 1.2337, 1.2181), floor_height=-0.4,
+               floor_color=(1.0, 1.0, 1.0), floor_material=1, background=(0.0, 0.0, 0.0))
+    mat, col = render_scene(R, 9)
+    r = make_reference_renderer(W, H, R, mat, col, cfg)
+    sc, tr = synthetic_sky_tables(S)
+    r.use_physical_atmosphere[None] = 1
+    r.atmos.skybox_res = ti.Vector([S, S])
+    r.atmos.skybox_fres = ti.Vector([1.0 / S, 1.0 / S])
+    r.atmos.skybox_scattering = ti.Vector.field(3, dtype=ti.f32, shape=(S, S))
+    r.atmos.skybox_transmittance = ti.Vector.field(3, dtype=ti.f32, shape=(S, S))
+    r.atmos.skybox_scattering.arr[...] = sc
+    r.atmos.skybox_transmittance.arr[...] = tr
+    r.color_buffer.oob_zero = r.color_buffer_specular.oob_zero = True  # bilinear_sample reads column W / row H with weight ~0 (pathtracer.py:1077-1090)
+    pos, view, proj = default_camera_matrices(W, H, pos=(-0.7, 0.9, 1.8))
+    state = {"sample": 0, "count": {}}
+    r.set_max_samples(999999999.0)
+    r.set_render_scale(1.0)
+    r.set_camera_is_moving(False)
+    r.reset_framebuffer()
+    r.current_spp = 0  # reset_framebuffer leaves 1 (pathtracer.py:664-668); only _render_to_image's unused argument reads it
+    for s in range(n_frames):
+        set_reference_camera(r, pos, view, proj)
+        state["sample"], state["count"] = s, {}
+        ti.set_random_source(path_random_source(W, seed, state), with_frame=True)
+        r.accumulate()
+        ti.set_random_source(None)
+        img = r.fetch_image()
+        r.copy_prev_matrices()
+        print("frame %d: hdr mean %.4f ldr mean %.4f" % (s, float(r.color_buffer.arr.mean()), float(img.arr[..., :3].mean())))
+    out = dict(material=mat, color=col, cam_pos=pos, view=view, proj=proj, seed=np.int32(seed), W=np.int32(W), H=np.int32(H),
+               sky_res=np.int32(S), sky_scatter=sc, sky_trans=tr, n_frames=np.int32(n_frames), exposure=np.float32(3.0),
+               hdr=np.transpose(r.color_buffer.arr, (1, 0, 2)).copy(), ldr=np.transpose(img.arr, (1, 0, 2)).copy())
+    for k, v in cfg.items():
+        out["cfg_" + k] = np.asarray(v, np.float32)
+    np.savez_compressed(os.path.join(HERE, "ref_frame.npz"), **out)
+
+
+# ------------------------------------------------------------------------- atmos.py (sky)
+def section_sky():
+    """renderer/atmos.py: (1) 640 entries of the transmittance LUT from generate_transmittance_lut,
+    (2) the whole precompute pipeline of Scene.finish (cloud ambient -> accumulate_clouds x passes ->
+    compute_skybox, scene.py:243-253) on a 6 x 6 table, ti.random() answering from the oracle's
+    per-texel counter sampler (key = (texel, pass), running counter) so tables compare per texel,
+    (3) project_sky / unproject_sky / sample_skybox(_transmittance) lookups.
+    The pipeline reads the LUT at arbitrary entries; computing all 32768 through the emulator
+    would take ~45 min, so after (1) the reference's LUT field is filled from the oracle's table
+    (stored in the fixture: lut_full)."""
+    sys.path.insert(0, ROOT)
+    from oracle import binding as oracle
+    from renderer.atmos import Atmos
+    from voxel_rt2_b200.materials import material_table
+
+    out = {}
+    atm = Atmos()
+    atm.load_textures()
+    rng = np.random.default_rng(99)
+    # (1) LUT subset: edges, horizon band, random interior
+    sub = {(x, y) for x in (0, 1, 127, 128, 129, 254, 255) for y in (0, 1, 63, 126, 127)}
+    sub |= {(int(x), int(y)) for x, y in zip(rng.integers(0, 256, 400), rng.integers(0, 128, 400))}
+    sub |= {(int(x), int(y)) for x, y in zip(rng.integers(120, 140, 205), rng.integers(0, 128, 205))}
+    sub = sorted(sub)
+    atm.trans_LUT._struct_for = lambda: iter([(np.int32(x), np.int32(y)) for x, y in sub])
+    atm.generate_transmittance_lut()
+    del atm.trans_LUT._struct_for
+    idx = np.array(sub, np.int32)
+    out["lut_idx"] = idx
+    out["lut_val"] = atm.trans_LUT.arr[idx[:, 0], idx[:, 1]].copy()
+    print("sky: %d LUT entries" % len(sub))
+
+    # (2) pipeline on an S x S table
+    S, passes, seed = 6, 2, 5
+    sun_dir, cone, sun_col = (0.6, 0.5, -0.62), 0.05, (1.3, 1.2337, 1.2181)
+    tex = np.load(os.path.join(ROOT, "voxel_rt2_b200", "assets", "cloud_texture.npz"))["tex"]
+    assert np.array_equal(tex, atm.cloud_tex.arr), "the packaged cloud texture differs from ti.tools.imread's decode"
+    o = oracle.OracleRenderer(dx=2 / 16, image_res=(16, 16), grid_res=16, sky_res=S, cloud_passes=passes, seed=seed,
+                              materials=material_table(), cloud_tex=tex)
+    o.set_directional_light(sun_dir, cone, sun_col)
+    o.set_use_physical_sky(True, True)
+    o.prepare_data()
+    lut = o.get_trans_lut()
+    out["lut_full"] = lut
+    atm.trans_LUT.arr[...] = lut
+    atm.skybox_res = ti.Vector([S, S])
+    atm.skybox_fres = ti.Vector([1.0 / S, 1.0 / S])
+    atm.skybox_scattering = ti.Vector.field(3, dtype=ti.f32, shape=(S, S))
+    atm.skybox_transmittance = ti.Vector.field(3, dtype=ti.f32, shape=(S, S))
+    atm.use_clouds[None] = 1
+    d = np.asarray(sun_dir, np.float64)
+    light_dir = vec((d / np.sqrt((d * d).sum())).astype(np.float32))   # set_directional_light (pathtracer.py:138-144)
+    light_col = vec(np.asarray(sun_col, np.float32)) * 3.0                # light_color * light_weight
+    cosmax = np.float32(np.cos(cone * 0.5))
+    state = {"pass": 0, "count": {}}
+
+    def source(name, frame):
+        f = frame
+        while f is not None and f.f_code.co_name not in ("accumulate_clouds", "compute_skybox", "compute_cloud_ambient"):
+            f = f.f_back
+        k = f.f_code.co_name
+        if k == "compute_cloud_ambient":
+            texel, pas = 0xFFFFFFFF, 2000
+        elif k == "accumulate_clouds":
+            texel, pas = int(f.f_locals["u"]) * S + int(f.f_locals["v"]), state["pass"]
+        else:
+            off = f.f_locals["offset"]
+            texel, pas = int(off[0]) * S + int(off[1]), 1000
+        n = state["count"].get((texel, pas), 0)
+        state["count"][(texel, pas)] = n + 1
+        return sampler_rnd(texel, pas, seed, n)
+
+    ti.set_random_source(source, with_frame=True)
+    atm.compute_cloud_ambient(light_dir, light_col, cosmax)
+    out["cloud_ambient"] = atm.cloud_ambient.arr.copy()
+    for p in range(passes):
+        state["pass"] = p
+        atm.accumulate_clouds(light_dir, light_col, cosmax, passes)
+    out["clouds_scatter"], out["clouds_trans"] = atm.skybox_scattering.arr.copy(), atm.skybox_transmittance.arr.copy()
+    for sl in range(S):
+        atm.compute_skybox(light_dir, light_col, cosmax, sl, S)
+    ti.set_random_source(None)
+    out["sky_scatter"], out["sky_trans"] = atm.skybox_scattering.arr.copy(), atm.skybox_transmittance.arr.copy()
+    out.update(S=np.int32(S), passes=np.int32(passes), seed=np.int32(seed), sun_dir=np.asarray(sun_dir, np.float32), cone=np.float32(cone),
+               sun_col=np.asarray(sun_col, np.float32))
+    print("sky: %dx%d tables, mean scatter %.4f trans %.4f, %d draws" % (S, S, out["sky_scatter"].mean(), out["sky_trans"].mean(),
+                                                                        sum(state["count"].values())))
+    # (3) parameterisation and lookups on those tables
+    n = 96
+    dirs = unit(rng, n)
+    dirs[:4] = [[0, 1, 0], [0, -1, 0], [1, 0, 0], [0.3, 1e-4, -0.95]]
+    dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    uv = np.array([atm.project_sky(vec(x)).data for x in dirs], np.float32)
+    uv_in = rng.random((n, 2)).astype(np.float32)
+    back = np.array([atm.unproject_sky(vec(x)).data for x in uv_in], np.float32)
+    tr = np.array([atm.sample_skybox_transmittance(vec(x)).data for x in dirs], np.float32)
+    jit = rng.random((n, 3)).astype(np.float32)
+    sc2, tr2 = np.zeros((n, 3), F), np.zeros((n, 3), F)
+    for i in range(n):
+        q = list(jit[i])
+        ti.set_random_source(lambda name: q.pop(0))
+        a, b = atm.sample_skybox(vec(dirs[i]))
+        sc2[i], tr2[i] = a.data, b.data
+    ti.set_random_source(None)
+    out.update(dirs=dirs, project_uv=uv, unproject_in=uv_in, unproject_dir=back, lookup_trans=tr, lookup_jitter=jit, lookup_scatter_j=sc2,
+               lookup_trans_j=tr2)
+    np.savez_compressed(os.path.join(HERE, "ref_sky.npz"), **out)
+
+
+SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render, "frame": section_frame,
+            "sky": section_sky}
 
 if __name__ == "__main__":
     for s in (sys.argv[1:] or list(SECTIONS)):

@@ -563,8 +563,9 @@ def test_merged_resolve_without_peers_equals_fetch_image(vrt):
 def test_cuda_matches_reference_source_vectors(vrt):
     """The CUDA path against vectors computed by the REFERENCE'S OWN renderer source (executed
     through oracle/ti_emu; tests/golden/make_ref_vectors.py), without the oracle in between:
-    hit buffer bit-exact; per-pixel radiance of single samples within 2e-3 on >= 97 % of the
-    pixels (SFU-approximate shading arithmetic) and 1 % in the image mean."""
+    hit buffer bit-exact; per-pixel radiance of single samples within 2e-3 on >= 99 % of the
+    pixels (measured: all of them, worst 4e-4; the shading arithmetic uses SFU approximations) and
+    0.1 % in the image mean."""
     import os
 
     from util import reference_hit_fields, reference_radiance, renderer_from_reference_fixture
@@ -587,5 +588,26 @@ def test_cuda_matches_reference_source_vectors(vrt):
         err = np.abs(a - b).max(-1) / np.maximum(np.abs(b).max(-1), 1e-3)
         close = np.mean(err <= 2e-3)
         print("sample %d: within 2e-3 on %.4f of the pixels, worst %.3e" % (s, close, err.max()))
-        assert close >= 0.97
-        assert abs(a.mean() - b.mean()) <= 0.01 * b.mean()
+        assert close >= 0.99
+        assert abs(a.mean() - b.mean()) <= 1e-3 * b.mean()
+
+
+def test_cuda_matches_reference_source_frame_loop(vrt):
+    """CUDA accumulate + fetch_image against the reference's own static-camera frame loop (4 frames,
+    physical sky lookups, temporal accumulation, tonemap) from tests/golden/ref_frame.npz."""
+    import os
+
+    from util import renderer_from_reference_fixture
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_frame.npz"))
+    g = renderer_from_reference_fixture(vrt.Renderer, z, exposure=float(z["exposure"]))
+    g.set_use_physical_sky(True, False)
+    g.set_sky_tables(z["sky_scatter"], z["sky_trans"])
+    g.prepare_data()
+    g.accumulate(int(z["n_frames"]))
+    hdr, ldr = g.fetch_hdr(), g.fetch_image()
+    err = np.abs(hdr[..., :3] - z["hdr"]).max(-1) / np.maximum(np.abs(z["hdr"]).max(-1), 1e-3)
+    print("HDR: within 2e-3 on %.4f of the pixels, worst %.3e; LDR worst abs %.3e" % (np.mean(err <= 2e-3), err.max(),
+                                                                                      np.abs(ldr[..., :3] - z["ldr"][..., :3]).max()))
+    assert np.mean(err <= 2e-3) >= 0.99
+    assert np.abs(ldr[..., :3] - z["ldr"][..., :3]).max() < 5e-3
