@@ -3,10 +3,12 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load anything under oracle/.
 //
-// Parity status: "parity unpinned" w.r.t. Taichi itself — the reference ships no golden
-// vectors and Taichi is not installable here. Semantics below follow
-// Taichi's documented Python definitions (taichi.math: mix/clamp/fract/sign/reflect,
-// Vector.dot/norm/normalized) with IEEE float32, no FMA contraction.
+// Parity status: the reference ships no golden vectors and Taichi is not installable here
+// (SURVEY.md §8c); the oracle is pinned against the reference's OWN Python source executed
+// through oracle/ti_emu (a float32 Taichi emulator): tests/golden/ref_*.npz, checked by
+// tests/test_reference_vectors.py. Semantics below follow Taichi's Python definitions
+// (taichi.math: mix/clamp/fract/sign/reflect, Vector.dot/norm/normalized) with IEEE float32,
+// no FMA contraction.
 #pragma once
 #include <cmath>
 #include <cstdint>

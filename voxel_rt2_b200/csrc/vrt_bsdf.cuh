@@ -7,6 +7,8 @@
 #pragma once
 #include "vrt_common.cuh"
 
+#define VRT_COLD static __device__ __noinline__
+
 enum { LOBE_DIFFUSE = 0, LOBE_SPEC_REFL = 1, LOBE_CLEARC = 2 };
 
 HD Mat load_mat(const float4* __restrict__ mats, int id) {
@@ -55,6 +57,27 @@ HD float cone_sample_pdf(float cos_theta_max, float cos_theta) {
   return cos_theta >= cos_theta_max ? 1.0f / (2.0f * VRT_PI * (1.0f - cos_theta_max)) : 0.0f;
 }
 
+// Sheen and subsurface terms of disney_diffuse (bsdf.py:56-67). Kept out of line (VRT_COLD): most
+// material rows have neither, and the path kernel is instruction-fetch bound — code that is rarely
+// executed must not sit inside its main loop.
+VRT_COLD f3 diffuse_sheen_subsurface(f3 base_col, float sheen_w, float sheen_tint, float subsurface, float roughness, f3 f_d, float n_dot_l,
+                                     float n_dot_v, float l_dot_h, float F_L, float F_V) {
+  f3 sheen = mk3(0.0f);
+  if (sheen_w != 0.0f) {
+    float albedo_lum = luminance(base_col);
+    f3 sheen_col = albedo_lum > 0.0f ? base_col / albedo_lum : mk3(1.0f);
+    sheen = sheen_w * mix3(mk3(1.0f), sheen_col, sheen_tint) * pow5(1.0f - l_dot_h);
+  }
+  if (subsurface != 0.0f) {
+    float Fss90 = l_dot_h * l_dot_h * roughness;
+    float Fss = mixf(1.0f, Fss90, F_L) * mixf(1.0f, Fss90, F_V);
+    float ss = 1.25f * (Fss * (frcp(n_dot_l + n_dot_v) - 0.5f) + 0.5f);
+    f3 sub = ((1.0f / VRT_PI) * ss) * base_col;
+    f_d = mix3(f_d, sub, subsurface);
+  }
+  return f_d + sheen;
+}
+
 // bsdf.py:39-67 diffuse + retro-reflection + sheen + subsurface
 HD f3 disney_diffuse(const Mat& m, float n_dot_l, float n_dot_v, float l_dot_h) {
   float R_R = 2.0f * m.roughness * sqr(l_dot_h);
@@ -63,20 +86,9 @@ HD f3 disney_diffuse(const Mat& m, float n_dot_l, float n_dot_v, float l_dot_h) 
   f3 f_lambert = m.base_col * (1.0f / VRT_PI);
   f3 f_retro = f_lambert * (R_R * (F_L + F_V + F_L * F_V * (R_R - 1.0f)));
   f3 f_d = f_lambert * ((1.0f - 0.5f * F_L) * (1.0f - 0.5f * F_V)) + f_retro;
-  f3 sheen = mk3(0.0f);
-  if (m.sheen != 0.0f) {
-    float albedo_lum = luminance(m.base_col);
-    f3 sheen_col = albedo_lum > 0.0f ? m.base_col / albedo_lum : mk3(1.0f);
-    sheen = m.sheen * mix3(mk3(1.0f), sheen_col, m.sheen_tint) * pow5(1.0f - l_dot_h);
-  }
-  if (m.subsurface != 0.0f) {
-    float Fss90 = l_dot_h * l_dot_h * m.roughness;
-    float Fss = mixf(1.0f, Fss90, F_L) * mixf(1.0f, Fss90, F_V);
-    float ss = 1.25f * (Fss * (frcp(n_dot_l + n_dot_v) - 0.5f) + 0.5f);
-    f3 sub = ((1.0f / VRT_PI) * ss) * m.base_col;
-    f_d = mix3(f_d, sub, m.subsurface);
-  }
-  return f_d + sheen;
+  if (m.sheen != 0.0f || m.subsurface != 0.0f)
+    return diffuse_sheen_subsurface(m.base_col, m.sheen, m.sheen_tint, m.subsurface, m.roughness, f_d, n_dot_l, n_dot_v, l_dot_h, F_L, F_V);
+  return f_d;
 }
 
 // bsdf.py:69-71: 1 / (pi ax ay (hx^2/ax^2 + hy^2/ay^2 + nh^2)^2); 1/(pi ax ay) comes from the table
@@ -115,6 +127,46 @@ HD float disney_clearcoat(const Mat& m, float n_dot_l, float n_dot_v, float n_do
   return m.clearcoat * D * F * G;
 }
 
+// Clear-coat code of the path kernel, out of line (VRT_COLD, see diffuse_sheen_subsurface): only
+// material rows 21, 22, 32 and 54 of the default set have a clear coat. Arguments by value so the
+// caller's material stays in registers.
+struct CoatParams {
+  float clearcoat, cc_alpha, cc_norm, cw;
+};
+HD CoatParams coat_of(const Mat& m) { return CoatParams{m.clearcoat, m.cc_alpha, m.cc_norm, m.cw}; }
+HD Mat coat_mat(CoatParams c) {
+  Mat m{};
+  m.clearcoat = c.clearcoat, m.cc_alpha = c.cc_alpha, m.cc_norm = c.cc_norm, m.cw = c.cw;
+  return m;
+}
+VRT_COLD float cold_clearcoat_eval(CoatParams c, float n_dot_l, float n_dot_v, float n_dot_h, float l_dot_h) {
+  return disney_clearcoat(coat_mat(c), n_dot_l, n_dot_v, n_dot_h, l_dot_h);
+}
+VRT_COLD float cold_clearcoat_pdf(CoatParams c, float n_dot_h, float v_dot_h) {  // bsdf.py:190-199
+  float ndh = fabsf(n_dot_h);
+  return fdiv(GTR1(coat_mat(c), ndh) * ndh, 4.0f * v_dot_h) * c.cw;
+}
+// bsdf.py:201-224 sample_clearcoat: returns (direction, lobe pdf x lobe probability)
+VRT_COLD float4 cold_clearcoat_sample(CoatParams c, f3 v, f3 n, f3 tang, f3 bitang, float ux, float uy) {
+  const Mat m = coat_mat(c);
+  float a2 = sqr(m.cc_alpha);
+  float cosTheta = fsqrt(fmaxf(1e-4f, fdiv(1.0f - __powf(a2, 1.0f - ux), 1.0f - a2)));
+  float sinTheta = fsqrt(fmaxf(1e-4f, 1.0f - cosTheta * cosTheta));
+  float s, co;
+  __sincosf(2.0f * VRT_PI * uy, &s, &co);
+  f3 h = (sinTheta * co) * tang + (sinTheta * s) * bitang + cosTheta * n;
+  if (dot(h, v) < 0.0f) h *= -1.0f;
+  f3 dir = reflect(-v, h);
+  float ndh = fabsf(dot(n, h));
+  float pdf = fdiv(GTR1(m, ndh) * ndh, 4.0f * dot(v, h)) * m.cw;
+  return make_float4(dir.x, dir.y, dir.z, pdf);
+}
+// brdf of the sampled clear-coat direction, half vector recomputed from (dir, v) as the reference does
+VRT_COLD float cold_clearcoat_brdf(CoatParams c, f3 v, f3 n, f3 dir) {
+  f3 h = normalize(dir + v);
+  return disney_clearcoat(coat_mat(c), dot(n, dir), dot(n, v), dot(n, h), dot(dir, h));
+}
+
 // Shared dot products of one (v, n, l) configuration.
 struct Geo {
   float n_dot_l, n_dot_v, l_dot_h, n_dot_h, h_dot_x, h_dot_y, l_dot_x, l_dot_y, v_dot_x, v_dot_y, v_dot_h;
@@ -147,15 +199,12 @@ HD void eval_and_pdf(const Mat& m, f3 v, f3 n, f3 l, f3 tang, f3 bitang, f3& bsd
     bsdf_d = disney_diffuse(m, g.n_dot_l, g.n_dot_v, g.l_dot_h) * (1.0f - m.metallic);
     float Gl = smithG_GGX_aniso(g.n_dot_l, g.l_dot_x, g.l_dot_y, m.ax, m.ay);
     bsdf_s = (D * (Gl * Gv)) * disney_fresnel(m, g.l_dot_h);
-    if (m.clearcoat != 0.0f) bsdf_s += mk3(disney_clearcoat(m, g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
+    if (m.clearcoat != 0.0f) bsdf_s += mk3(cold_clearcoat_eval(coat_of(m), g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
   }
   // pdf_disney = sum of lobe pdfs times lobe probabilities
   pdf = (saturate(g.n_dot_l) * (1.0f / VRT_PI)) * m.dw;
   pdf += fdiv(Gv * fabsf(g.l_dot_h) * D, fabsf(g.n_dot_l)) * m.sw;  // bsdf.py:254-277
-  if (m.cw != 0.0f) {                                               // bsdf.py:190-199 (cw == 0 adds 0)
-    float ndh = fabsf(g.n_dot_h);
-    pdf += fdiv(GTR1(m, ndh) * ndh, 4.0f * g.v_dot_h) * m.cw;
-  }
+  if (m.cw != 0.0f) pdf += cold_clearcoat_pdf(coat_of(m), g.n_dot_h, g.v_dot_h);  // bsdf.py:190-199 (cw == 0 adds 0)
 }
 
 // bsdf.py:226-252 VNDF sampling in the (tangent, normal, bitangent) frame
@@ -201,20 +250,11 @@ HD f3 sample_disney(const Mat& m, f3 v, f3 n, f3 tang, f3 bitang, float u_lobe, 
     Geo g = make_geo(v, n, dir, tang, bitang);
     brdf = disney_specular(m, g);
   } else {
-    // bsdf.py:201-224 sample_clearcoat
-    float a2 = sqr(m.cc_alpha);
-    float cosTheta = fsqrt(fmaxf(1e-4f, fdiv(1.0f - __powf(a2, 1.0f - ux), 1.0f - a2)));
-    float sinTheta = fsqrt(fmaxf(1e-4f, 1.0f - cosTheta * cosTheta));
-    float s, c;
-    __sincosf(2.0f * VRT_PI * uy, &s, &c);
-    f3 h = (sinTheta * c) * tang + (sinTheta * s) * bitang + cosTheta * n;
-    if (dot(h, v) < 0.0f) h *= -1.0f;
-    dir = reflect(-v, h);
-    float ndh = fabsf(dot(n, h));
-    pdf = fdiv(GTR1(m, ndh) * ndh, 4.0f * dot(v, h)) * m.cw;
+    const float4 r = cold_clearcoat_sample(coat_of(m), v, n, tang, bitang, ux, uy);
+    dir = f3{r.x, r.y, r.z};
+    pdf = r.w;
     lobe = LOBE_CLEARC;
-    Geo g = make_geo(v, n, dir, tang, bitang);
-    brdf = mk3(disney_clearcoat(m, g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
+    brdf = mk3(cold_clearcoat_brdf(coat_of(m), v, n, dir));
   }
   if (isbad(pdf)) pdf = 1.0f;
   return dir;

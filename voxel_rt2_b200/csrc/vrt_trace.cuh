@@ -37,6 +37,27 @@ HD bool upper_bit(const Params& P, const uint32_t* __restrict__ upper, int x, in
   return (upper[P.upper_off[lod - 3] + (idx >> 5)] >> (idx & 31)) & 1u;
 }
 
+// One axis of ray_aabb_intersection against [0,R] (math_utils.py:103-123; an axis with d == 0 is
+// skipped, as in the reference). Out of line: three calls share one copy of the two IEEE divisions
+// (measured +0.8 %; sharing the hotter helpers this way — every division, the sky fetches — was
+// measured 4 % slower: a call on the hot path costs more fetch redirects than the footprint saves).
+struct SlabRange {
+  float near_int, far_int;
+};
+static __device__ __noinline__ SlabRange slab_axis_nl(float o, float d, float Rf, float near_int, float far_int) {
+  if (d != 0.0f) {
+    float i1 = __fdiv_rn(xsub(0.0f, o), d);
+    float i2 = __fdiv_rn(xsub(Rf, o), d);
+    far_int = fminf(fmaxf(i1, i2), far_int);
+    near_int = fmaxf(fminf(i1, i2), near_int);
+  }
+  return SlabRange{near_int, far_int};
+}
+HD void slab_axis(float o, float d, float Rf, float& near_int, float& far_int) {
+  const SlabRange r = slab_axis_nl(o, d, Rf, near_int, far_int);
+  near_int = r.near_int, far_int = r.far_int;
+}
+
 template <bool STATS>
 HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3 d, TraceCounters* tc) {
   RayHit h;
@@ -51,18 +72,9 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
   // (Skipping the three entry-side divisions for origins inside the box is exact but was measured
   // 6 % slower: primary and secondary rays share warps, so both variants execute.)
   float near_int = -VRT_INF, far_int = VRT_INF;
-  {
-    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      if (dd[i] != 0.0f) {
-        float i1 = xdiv(xsub(0.0f, oo[i]), dd[i]);
-        float i2 = xdiv(xsub(Rf, oo[i]), dd[i]);
-        far_int = fminf(fmaxf(i1, i2), far_int);
-        near_int = fmaxf(fminf(i1, i2), near_int);
-      }
-    }
-  }
+  slab_axis(o.x, d.x, Rf, near_int, far_int);
+  slab_axis(o.y, d.y, Rf, near_int, far_int);
+  slab_axis(o.z, d.z, Rf, near_int, far_int);
   if (!(near_int <= far_int && VRT_EPS < far_int && near_int < VRT_INF)) {
     return h;
   }
