@@ -272,7 +272,7 @@ HD void disney_evaluate_lobewise_split(const Mat& m, f3 v, f3 n, f3 l, f3 tang, 
     if (lobe_id == LOBE_DIFFUSE || lobe_id == LOBE_ALL) bsdf_d = disney_diffuse(m, g.n_dot_l, g.n_dot_v, g.l_dot_h) * (1.0f - m.metallic);
     if (lobe_id == LOBE_SPEC_REFL || lobe_id == LOBE_ALL) bsdf_s = disney_specular(m, g);
     if ((lobe_id == LOBE_CLEARC || lobe_id == LOBE_ALL) && m.clearcoat != 0.0f)
-      bsdf_s += mk3(disney_clearcoat(m, g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
+      bsdf_s += mk3(cold_clearcoat_eval(coat_of(m), g.n_dot_l, g.n_dot_v, g.n_dot_h, g.l_dot_h));
   }
 }
 HD f3 disney_evaluate_lobewise(const Mat& m, f3 v, f3 n, f3 l, f3 tang, f3 bitang, int lobe_id) {
@@ -291,8 +291,7 @@ HD float pdf_disney_lobewise(const Mat& m, f3 v, f3 n, f3 l, f3 tang, f3 bitang,
     float Gv = smithG_GGX_aniso(g.n_dot_v, g.v_dot_x, g.v_dot_y, m.ax, m.ay);
     pdf = fdiv(Gv * fabsf(g.l_dot_h) * D, fabsf(g.n_dot_l)) * m.sw;
   } else {
-    float ndh = fabsf(g.n_dot_h);
-    pdf = fdiv(GTR1(m, ndh) * ndh, 4.0f * g.v_dot_h) * m.cw;
+    pdf = cold_clearcoat_pdf(coat_of(m), g.n_dot_h, g.v_dot_h);
   }
   if (isbad(pdf)) pdf = 1.0f;
   return pdf;

@@ -196,7 +196,17 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
     const float center_F_lum = luminance(center.z.F);
     const RcPre center_rc = prep_rc(G, center.z, true);
     const DstPre center_dst = prep_dst(G, center_x1, center_n1);
+    // The tap loop is split in two so that each loop body inlines ONE copy of shift() (~17 KB of
+    // BSDF code): with both shifts in one body the loop was 40 KB, beyond the SM's instruction
+    // cache, and the kernel was instruction-fetch bound (ncu: 3.0 no-instruction stalls per issue).
+    // Pass A shifts the centre sample to every accepted neighbour (needs the neighbour's G-buffer
+    // record only) and keeps p_hat(centre -> tap) and the tap's pixel index in local memory;
+    // pass B shifts each neighbour's sample to the centre and merges, in the reference's tap order.
+    float tap_center_p_hat[32];
+    int tap_index[32];
+#pragma unroll 1
     for (int i = 0; i < max_taps; i++) {
+      tap_index[i] = -1;
       const float golden_angle = 2.399963229728f;
       const float angle = ((float)i + angle_shift) * golden_angle;
       const float offset_radius = sqrtf(((float)i + radius_shift) / (float)max_taps) * max_radius;
@@ -207,33 +217,31 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
       const int tu = u + ox, tv = v + oy;
       if (tu < 0 || tv < 0 || tu >= W || tv >= H) continue;
       const size_t ti = (size_t)tv * W + tu;
-      // issue every load of the tap up front (G-buffer record + 56-byte reservoir): one memory
-      // round trip per tap instead of three dependent ones
       const float4 ngp = __ldg(RB.gpos + ti);
       const uint2 nga = __ldg(RB.gattr + ti);
-      uint32_t nw[14];
-      {
-        const uint2* src = RB.reservoirs + ti * 7;
-#pragma unroll
-        for (int q = 0; q < 7; q++) {
-          const uint2 t = __ldg(src + q);
-          nw[2 * q] = t.x, nw[2 * q + 1] = t.y;
-        }
-      }
       if (ngp.w != 0.0f) continue;
       const f3 neighbour_n1 = decode_unit_vector_3x16(h16val(nga.x), h16val(nga.x >> 16));
       const f3 neighbour_x1{ngp.x, ngp.y, ngp.z};
       const float neighbour_dist = length(neighbour_x1 - P.cam_pos);
       if (fabsf(neighbour_dist - center_dist) > 0.1f * center_dist || dot(center_n1, neighbour_n1) < 0.5f) continue;
-      RReservoir nb;
-      decode_reservoir(nw, s_unorm, nb);
       int neighbour_mat_id;
       const Mat neighbour_mat = decode_material(G, nga.y, neighbour_mat_id);
-      f3 c_d, c_s, s_d, s_s;
-      float c_jacobian, jacobian;
+      f3 c_d, c_s;
+      float c_jacobian;
       shift_sample(G, neighbour_x1, neighbour_n1, neighbour_mat, prep_dst(G, neighbour_x1, neighbour_n1), center, center_rc, c_d, c_s, c_jacobian);
+      tap_center_p_hat[i] = luminance(c_d + c_s) * c_jacobian;
+      tap_index[i] = (int)ti;
+    }
+#pragma unroll 1
+    for (int i = 0; i < max_taps; i++) {
+      const int ti = tap_index[i];
+      if (ti < 0) continue;
+      RReservoir nb;
+      load_reservoir(RB.reservoirs, (size_t)ti, s_unorm, nb);
+      f3 s_d, s_s;
+      float jacobian;
       shift_sample(G, center_x1, center_n1, center_mat, center_dst, nb, prep_rc(G, nb.z, false), s_d, s_s, jacobian);
-      const float center_p_hat = luminance(c_d + c_s) * c_jacobian;
+      const float center_p_hat = tap_center_p_hat[i];
       float canonical_weight = center_p_hat * nb.M;
       canonical_weight = canonical_weight / (center_p_hat * nb.M + center_F_lum * center.M / (float)max_taps);
       canonical_mis_weight += 1.0f - canonical_weight;
