@@ -204,12 +204,32 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "paths/s", "cores": cores, "kind": "port",
                              "sample": "oracle C++/OpenMP restatement; per step 1 spp over every 4th 8x4 tile of the 1080p frame"},
             "e2e": {"value": v, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Everything that libraries print to fd 1 during the run (NCCL's version banner, for one) goes to
+    stderr; the one JSON line is written to the real stdout at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
     global WORKLOAD
     args = parse()
+    _protect_stdout()
     WORKLOAD = args.workload
     if WORKLOAD != "config3":
         args.grid = 128
@@ -379,7 +399,7 @@ def main():
                                                      ("rays", "steps", "queries", "hits", "sky_escapes", "nee_visible")}}
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "paths/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
