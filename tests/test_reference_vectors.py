@@ -54,8 +54,10 @@ def test_traversal_matches_reference_raytrace_bit_for_bit(oracle, grid):
 
 
 def _close(a, b, rtol, atol=0.0):
+    """|a - b| <= atol + rtol |b| elementwise; a NaN matches a NaN (the reference's zenith / nadir
+    azimuth is 0/0 in project_sky, and so is the oracle's)."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.abs(a - b) <= atol + rtol * np.abs(b)
+    return (np.abs(a - b) <= atol + rtol * np.abs(b)) | (np.isnan(a) & np.isnan(b))
 
 
 def test_math_helpers_match_reference(oracle):
@@ -214,9 +216,9 @@ def test_sky_precompute_matches_reference_atmos(oracle):
     got = lut[idx[:, 0], idx[:, 1]]
     # f16 storage: allow one f16 ulp (2^-10 relative) where exp() differs in the last float32 bit
     assert (np.abs(got - ref) <= 1.0e-3 * np.abs(ref) + 1e-7).all()
-    assert (got == ref).mean() > 0.95
+    assert (got == ref).mean() > 0.98  # measured: all 627 identical
     assert np.array_equal(o.get_trans_lut().view(np.uint16), z["lut_full"].view(np.uint16))  # the table the reference run was given
-    rt = 2e-4
+    rt = 1e-4  # measured: scattering 3.5e-5, transmittance 7e-7, cloud ambient 8e-6
     assert _close(o.get_cloud_ambient(), z["cloud_ambient"], rt, 1e-7).all()
     sc, tr = o.get_sky_tables()
     assert _close(sc, z["sky_scatter"], rt, 1e-6).all(), np.abs(sc - z["sky_scatter"]).max()
