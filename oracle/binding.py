@@ -52,6 +52,7 @@ def load():
     lib.orc_get_trans_lut.argtypes = [P, P]
     lib.orc_get_cloud_ambient.argtypes = [P, fp]
     lib.orc_sample_skybox.argtypes = [P, C.c_int, fp, fp, fp, fp]
+    lib.orc_shift_probe.argtypes = [P, C.c_int, fp, fp]
     lib.orc_set_tile_shard.argtypes = [P, C.c_int, C.c_int]
     lib.orc_trace_primary.argtypes = [P, P]
     lib.orc_accumulate.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -234,6 +235,14 @@ class OracleRenderer:
         a = np.empty((256, 128, 3), np.float16)
         self._lib.orc_get_trans_lut(self._h, a.ctypes.data_as(C.c_void_p))
         return a
+
+    def shift_probe(self, rows):
+        """orc_shift_probe: rows[n][28] float32 (see oracle.cpp) -> [n][7]."""
+        self._sync_camera()
+        rows = np.ascontiguousarray(rows, np.float32)
+        out = np.empty((rows.shape[0], 7), np.float32)
+        self._lib.orc_shift_probe(self._h, rows.shape[0], _fp(rows), _fp(out))
+        return out
 
     def get_cloud_ambient(self):
         a = np.empty(3, np.float32)

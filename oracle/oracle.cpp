@@ -1252,6 +1252,32 @@ void orc_sample_sky_trans(void* p, int n, const float* d, float* out) {
     out[3 * i] = r.x, out[3 * i + 1] = r.y, out[3 * i + 2] = r.z;
   }
 }
+// shift() probe (pathtracer.py:672-812). in[n][28] = dst_pos 3, dst_normal 3, src_pos 3, rc_pos 3, rc_normal 3,
+// rc_incident_dir 3, rc_incident_L 3, rc_NEE_dir 3, cached_jacobian_term, lobes, dst_mat_info bits, rc_mat_info bits;
+// out[n][7] = diffuse 3, specular 3, jacobian * passed_checks
+void orc_shift_probe(void* p, int n, const float* in, float* out) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < n; i++) {
+    const float* a = in + 28 * i;
+    auto v3 = [&](int k) { return V3{a[k], a[k + 1], a[k + 2]}; };
+    Reservoir src;
+    src.z.rc_pos = v3(9), src.z.rc_normal = v3(12), src.z.rc_incident_dir = v3(15), src.z.rc_incident_L = v3(18), src.z.rc_NEE_dir = v3(21);
+    src.z.cached_jacobian_term = a[24];
+    src.z.lobes = (int)a[25];
+    uint32_t dst_info, rc_info;
+    std::memcpy(&dst_info, a + 26, 4);
+    std::memcpy(&rc_info, a + 27, 4);
+    src.z.rc_mat_info = rc_info;
+    Mat dst_mat;
+    int dst_id;
+    decode_material(*c, dst_info, dst_mat, dst_id);
+    V3 d, s;
+    float j;
+    shift_sample(*c, v3(0), v3(3), dst_mat, v3(6), src, d, s, j);
+    float* o = out + 7 * i;
+    o[0] = d.x, o[1] = d.y, o[2] = d.z, o[3] = s.x, o[4] = s.y, o[5] = s.z, o[6] = j;
+  }
+}
 // sample_skybox (atmos.py:94-115) with the three jitter numbers supplied
 void orc_sample_skybox(void* p, int n, const float* d, const float* jitter, float* scat, float* trans) {
   Ctx* c = (Ctx*)p;

@@ -14,7 +14,8 @@ What is emulated (and how):
     parameters, which are passed by reference (written back at statement-level call sites);
   * Matrix helpers follow Taichi's python implementations: normalized() = (1 / norm) * v,
     dot / norm_sqr / matmul accumulate left to right, mix(x, y, a) = x * (1 - a) + y * a,
-    clamp(x, lo, hi) = max(lo, min(x, hi)), reflect(x, n) = x - 2 * dot(x, n) * n;
+    clamp(x, lo, hi) = max(lo, min(x, hi)), reflect(x, n) = x - 2 * dot(x, n) * n; ti.max / ti.min
+    ignore a NaN operand (fmax / fmin, as the LLVM backends lower them);
   * fields are numpy arrays (SNode dense layouts only), struct-for loops run sequentially,
     textures are float arrays with UNORM8 quantisation for rgba8;
   * ti.random() pops from a host-supplied source (`set_random_source`) so a harness can feed the
@@ -558,7 +559,7 @@ def _minmax(fn):
         acc = xs[0]
         for x in xs[1:]:
             if type(acc) in _PYNUM and type(x) in _PYNUM:
-                acc = builtins.max(acc, x) if fn is np.maximum else builtins.min(acc, x)
+                acc = builtins.max(acc, x) if fn is np.fmax else builtins.min(acc, x)
                 continue
             dt = _np_dtype(_promote(_kind(acc), _kind(x)))
             acc = _wrap(fn(_raw(acc, dt), _raw(x, dt)))
@@ -566,8 +567,9 @@ def _minmax(fn):
     return g
 
 
-max = _minmax(np.maximum)
-min = _minmax(np.minimum)
+# fmax / fmin semantics (a NaN operand is ignored), as Taichi's LLVM backends lower ti.max / ti.min
+max = _minmax(np.fmax)
+min = _minmax(np.fmin)
 
 
 def select(c, a, b):

@@ -465,6 +465,75 @@ def section_frame():
     np.savez_compressed(os.path.join(HERE, "ref_frame.npz"), **out)
 
 
+# ------------------------------------------------------------- ReSTIR reconnection shift
+def section_shift():
+    """Renderer.shift() (pathtracer.py:672-812), the reconnection shift of the ReSTIR-PT mode, on
+    160 hand-built (destination vertex, source sample) pairs covering the four kinds of
+    reconnection vertex (surface with continuation, last vertex, escape vertex, NEE-only) and all
+    lobe codes. The zero-vector markers are set explicitly, so no NaN encodings are involved."""
+    sys.path.insert(0, ROOT)
+    import renderer.math_utils as mu
+    from renderer.reservoir import Reservoir
+
+    W, H, R = 32, 16, 32
+    cfg = dict(voxel_edges=0.06, light_dir=(0.4, 0.8, 0.45), light_cone=0.05, light_color=(1.2, 1.1, 0.9), floor_height=-0.5,
+               floor_color=(1.0, 1.0, 1.0), floor_material=1, background=(0.1, 0.1, 0.1))
+    mat, col = render_scene(R, 3)
+    r = make_reference_renderer(W, H, R, mat, col, cfg)
+    cam = (0.7, 0.9, 1.6)
+    r.set_camera_pos(*cam)
+    rng = np.random.default_rng(2024)
+    n = 160
+    ids = np.array([1, 2, 11, 21, 32, 40, 50, 52, 54, 80, 82], np.int32)
+    rows = np.zeros((n, 28), np.float32)
+    out = np.zeros((n, 7), np.float32)
+    for i in range(n):
+        kind = i % 4  # 0 surface + continuation, 1 last vertex, 2 escape vertex, 3 surface, NEE invisible
+        dst_pos = rng.uniform(-0.5, 0.5, 3)
+        dst_n = unit(rng, 1)[0]
+        src_pos = dst_pos + rng.normal(0, 0.05, 3)
+        rc_pos = dst_pos + dst_n * rng.uniform(0.1, 0.6) + rng.normal(0, 0.2, 3)
+        to_dst = dst_pos - rc_pos
+        rc_n = unit(rng, 1)[0]
+        if np.dot(rc_n, to_dst) < 0 and i % 8 < 6:  # mostly front-facing reconnections; some fail the N.L check
+            rc_n = -rc_n
+        inc = unit(rng, 1)[0]
+        if np.dot(inc, rc_n) < 0:
+            inc = -inc
+        nee = np.asarray(cfg["light_dir"]) / np.linalg.norm(cfg["light_dir"]) + rng.normal(0, 0.01, 3)
+        nee /= np.linalg.norm(nee)
+        L = rng.uniform(0.0, 2.0, 3)
+        if kind == 1:
+            inc = np.zeros(3)
+        if kind == 2:
+            rc_n, inc, nee = np.zeros(3), np.zeros(3), np.zeros(3)
+            rc_pos = unit(rng, 1)[0]  # a direction for escape vertices
+            if np.dot(rc_pos, dst_n) < 0 and i % 8 < 6:
+                rc_pos = -rc_pos
+        if kind == 3 or (kind == 1 and i % 8 >= 4):
+            nee = np.zeros(3)
+        res = Reservoir()
+        res.z.rc_pos, res.z.rc_normal, res.z.rc_incident_dir = vec(rc_pos), vec(rc_n), vec(inc)
+        res.z.rc_incident_L, res.z.rc_NEE_dir = vec(L), vec(nee)
+        rc_info = mu.encode_material(np.int32(rng.choice(ids)), vec(rng.uniform(0.1, 1.0, 3)))
+        dst_info = mu.encode_material(np.int32(rng.choice(ids)), vec(rng.uniform(0.1, 1.0, 3)))
+        res.z.rc_mat_info = rc_info
+        res.z.lobes = np.int32(int(rng.integers(0, 3)) * 10 + int(rng.integers(0, 3)))
+        res.z.cached_jacobian_term = np.float32(rng.uniform(0.05, 3.0))
+        dst_mat, _ = mu.decode_material(r.mats.mat_list, dst_info)
+        d, s, j = r.shift(vec(dst_pos), vec(dst_n), dst_mat, vec(src_pos), vec(dst_n), dst_mat, res)
+        z = res.z
+        rows[i, 0:3], rows[i, 3:6], rows[i, 6:9] = dst_pos, dst_n, src_pos
+        rows[i, 9:12], rows[i, 12:15], rows[i, 15:18] = z.rc_pos.data, z.rc_normal.data, z.rc_incident_dir.data
+        rows[i, 18:21], rows[i, 21:24] = z.rc_incident_L.data, z.rc_NEE_dir.data
+        rows[i, 24], rows[i, 25] = z.cached_jacobian_term, float(z.lobes)
+        rows[i, 26:28] = np.array([dst_info, rc_info], np.uint32).view(np.float32)
+        out[i, 0:3], out[i, 3:6], out[i, 6] = d.data, s.data, j
+    cfgo = {("cfg_" + k): np.asarray(v, np.float32) for k, v in cfg.items()}
+    np.savez_compressed(os.path.join(HERE, "ref_shift.npz"), rows=rows, out=out, cam_pos=np.asarray(cam, np.float32), **cfgo)
+    print("shift: %d probes, %d with non-zero Jacobian" % (n, int((out[:, 6] != 0).sum())))
+
+
 # ------------------------------------------------------------------------- atmos.py (sky)
 def section_sky():
     """renderer/atmos.py: (1) 640 entries of the transmittance LUT from generate_transmittance_lut,
@@ -575,7 +644,7 @@ def section_sky():
 
 
 SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render, "frame": section_frame,
-            "sky": section_sky}
+            "shift": section_shift, "sky": section_sky}
 
 if __name__ == "__main__":
     for s in (sys.argv[1:] or list(SECTIONS)):

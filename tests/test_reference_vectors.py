@@ -230,3 +230,22 @@ def test_sky_precompute_matches_reference_atmos(oracle):
     assert _close(o.sample_sky_trans(z["dirs"]), z["lookup_trans"], 1e-4, 1e-6).all()
     s2, t2 = o.sample_skybox(z["dirs"], z["lookup_jitter"])
     assert _close(s2, z["lookup_scatter_j"], 1e-4, 1e-6).all() and _close(t2, z["lookup_trans_j"], 1e-4, 1e-6).all()
+
+
+def test_restir_shift_matches_reference(oracle):
+    """Renderer.shift() (pathtracer.py:672-812) evaluated by the reference source on 160 reconnections
+    (surface with continuation / last vertex / escape vertex / NEE-invisible, all lobe codes, some
+    failing the N.L checks): the oracle's shifted integrand (diffuse, specular) and Jacobian agree."""
+    from voxel_rt2_b200.materials import material_table
+
+    z = np.load(os.path.join(G, "ref_shift.npz"))
+    o = oracle.OracleRenderer(dx=2.0 / 32, image_res=(32, 16), grid_res=32, sky_res=0, materials=material_table())
+    o.set_voxels(*scenes.empty(32))
+    o.set_directional_light(z["cfg_light_dir"], float(z["cfg_light_cone"]), z["cfg_light_color"])
+    o.set_camera_pos(*[float(x) for x in z["cam_pos"]])
+    got, ref = o.shift_probe(z["rows"]), z["out"]
+    assert (ref[:, 6] != 0).sum() >= 100 and (ref[:, 6] == 0).sum() >= 10
+    assert _close(got[:, 6], ref[:, 6], 2e-6, 1e-9).all()
+    live = ref[:, 6] != 0  # a zero Jacobian multiplies every use of the integrand (the CUDA path skips it)
+    assert _close(got[live, :6], ref[live, :6], 1e-4, 1e-7).all(), np.abs(got[live, :6] - ref[live, :6]).max()
+    assert np.abs(ref[live, :6]).max() > 0.01
