@@ -465,6 +465,68 @@ def section_frame():
     np.savez_compressed(os.path.join(HERE, "ref_frame.npz"), **out)
 
 
+# ------------------------------------------------ BASELINE config 1: example1 hit buffer
+def section_example1():
+    """BASELINE.json configs[0] at reduced resolution: the example1.py scene (shim seed 0, the committed
+    tests/golden/example1_seed0.npz) in the Renderer exactly as shipped (128^3 grid, dx = 1/64, default
+    camera, fov 50), 64 x 64 primary rays + the sun shadow ray on the cone axis, through the
+    reference's own get_cast_dir / next_hit / _update_lods / _make_texture."""
+    sys.path.insert(0, ROOT)
+    from renderer.math_utils import eps, inf
+    from renderer.pathtracer import Renderer
+    from renderer.raytracer import VoxelOctreeRaytracer
+    from voxel_rt2_b200.camera import default_camera_matrices
+
+    z = np.load(os.path.join(HERE, "example1_seed0.npz"))
+    W = H = 64
+    r = Renderer(dx=1.0 / 64.0, image_res=(W, H), up=(0, 1, 0), voxel_edges=float(z["voxel_edges"]), exposure=float(z["exposure"]))
+    R = r.voxel_grid_res
+    r.voxel_raytracer.occupancy = ti.field(ti.i32, shape=(2 * R ** 3 // 32 + 1,))  # A1
+    r.world.voxel_material.arr[...] = z["material"]
+    r.world.voxel_color.arr[...] = z["color"]
+    r.set_directional_light(tuple(float(x) for x in z["light_dir"]), float(z["light_noise"]), tuple(float(x) for x in z["light_color"]))
+    r.floor_height[None] = float(z["floor_height"])
+    r.floor_color[None] = tuple(float(x) for x in z["floor_color"])
+    r.floor_material[None] = int(z["floor_material"])
+    r.camera_is_moving[None] = 0
+    r.render_scale[None] = 1.0
+    r.prepare_data()  # world.update_data() + _update_lods, as Scene.finish calls it
+    inner = VoxelOctreeRaytracer.query_occupancy
+
+    def checked(ipos, lod, _rt=r.voxel_raytracer):  # A3
+        n = R >> int(lod)
+        if int(ipos.data.min()) < 0 or int(ipos.data.max()) >= n:
+            return False
+        return inner(_rt, ipos, lod)
+
+    r.voxel_raytracer.query_occupancy = checked
+    pos, view, proj = default_camera_matrices(W, H)
+    set_reference_camera(r, pos, view, proj)
+    tex = r.world.voxel_color_texture
+    hit_t = np.zeros((H, W), np.float32)
+    hit_n = np.zeros((H, W, 3), np.float32)
+    hit_mat = np.zeros((H, W), np.int32)
+    hit_light = np.zeros((H, W), np.int32)
+    shadow = np.full((H, W), 3, np.int32)
+    cam = r.camera_pos[None].copy()
+    ldir = r.light_direction[None].copy()
+    for v in range(H):
+        for u in range(W):
+            d = r.get_cast_dir(np.int32(u), np.int32(v))
+            closest, normal, albedo, hl, iters, mid = r.next_hit(cam, d, inf, tex, shadow_ray=False)
+            hit_t[v, u], hit_n[v, u], hit_mat[v, u], hit_light[v, u] = closest, normal.data, mid, hl
+            if not hl and closest < inf:
+                p = cam + closest * d + normal * eps
+                if ldir.dot(normal) > 0:
+                    shadow[v, u] = 0 if r.next_hit(p, ldir, inf, tex, shadow_ray=True)[0] >= inf else 1
+                else:
+                    shadow[v, u] = 2
+    np.savez_compressed(os.path.join(HERE, "ref_example1_hits_64.npz"), W=np.int32(W), H=np.int32(H), cam_pos=pos, view=view, proj=proj,
+                        hit_t=hit_t, hit_normal=hit_n, hit_mat=hit_mat, hit_light=hit_light, hit_shadow=shadow)
+    print("example1: %d of %d pixels hit, %d voxel hits, shadow states %s" % (int(np.isfinite(hit_t).sum()), W * H,
+                                                                              int((np.abs(hit_n[..., 1]) != 1).sum()), np.bincount(shadow.ravel())))
+
+
 # ------------------------------------------------------------- ReSTIR reconnection shift
 def section_shift():
     """Renderer.shift() (pathtracer.py:672-812), the reconnection shift of the ReSTIR-PT mode, on
@@ -644,7 +706,7 @@ def section_sky():
 
 
 SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render, "frame": section_frame,
-            "shift": section_shift, "sky": section_sky}
+            "shift": section_shift, "example1": section_example1, "sky": section_sky}
 
 if __name__ == "__main__":
     for s in (sys.argv[1:] or list(SECTIONS)):

@@ -636,3 +636,12 @@ def test_cuda_sky_precompute_matches_reference_source_vectors(vrt):
         rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-4)
         print(name, "max rel", rel.max())
         assert rel.max() < 1e-3  # measured 1.7e-4 / 1.3e-6
+
+
+def test_cuda_config1_example1_hit_buffer_matches_reference_source(vrt):
+    """BASELINE config 1 at 64 x 64 (example1.py scene, Renderer as shipped): the CUDA hit buffer
+    equals the one the reference's own next_hit produced (tests/golden/ref_example1_hits_64.npz)."""
+    from util import assert_hits_equal_reference, example1_renderer
+
+    g, h = example1_renderer(vrt.Renderer)
+    assert_hits_equal_reference(g.trace_primary(), h)

@@ -249,3 +249,15 @@ def test_restir_shift_matches_reference(oracle):
     live = ref[:, 6] != 0  # a zero Jacobian multiplies every use of the integrand (the CUDA path skips it)
     assert _close(got[live, :6], ref[live, :6], 1e-4, 1e-7).all(), np.abs(got[live, :6] - ref[live, :6]).max()
     assert np.abs(ref[live, :6]).max() > 0.01
+
+
+def test_config1_example1_hit_buffer_matches_reference(oracle):
+    """BASELINE config 1 at 64 x 64: the example1.py scene in the Renderer exactly as shipped (128^3
+    grid built by the reference's _update_lods / _make_texture), primary ray + sun shadow ray per
+    pixel through the reference's get_cast_dir / next_hit — the oracle's hit buffer is bit-identical."""
+    from util import assert_hits_equal_reference, example1_renderer
+    from voxel_rt2_b200.materials import material_table
+
+    o, h = example1_renderer(oracle.OracleRenderer, materials=material_table())
+    hit = assert_hits_equal_reference(o.trace_primary(), h)
+    assert hit.sum() > 1000 and (h["hit_mat"][hit] == 2).any() and (np.abs(h["hit_normal"][hit][:, 1]) != 1).sum() > 300

@@ -61,3 +61,31 @@ def reference_radiance(z, s):
         c[bad] = 0
         return c
     return scrub(z["render_diffuse"][s]) + scrub(z["render_specular"][s])
+
+
+def example1_renderer(factory, **kw):
+    """The example1.py scene (shim seed 0) in a Renderer configured as the reference ships it
+    (128^3, dx = 1/64, default camera, fov 50 deg) at 64 x 64: the setup of
+    tests/golden/ref_example1_hits_64.npz."""
+    import os
+
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, h = np.load(os.path.join(g, "example1_seed0.npz")), np.load(os.path.join(g, "ref_example1_hits_64.npz"))
+    r = factory(dx=1.0 / 64.0, image_res=(int(h["W"]), int(h["H"])), grid_res=128, sky_res=0, jitter=False, voxel_edges=float(z["voxel_edges"]), **kw)
+    r.set_voxels(z["material"], z["color"])
+    r.set_floor(float(z["floor_height"]), z["floor_color"], int(z["floor_material"]))
+    r.set_directional_light(z["light_dir"], float(z["light_noise"]), z["light_color"])
+    r.set_view_proj(h["cam_pos"], h["view"], h["proj"])
+    r.prepare_data()
+    return r, h
+
+
+def assert_hits_equal_reference(hits, h):
+    got = reference_hit_fields(hits)
+    assert np.array_equal(got["t"].view(np.uint32), h["hit_t"].view(np.uint32))
+    hit = np.isfinite(h["hit_t"])
+    assert np.array_equal(got["normal"][hit], h["hit_normal"][hit] + 0.0)
+    assert np.array_equal(got["mat"][hit], h["hit_mat"][hit])
+    assert np.array_equal(got["light"][hit], h["hit_light"][hit])
+    assert np.array_equal(got["shadow"], h["hit_shadow"])
+    return hit

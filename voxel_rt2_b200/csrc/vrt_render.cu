@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(128) k_primary(const __grid_constant__ Params 
 enum { ST_SEGMENT = 0, ST_SHADOW = 1 };
 enum { PIX_IDLE = -1, PIX_DONE = -2 };
 
+#ifndef VRT_PASS1_MIN_LANES
+#define VRT_PASS1_MIN_LANES 12 // lanes with a fresh shadow ray that justify a second trace pass in the same iteration
+#endif
 #ifndef VRT_PATH_MIN_BLOCKS
 #define VRT_PATH_MIN_BLOCKS 5  // resident CTAs per SM the register allocation is tuned for
 #endif
@@ -305,88 +308,99 @@ __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_pa
     if (__all_sync(FULL, pix == PIX_DONE)) break;
     const bool active = pix >= 0;
 
-    // ---- (2) trace the lane's current ray (path segment or sun shadow ray)
-    Hit h;
-    h.closest = VRT_INF, h.hit_light = 0, h.mat_id = 0, h.kind = 0, h.nx = h.ny = h.nz = 0.0f, h.albedo = mk3(1.0f);
-    if (active) h = next_hit<STATS>(P, upper, unorm8, pos, d, state == ST_SHADOW, &tc, &c_hits);
-
-    // ---- (3) classify
+    // ---- (2)+(3) up to two trace passes per iteration through ONE copy of the traversal code: pass 0
+    // traces every live lane's current ray, pass 1 the sun shadow rays that pass 0 spawned. The
+    // stages around the passes (retire, refill, restart, sky site, shade) cost the same whether
+    // few or many lanes need them, so a path vertex should take one outer iteration, not two.
     bool do_shade = false, escaped = false, sky_need = false;
     float visible = 0.0f;
     f3 light_dir = d, sky_dir = d;
-    if (active) {
-      if (state == ST_SEGMENT) {
-        const uint32_t base = 8u * (uint32_t)depth;
-        if (MOVING) {  // pathtracer.py:402-412
-          if (depth == 0) {
-            primary_pos = pos + h.closest * d;
-            primary_albedo = h.albedo;
-            pm_info = encode_material(h.mat_id, h.albedo);
-            float ex = 0.0f, ey = 0.0f;
-            if (h.closest < VRT_INF) encode_unit_vector_3x16(f3{h.nx, h.ny, h.nz}, ex, ey);
-            primary_noct = h16bits(ex) | (h16bits(ey) << 16);
-          } else if (depth == 1 && f_lobe != LOBE_DIFFUSE) {
-            refl_dist += h.closest;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const bool tracing = active && (pass == 0 || state == ST_SHADOW);
+      // pass 1 only pays when enough lanes have a fresh shadow ray: below the threshold the rays wait
+      // (state stays ST_SHADOW) and are traced by pass 0 of the next iteration together with the segments
+      if (pass == 1 && __popc(__ballot_sync(FULL, tracing)) < VRT_PASS1_MIN_LANES) break;
+      Hit h;
+      h.closest = VRT_INF, h.hit_light = 0, h.mat_id = 0, h.kind = 0, h.nx = h.ny = h.nz = 0.0f, h.albedo = mk3(1.0f);
+      if (tracing) h = next_hit<STATS>(P, upper, unorm8, pos, d, state == ST_SHADOW, &tc, &c_hits);
+
+      // ---- (3) classify
+      if (tracing) {
+        if (state == ST_SEGMENT) {
+          const uint32_t base = 8u * (uint32_t)depth;
+          if (MOVING) {  // pathtracer.py:402-412
+            if (depth == 0) {
+              primary_pos = pos + h.closest * d;
+              primary_albedo = h.albedo;
+              pm_info = encode_material(h.mat_id, h.albedo);
+              float ex = 0.0f, ey = 0.0f;
+              if (h.closest < VRT_INF) encode_unit_vector_3x16(f3{h.nx, h.ny, h.nz}, ex, ey);
+              primary_noct = h16bits(ex) | (h16bits(ey) << 16);
+            } else if (depth == 1 && f_lobe != LOBE_DIFFUSE) {
+              refl_dist += h.closest;
+            }
           }
-        }
-        if (RESTIR) {  // pathtracer.py:402-417
-          const f3 hit_pos = pos + h.closest * d;
-          if (depth == 0) {
-            primary_pos = hit_pos;
-            pm_info = encode_material(h.mat_id, h.albedo);
-            float ex = 0.0f, ey = 0.0f;
-            if (h.closest < VRT_INF) encode_unit_vector_3x16(f3{h.nx, h.ny, h.nz}, ex, ey);
-            primary_noct = h16bits(ex) | (h16bits(ey) << 16);
-          } else if (depth == 1) {
-            rz.rc_pos = hit_pos;
-            rz.rc_normal = f3{h.nx, h.ny, h.nz};
-            rz.rc_mat_info = encode_material(h.mat_id, h.albedo);
-            f_bounce_light_pdf = cone_sample_pdf(P.light_cos_max, dot(P.light_dir, d));
-          } else if (depth == 2) {
-            rz.rc_incident_dir = d;
+          if (RESTIR) {  // pathtracer.py:402-417
+            const f3 hit_pos = pos + h.closest * d;
+            if (depth == 0) {
+              primary_pos = hit_pos;
+              pm_info = encode_material(h.mat_id, h.albedo);
+              float ex = 0.0f, ey = 0.0f;
+              if (h.closest < VRT_INF) encode_unit_vector_3x16(f3{h.nx, h.ny, h.nz}, ex, ey);
+              primary_noct = h16bits(ex) | (h16bits(ey) << 16);
+            } else if (depth == 1) {
+              rz.rc_pos = hit_pos;
+              rz.rc_normal = f3{h.nx, h.ny, h.nz};
+              rz.rc_mat_info = encode_material(h.mat_id, h.albedo);
+              f_bounce_light_pdf = cone_sample_pdf(P.light_cos_max, dot(P.light_dir, d));
+            } else if (depth == 2) {
+              rz.rc_incident_dir = d;
+            }
           }
-        }
-        if (h.closest == VRT_INF) {
-          // escaped: background or sky tables + sun disk (pathtracer.py:499-511); the table
-          // lookup happens at the merged sky site (3b) below
-          escaped = true;
-          if (P.use_sky) {
-            sky_dir = normalize(d + f3{rnd(key, base + 5), rnd(key, base + 6), rnd(key, base + 7)} * 0.0015f);
-            sky_need = true;
-            if (STATS) c_escapes++;
-          }
-          finished = true;
-        } else if (h.hit_light) {
-          // emissive voxel / floor terminates the path (pathtracer.py:519-525)
-          if (depth > 0) contrib += thr * h.albedo;
-          if (depth == 0) pm_info = encode_material(h.mat_id, h.albedo);
-          if (RESTIR && depth >= 2) rz.rc_incident_L += firefly_filter(thr_after_rc * h.albedo);
-          finished = true;
-        } else {
-          if (STATS) c_vertices++;
-          s_n = f3{h.nx, h.ny, h.nz};
-          s_alb = h.albedo;
-          s_mat = h.mat_id;
-          s_view = -d;
-          pos = (pos + h.closest * d) + s_n * VRT_EPS;
-          light_dir = sample_cone_oriented(P.light_cos_max, P.light_dir, sun_bx, sun_by, rnd(key, base + 0), rnd(key, base + 1));
-          if (dot(light_dir, s_n) > 0.0f) {
-            d = light_dir;
-            state = ST_SHADOW;
+          if (h.closest == VRT_INF) {
+            // escaped: background or sky tables + sun disk (pathtracer.py:499-511); the table
+            // lookup happens at the merged sky site (3b) below
+            escaped = true;
+            if (P.use_sky) {
+              sky_dir = normalize(d + f3{rnd(key, base + 5), rnd(key, base + 6), rnd(key, base + 7)} * 0.0015f);
+              sky_need = true;
+              if (STATS) c_escapes++;
+            }
+            finished = true;
+          } else if (h.hit_light) {
+            // emissive voxel / floor terminates the path (pathtracer.py:519-525)
+            if (depth > 0) contrib += thr * h.albedo;
+            if (depth == 0) pm_info = encode_material(h.mat_id, h.albedo);
+            if (RESTIR && depth >= 2) rz.rc_incident_L += firefly_filter(thr_after_rc * h.albedo);
+            finished = true;
           } else {
-            do_shade = true;
+            if (STATS) c_vertices++;
+            s_n = f3{h.nx, h.ny, h.nz};
+            s_alb = h.albedo;
+            s_mat = h.mat_id;
+            s_view = -d;
+            pos = (pos + h.closest * d) + s_n * VRT_EPS;
+            light_dir = sample_cone_oriented(P.light_cos_max, P.light_dir, sun_bx, sun_by, rnd(key, base + 0), rnd(key, base + 1));
+            if (dot(light_dir, s_n) > 0.0f) {
+              d = light_dir;
+              state = ST_SHADOW;
+            } else {
+              do_shade = true;
+            }
           }
-        }
-      } else {
-        visible = h.closest >= VRT_INF ? 1.0f : 0.0f;
-        state = ST_SEGMENT;
-        do_shade = true;
-        if (visible != 0.0f && P.use_sky) {
-          sky_need = true;  // sky_dir == d == the sun sample the shadow ray was traced along
-          if (STATS) c_nee++;
+        } else {
+          visible = h.closest >= VRT_INF ? 1.0f : 0.0f;
+          state = ST_SEGMENT;
+          do_shade = true;
+          if (visible != 0.0f && P.use_sky) {
+            sky_need = true;
+            sky_dir = d;  // the sun sample the shadow ray was traced along
+            if (STATS) c_nee++;
+          }
         }
       }
-    }
+    }  // trace passes
 
     // ---- (3b) merged sky site: one projection + bilinear footprint per lane for both users of
     // the tables, escaped segments (scattering + transmittance, atmos.py:94-115) and visible sun
