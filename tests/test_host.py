@@ -159,3 +159,25 @@ def test_reference_examples_run_unchanged_through_the_shim(example, occupied):
     finally:
         S.Scene.__init__, S.save_image = orig, save
     assert int((g["scene"].voxel_material > 0).sum()) == occupied
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """bench.py --impl reference (CPU oracle arm) on a tiny configuration: stdout is exactly one JSON
+    line carrying the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--res", "64x32",
+                        "--grid", "32", "--sky-res", "16"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in j, k
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0

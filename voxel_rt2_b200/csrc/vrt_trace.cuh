@@ -16,10 +16,6 @@
 #pragma once
 #include "vrt_common.cuh"
 
-#ifndef VRT_OPT_DDA
-#define VRT_OPT_DDA 1
-#endif
-
 struct RayHit {
   float t;  // voxel units, +inf on miss
   int cx, cy, cz;
@@ -86,7 +82,6 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
   int py = (int)clampf(floorf(ipy), 0.0f, Rf - 1.0f);
   int pz = (int)clampf(floorf(ipz), 0.0f, Rf - 1.0f);
   const float ivx = __frcp_rn(fabsf(d.x)), ivy = __frcp_rn(fabsf(d.y)), ivz = __frcp_rn(fabsf(d.z));  // == 1.0f / |d|, correctly rounded
-  const float sgx = signf(d.x), sgy = signf(d.y), sgz = signf(d.z);
   int lod = 0;
   const float far = xsub(fminf(VRT_INF, far_int), VRT_EPS);
   {
@@ -123,7 +118,6 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
         w = __ldg(P.bricks + b);
         last_b = b;
       }
-#if VRT_OPT_DDA
       // LOD 2 / 1 / 0 all come from the one brick word: e2 => e1 => e0 (an empty 4^3 block has empty
       // 2^3 sub-blocks and voxels), so "descend from `lod` while occupied" is the first empty level
       // at or below `lod`: min(lod, coarsest empty level); a hit iff the voxel bit is set.
@@ -135,39 +129,13 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
       if (STATS) tc->queries += e0 ? lod - min(lod, first_empty) + 1 : lod + 1;
       lod = min(lod, first_empty);
       occ = !e0;
-#else
-      if (lod == 2) {
-        if (STATS) tc->queries++;
-        if (w == 0ull)
-          occ = false;
-        else
-          lod = 1;
-      }
-      if (occ && lod == 1) {
-        if (STATS) tc->queries++;
-        int sh = ((px >> 1) & 1) * 2 + ((py >> 1) & 1) * 8 + ((pz >> 1) & 1) * 32;
-        if ((w & (0x0000000000330033ull << sh)) == 0ull)
-          occ = false;
-        else
-          lod = 0;
-      }
-      if (occ && lod == 0) {
-        if (STATS) tc->queries++;
-        occ = (w >> ((pz & 3) * 16 + (py & 3) * 4 + (px & 3))) & 1ull;
-      }
-#endif
     }
     if (occ) break;
     // --- step to the exit face of the empty LOD-`lod` cell (raytracer.py:124-147)
     const float cell_size = (float)(1 << lod);
-#if VRT_OPT_DDA
     // (px >> lod) * 2^lod == px with the low `lod` bits cleared: same float, no multiply
     const int cmask = -(1 << lod);
     const float bx = (float)(px & cmask), by = (float)(py & cmask), bz = (float)(pz & cmask);
-#else
-    const int cxi = px >> lod, cyi = py >> lod, czi = pz >> lod;
-    const float bx = xmul((float)cxi, cell_size), by = xmul((float)cyi, cell_size), bz = xmul((float)czi, cell_size);
-#endif
     const float fx = xsub(xadd(o.x, xmul(d.x, hit_distance)), bx);
     const float fy = xsub(xadd(o.y, xmul(d.y, hit_distance)), by);
     const float fz = xsub(xadd(o.z, xmul(d.z, hit_distance)), bz);
@@ -182,17 +150,11 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
     const float ey = clampf(floorf(xadd(fy, xmul(min_t, d.y))), 0.0f, cell_size - 1.0f);
     const float ez = clampf(floorf(xadd(fz, xmul(min_t, d.z))), 0.0f, cell_size - 1.0f);
     hit_distance = xadd(hit_distance, min_t);
-#if VRT_OPT_DDA
     // (t == min_t ? 1 : 0) * sign(d): for d != 0 the product is 1 or 0 carrying d's sign bit; an
     // axis with d == +-0 has t = +inf, never the minimum, and the reference product is +0.
     h.nx = __uint_as_float((tx == min_t ? 0x3f800000u : 0u) | (d.x < 0.0f ? 0x80000000u : 0u));
     h.ny = __uint_as_float((ty == min_t ? 0x3f800000u : 0u) | (d.y < 0.0f ? 0x80000000u : 0u));
     h.nz = __uint_as_float((tz == min_t ? 0x3f800000u : 0u) | (d.z < 0.0f ? 0x80000000u : 0u));
-#else
-    h.nx = (tx == min_t ? 1.0f : 0.0f) * sgx;
-    h.ny = (ty == min_t ? 1.0f : 0.0f) * sgy;
-    h.nz = (tz == min_t ? 1.0f : 0.0f) * sgz;
-#endif
     px = (int)(bx + ex + h.nx);
     py = (int)(by + ey + h.ny);
     pz = (int)(bz + ez + h.nz);
