@@ -239,7 +239,9 @@ HD Hit next_hit(const Params& P, const uint32_t* __restrict__ upper, const float
       int mat = 0;
       if ((unsigned)r.cx < (unsigned)P.R && (unsigned)r.cy < (unsigned)P.R && (unsigned)r.cz < (unsigned)P.R) {
         int b = ((r.cz >> 2) * P.brick_res + (r.cy >> 2)) * P.brick_res + (r.cx >> 2);
-        uint32_t c = __ldg(P.color + (size_t)b * 64 + ((r.cz & 3) * 16 + (r.cy & 3) * 4 + (r.cx & 3)));
+        // one texel per surface hit out of 8-64 MB: bypass L1 allocation so the occupancy bricks stay resident
+        uint32_t c;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(c) : "l"(P.color + (size_t)b * 64 + ((r.cz & 3) * 16 + (r.cy & 3) * 4 + (r.cx & 3))));
         col = f3{unorm8[c & 255u], unorm8[(c >> 8) & 255u], unorm8[(c >> 16) & 255u]};  // k / 255.0f, correctly rounded
         mat = (int)(c >> 24);
         if (STATS) (*n_hits)++;
