@@ -465,6 +465,81 @@ def section_frame():
     np.savez_compressed(os.path.join(HERE, "ref_frame.npz"), **out)
 
 
+# ------------------------------------------------------------ moving-camera temporal path
+class _SnapshotReads:
+    """Field proxy: reads see the array as it was when the proxy was made, writes go to the field.
+    Used for gbuff_depth_reflection during temporal_filter_prepass, which blurs that buffer in place
+    while neighbouring threads still read it (pathtracer.py:1055,1066): the emulator would serialise
+    the race in loop order; the snapshot is the "all reads before any write" outcome the oracle pins."""
+
+    def __init__(self, field):
+        self.f, self.snap = field, field.arr.copy()
+
+    def __getitem__(self, k):
+        return self.snap[self.f._key(k)]
+
+    def __setitem__(self, k, v):
+        self.f[k] = v
+
+
+def section_moving():
+    """Scene.finish's moving-camera loop (scene.py:214-262) for 4 frames of a camera translation:
+    render at render_scale 0.5 with albedo demodulation, temporal_filter_prepass, temporal_filter and
+    temporal_filter_specular with reprojection / Catmull-Rom history / depth + normal rejection
+    (pathtracer.py:993-1303), copy_prev_matrices. Stored: color_buffer after every frame.
+    Two upstream hazards are resolved the way the oracle / CUDA pin them (DESIGN.md "Moving-camera
+    pins"), otherwise the comparison would measure the hazards, not the filters: (1) the prepass
+    blurs gbuff_depth_reflection in place while neighbours read it — reads see a snapshot; (2) a
+    glossy first bounce that escapes leaves an infinite reflection distance, whose NaN depth the 4x4
+    blur spreads and which resets the specular history of every pixel it reaches — non-finite
+    reflection depths are zeroed ("no reflection") after render()."""
+    sys.path.insert(0, ROOT)
+    from voxel_rt2_b200.camera import default_camera_matrices
+
+    W, H, R, seed, n_frames, scale = 64, 32, 32, 321, 4, 0.5
+    cfg = dict(voxel_edges=0.06, light_dir=(0.7, 0.9, 0.5), light_cone=0.05, light_color=(1.2, 1.1, 1.0), floor_height=-0.45,
+               floor_color=(0.9, 0.9, 0.9), floor_material=1, background=(0.2, 0.3, 0.5))
+    mat, col = render_scene(R, 12)
+    r = make_reference_renderer(W, H, R, mat, col, cfg)
+    for f in (r.color_buffer, r.color_buffer_specular):
+        f.oob_zero = True
+    r.set_max_samples(50.0)
+    r.set_render_scale(scale)
+    r.set_camera_is_moving(True)
+    r.reset_framebuffer()
+    state = {"sample": 0, "count": {}}
+    cams, frames, bad_total = [], [], 0
+    tex = r.world.voxel_color_texture
+    for fidx in range(n_frames):
+        pos, view, proj = default_camera_matrices(W, H, pos=(0.9 - 0.06 * fidx, 0.8 + 0.02 * fidx, 1.9 - 0.03 * fidx))
+        set_reference_camera(r, pos, view, proj)
+        if fidx == 0:
+            r.copy_prev_matrices()  # the first moving frame reprojects into the same camera
+        state["sample"], state["count"] = fidx, {}
+        ti.set_random_source(path_random_source(W, seed, state), with_frame=True)
+        r.render(tex)                                   # Renderer.accumulate (pathtracer.py:1310-1319), kernel by kernel
+        ti.set_random_source(None)
+        real = r.gbuff_depth_reflection
+        n_bad = int((~np.isfinite(real.arr)).sum())
+        real.arr[~np.isfinite(real.arr)] = 0.0          # see the docstring: non-finite reflection depth = no reflection
+        bad_total += n_bad
+        r.gbuff_depth_reflection = _SnapshotReads(real)
+        r.temporal_filter_prepass()
+        r.gbuff_depth_reflection = real
+        r.temporal_filter()
+        r.temporal_filter_specular()
+        r.copy_prev_matrices()
+        cams.append((pos, view, proj))
+        frames.append(np.transpose(r.color_buffer.arr, (1, 0, 2)).copy())
+        print("moving frame %d: mean %.4f, %d non-finite reflection depths zeroed" % (fidx, float(frames[-1][: H // 2, : W // 2].mean()), n_bad))
+    out = dict(material=mat, color=col, seed=np.int32(seed), W=np.int32(W), H=np.int32(H), scale=np.float32(scale), max_accum=np.float32(50.0),
+               cam_pos=np.array([c[0] for c in cams]), view=np.array([c[1] for c in cams]), proj=np.array([c[2] for c in cams]),
+               frames=np.array(frames))
+    for k, v in cfg.items():
+        out["cfg_" + k] = np.asarray(v, np.float32)
+    np.savez_compressed(os.path.join(HERE, "ref_moving.npz"), **out)
+
+
 # ------------------------------------------------ BASELINE config 1: example1 hit buffer
 def section_example1():
     """BASELINE.json configs[0] at reduced resolution: the example1.py scene (shim seed 0, the committed
@@ -706,7 +781,7 @@ def section_sky():
 
 
 SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render, "frame": section_frame,
-            "shift": section_shift, "example1": section_example1, "sky": section_sky}
+            "shift": section_shift, "moving": section_moving, "example1": section_example1, "sky": section_sky}
 
 if __name__ == "__main__":
     for s in (sys.argv[1:] or list(SECTIONS)):

@@ -645,3 +645,27 @@ def test_cuda_config1_example1_hit_buffer_matches_reference_source(vrt):
 
     g, h = example1_renderer(vrt.Renderer)
     assert_hits_equal_reference(g.trace_primary(), h)
+
+
+def test_cuda_moving_camera_path_matches_reference_source_vectors(vrt):
+    """vrt_accumulate_moving against the reference's own moving-camera loop (4 frames,
+    tests/golden/ref_moving.npz; hazards resolved as in DESIGN.md "Moving-camera pins")."""
+    import os
+
+    from util import renderer_from_reference_fixture
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_moving.npz"))
+    W, H = int(z["W"]), int(z["H"])
+    zz = dict(z)
+    zz["cam_pos"], zz["view"], zz["proj"] = z["cam_pos"][0], z["view"][0], z["proj"][0]
+    g = renderer_from_reference_fixture(vrt.Renderer, zz)
+    g.prepare_data()
+    for f in range(z["frames"].shape[0]):
+        g.set_view_proj(z["cam_pos"][f], z["view"][f], z["proj"][f])
+        g.accumulate_moving(float(z["scale"]), float(z["max_accum"]))
+        a = g.fetch_hdr_moving()[::2, ::2, :3][: H // 2, : W // 2]
+        b = z["frames"][f][: H // 2, : W // 2]
+        err = np.abs(a - b).max(-1) / np.maximum(np.abs(b).max(-1), 1e-3)
+        print("frame %d: within 2e-3 on %.4f of the pixels, worst %.3e" % (f, np.mean(err <= 2e-3), err.max()))
+        assert np.mean(err <= 2e-3) >= 0.97
+        assert abs(a.mean() - b.mean()) <= 5e-3 * b.mean()
