@@ -138,7 +138,7 @@ HD void load_reservoir(const uint2* __restrict__ base, size_t pidx, const float*
 }
 
 #ifndef VRT_GRIS_MIN_BLOCKS
-#define VRT_GRIS_MIN_BLOCKS 2
+#define VRT_GRIS_MIN_BLOCKS 4  // 128 registers, 200 B of spills: measured 3.6 % faster than 2 or 3 blocks
 #endif
 __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int upper_in_smem, int fixed_words) {
   extern __shared__ uint32_t smem[];
