@@ -4,7 +4,15 @@
 //   k_path     fused bounce / shade / NEE path kernel: persistent warps, per-lane path
 //              regeneration from a warp-local tile queue, segment and shadow rays of different
 //              lanes traced by one shared traversal loop (renderer/pathtracer.py:355-632,
-//              non-ReSTIR estimator, static camera; accumulation :1185-1303 reduced to a sum)
+//              non-ReSTIR estimator, static camera; accumulation :1185-1303 reduced to a sum).
+//              Shape of one outer iteration (every stage is issued once per iteration whatever
+//              the number of lanes that need it, so the design goal is few iterations per path
+//              and a main loop that fits the SM's instruction cache):
+//                (0) retire finished paths   (1) refill idle lanes, start paths
+//                (2) trace pass 0: every lane's current ray; classify (escape / emissive / surface)
+//                    trace pass 1: the shadow rays spawned by pass 0, if >= 12 lanes have one
+//                (3b) ONE sky-table site for escaped segments and visible sun samples
+//                (4) shade: NEE term + BSDF sample (rare lobes in out-of-line functions)
 //   k_resolve  mean + vignette + exposure + Uchimura + gamma (renderer/pathtracer.py:634-662,
 //              renderer/math_utils.py:160-186), float4 in / float4 out
 #include "vrt_bsdf.cuh"
