@@ -112,6 +112,12 @@ int vrt_prepare(vrt_ctx* ctx);
  * set: install externally computed tables (skips the precompute in vrt_prepare). */
 int vrt_get_sky_tables(vrt_ctx* ctx, float* scattering, float* transmittance);
 int vrt_set_sky_tables(vrt_ctx* ctx, const float* scattering, const float* transmittance);
+/* Compact sky tables (no counterpart upstream, whose tables are f32 only,
+ * atmos.py:68-69): format 0 (default) keeps the two float tables; format 1 packs both into ONE table
+ * of 16-byte texels {scattering rgb, transmittance rgb} as binary16 (236 MB instead of 2 x 236 MB at
+ * 3840^2; relative texel error <= 2^-11). Applies to the static-camera path kernel (vrt_accumulate);
+ * the ReSTIR and moving-camera modes and vrt_get_sky_tables keep reading the float tables. */
+int vrt_set_sky_format(vrt_ctx* ctx, int32_t format);
 /* Atmos.trans_LUT (atmos.py:63): binary16 bits [256][128][3] */
 int vrt_get_trans_lut(vrt_ctx* ctx, uint16_t* lut);
 

@@ -669,3 +669,36 @@ def test_cuda_moving_camera_path_matches_reference_source_vectors(vrt):
         print("frame %d: within 2e-3 on %.4f of the pixels, worst %.3e" % (f, np.mean(err <= 2e-3), err.max()))
         assert np.mean(err <= 2e-3) >= 0.97
         assert abs(a.mean() - b.mean()) <= 5e-3 * b.mean()
+
+
+def test_compact_sky_table_format_within_rmse_budget(vrt):
+    """the packed binary16 sky table (vrt_set_sky_format 1) against the float tables on the
+    same samples: per-pixel radiance within 2e-3 on >= 99 % of the pixels and rel-RMSE <= 1e-3 (texel
+    error of binary16 <= 2^-11); without the physical sky the format changes nothing."""
+    R = 64
+    scene = scenes.random_grid(R, 0.5, 1234)
+    light = ((1, 1, 1), 0.025, (1.3, 0.949 * 1.3, 0.937 * 1.3))
+    imgs = {}
+    for fmt in ("f32", "f16"):
+        g = vrt.Renderer(dx=2.0 / R, image_res=(128, 96), grid_res=R, sky_res=64, cloud_passes=2, seed=3, sky_format=fmt)
+        g.set_voxels(*scene)
+        g.set_floor(-1e5, (1, 1, 1))
+        g.set_directional_light(*light)
+        g.set_use_physical_sky(True, True)
+        g.prepare_data()
+        g.accumulate(16)
+        imgs[fmt] = g.fetch_hdr()[..., :3]
+        if fmt == "f16":  # a sun change invalidates and rebuilds the packed table
+            g.set_directional_light((0.2, 1, 0.4), 0.025, light[2])
+            g.prepare_data()
+            g.reset_framebuffer()
+            g.accumulate(4)
+            other = g.fetch_hdr()[..., :3]
+            assert np.isfinite(other).all() and abs(other.mean() / imgs[fmt].mean() - 1.0) > 0.01
+    a, b = imgs["f16"], imgs["f32"]
+    err = np.abs(a - b).max(-1) / np.maximum(np.abs(b).max(-1), 1e-3)
+    print("f16 sky tables: within 2e-3 on %.4f of the pixels, rel-RMSE %.2e" % (np.mean(err <= 2e-3), rel_rmse(a, b)))
+    assert np.mean(err <= 2e-3) >= 0.99 and rel_rmse(a, b) <= 1e-3
+    assert not np.array_equal(a, b)
+    g0 = vrt.Renderer(dx=2.0 / R, image_res=(64, 64), grid_res=R, sky_res=0)  # no sky tables: format 1 is refused, 2 is unknown
+    assert g0._lib.vrt_set_sky_format(g0._h, 1) != 0 and g0._lib.vrt_set_sky_format(g0._h, 2) != 0 and g0._lib.vrt_set_sky_format(g0._h, 0) == 0

@@ -41,6 +41,9 @@ struct vrt_ctx {
   float4* d_mats = nullptr;
   float4* d_sky_scatter = nullptr;
   float4* d_sky_trans = nullptr;
+  uint4* d_sky_packed = nullptr;  // format 1 (vrt_set_sky_format), built from the float tables
+  int sky_format = 0;
+  bool sky_packed_valid = false;
   __half* d_trans_lut = nullptr;
   uint8_t* d_cloud_tex = nullptr;
   float* d_cloud_ambient = nullptr;
@@ -188,6 +191,7 @@ static void fill_params(const vrt_ctx* ctx, Params& P) {
   P.W = c.width, P.H = c.height;
   P.inv_w = 1.0f / (float)c.width, P.inv_h = 1.0f / (float)c.height;
   P.sky_scatter = ctx->d_sky_scatter, P.sky_trans = ctx->d_sky_trans, P.sky_res = c.sky_res;
+  P.sky_packed = (ctx->sky_format == 1 && ctx->sky_packed_valid) ? ctx->d_sky_packed : nullptr;
   P.mats = ctx->d_mats;
   P.accum = ctx->d_accum;
   P.seed = c.seed;
@@ -209,7 +213,7 @@ void vrt_destroy(vrt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_mat), cudaFree(ctx->d_rgb), cudaFree(ctx->d_bricks), cudaFree(ctx->d_color), cudaFree(ctx->d_upper);
-  cudaFree(ctx->d_mats), cudaFree(ctx->d_sky_scatter), cudaFree(ctx->d_sky_trans), cudaFree(ctx->d_trans_lut);
+  cudaFree(ctx->d_mats), cudaFree(ctx->d_sky_scatter), cudaFree(ctx->d_sky_trans), cudaFree(ctx->d_sky_packed), cudaFree(ctx->d_trans_lut);
   cudaFree(ctx->d_cloud_tex), cudaFree(ctx->d_cloud_ambient), cudaFree(ctx->d_accum), cudaFree(ctx->d_out), cudaFree(ctx->d_hits);
   cudaFree(ctx->d_jitter), cudaFree(ctx->d_work), cudaFree(ctx->d_stats);
   cudaFree(ctx->mv.col_d), cudaFree(ctx->mv.col_s), cudaFree(ctx->mv.out), cudaFree(ctx->mv.full), cudaFree(ctx->mv.refl), cudaFree(ctx->mv.refl_blur);
@@ -373,6 +377,7 @@ int vrt_set_light(vrt_ctx* ctx, const float direction[3], float cone_angle, cons
   ctx->light_cos_max = (float)std::cos((double)cone_angle * 0.5);
   memcpy(ctx->light_color, rgb, sizeof ctx->light_color);
   ctx->sky_valid = false;  // the sky tables depend on the sun
+  ctx->sky_packed_valid = false;
   return VRT_OK;
 }
 
@@ -423,6 +428,8 @@ int vrt_set_cloud_texture(vrt_ctx* ctx, const uint8_t* tex) {
   return VRT_OK;
 }
 
+static int sync_packed_sky(vrt_ctx* ctx);
+
 int vrt_prepare(vrt_ctx* ctx) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   if (!ctx->voxels_uploaded) {
@@ -451,7 +458,9 @@ int vrt_prepare(vrt_ctx* ctx) {
     CK(cudaEventElapsedTime(&ctx->stats.sky_precompute_ms, ctx->ev0, ctx->ev1));
     ctx->sky_valid = true;
     ctx->lut_valid = true;
+    ctx->sky_packed_valid = false;
   }
+  if (int rc = sync_packed_sky(ctx)) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->prepared = true;
   return VRT_OK;
@@ -490,7 +499,27 @@ int vrt_set_sky_tables(vrt_ctx* ctx, const float* scattering, const float* trans
     CK(cudaStreamSynchronize(ctx->stream));
   }
   ctx->sky_valid = true;
+  ctx->sky_packed_valid = false;
+  return sync_packed_sky(ctx);
+}
+
+// (Re)build the packed table whenever the float tables changed and format 1 is selected.
+static int sync_packed_sky(vrt_ctx* ctx) {
+  if (ctx->sky_format != 1 || !ctx->sky_valid || ctx->sky_packed_valid) return VRT_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t ns = (size_t)ctx->cfg.sky_res * ctx->cfg.sky_res;
+  if (!ctx->d_sky_packed) CK(cudaMalloc(&ctx->d_sky_packed, ns * sizeof(uint4)));
+  CK(vrt_launch_pack_sky(ctx->d_sky_scatter, ctx->d_sky_trans, ctx->d_sky_packed, ns, ctx->stream));
+  ctx->sky_packed_valid = true;
   return VRT_OK;
+}
+
+int vrt_set_sky_format(vrt_ctx* ctx, int32_t format) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(format == 0 || format == 1, "vrt_set_sky_format: format must be 0 (float tables) or 1 (packed binary16)");
+  REQUIRE(format == 0 || ctx->cfg.sky_res > 0, "vrt_set_sky_format: context was created with sky_res = 0");
+  ctx->sky_format = format;
+  return sync_packed_sky(ctx);
 }
 
 int vrt_get_trans_lut(vrt_ctx* ctx, uint16_t* lut) {

@@ -159,6 +159,7 @@ struct Params {
   // sky tables, float4 texels, [x][y] with y fastest
   const float4* sky_scatter;
   const float4* sky_trans;
+  const uint4* sky_packed;  // format 1: {scatter rgb, trans rgb, -, -} as 8 x binary16 per texel, or nullptr
   int sky_res;
   // materials
   const float4* mats;

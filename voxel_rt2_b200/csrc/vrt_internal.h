@@ -18,6 +18,7 @@ cudaError_t vrt_launch_path_moving(const Params& P, const MovingOut& MO, int sm_
 cudaError_t vrt_launch_moving_filters(const Params& P, const MovingFrame& F, float max_accum, cudaStream_t st);
 cudaError_t vrt_launch_moving_upsample(const float4* out, float4* full, int W, int H, float scale, cudaStream_t st);
 size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem);
+cudaError_t vrt_launch_pack_sky(const float4* scatter, const float4* trans, uint4* out, size_t n, cudaStream_t st);
 // vrt_restir.cu — spatial_GRIS (pathtracer.py:815-989); adds the frame's colour into P.accum
 cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t frame, cudaStream_t st);
 cudaError_t vrt_launch_resolve_merged(const float4* accum, const float4* const* peers, int n_peers, float4* ldr, int W, int H, float exposure,

@@ -110,7 +110,7 @@ enum { PIX_IDLE = -1, PIX_DONE = -2 };
 // render_scale into the lower-left corner, the diffuse part is divided by the primary albedo, and
 // the G-buffer the reprojecting temporal filters need (NDC depth, octahedral normal, material,
 // virtual reflection depth; pathtracer.py:535-546) is written next to the two colour buffers.
-template <bool STATS, int MODE>
+template <bool STATS, int MODE, bool SKY16 = false>
 __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem, RestirBuffers RB, MovingOut MO) {
   constexpr bool RESTIR = MODE == 1;
   constexpr bool MOVING = MODE == 2;
@@ -417,8 +417,14 @@ __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_pa
     f3 sky_T = mk3(1.0f), sky_scattering = P.background;
     if (sky_need) {
       const SkyTap t = sky_tap(P.sky_res, project_sky(sky_dir, sky_fres));
-      sky_T = sky_fetch(P.sky_trans, t);
-      if (escaped) sky_scattering = sky_fetch(P.sky_scatter, t);
+      if (SKY16) {
+        f3 sc;
+        sky_fetch_packed(P.sky_packed, t, sc, sky_T);
+        if (escaped) sky_scattering = sc;
+      } else {
+        sky_T = sky_fetch(P.sky_trans, t);
+        if (escaped) sky_scattering = sky_fetch(P.sky_scatter, t);
+      }
     }
     if (escaped) {
       const float hit_sun = dot(P.light_dir, d) >= P.light_cos_max ? 1.0f : 0.0f;
@@ -591,26 +597,28 @@ cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <bool STATS, int MODE>
+template <bool STATS, int MODE, bool SKY16 = false>
 static cudaError_t launch_path_t(const Params& P, int sm_count, cudaStream_t st, int* blocks_out, const RestirBuffers& RB, const MovingOut& MO) {
   int uis;
   size_t sm = smem_bytes(P, &uis);
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<STATS, MODE>, 128, sm);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<STATS, MODE, SKY16>, 128, sm);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   int blocks = sm_count * per_sm;  // persistent: one wave, a multiple of the SM count
   int max_useful = (P.n_tiles + 3) / 4;
   if (blocks > max_useful) blocks = max_useful > 0 ? max_useful : 1;
   if (blocks_out) *blocks_out = blocks;
-  k_path<STATS, MODE><<<blocks, 128, sm, st>>>(P, uis, RB, MO);
+  k_path<STATS, MODE, SKY16><<<blocks, 128, sm, st>>>(P, uis, RB, MO);
   return cudaGetLastError();
 }
 
 cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out) {
   RestirBuffers none{nullptr, nullptr, nullptr, nullptr, nullptr};
   MovingOut mo{nullptr, nullptr, nullptr, nullptr, nullptr, 1.0f};
-  return stats ? launch_path_t<true, 0>(P, sm_count, st, blocks_out, none, mo) : launch_path_t<false, 0>(P, sm_count, st, blocks_out, none, mo);
+  if (stats) return launch_path_t<true, 0>(P, sm_count, st, blocks_out, none, mo);  // the counting build reads the float tables
+  if (P.sky_packed && P.use_sky) return launch_path_t<false, 0, true>(P, sm_count, st, blocks_out, none, mo);
+  return launch_path_t<false, 0>(P, sm_count, st, blocks_out, none, mo);
 }
 
 cudaError_t vrt_launch_path_restir(const Params& P, const RestirBuffers& RB, int sm_count, cudaStream_t st) {
@@ -621,6 +629,21 @@ cudaError_t vrt_launch_path_restir(const Params& P, const RestirBuffers& RB, int
 cudaError_t vrt_launch_path_moving(const Params& P, const MovingOut& MO, int sm_count, cudaStream_t st) {
   RestirBuffers none{nullptr, nullptr, nullptr, nullptr, nullptr};
   return launch_path_t<false, 2>(P, sm_count, st, nullptr, none, MO);
+}
+
+// float tables -> one packed binary16 table (format 1 of vrt_set_sky_format)
+__global__ void __launch_bounds__(256) k_pack_sky(const float4* __restrict__ scatter, const float4* __restrict__ trans, uint4* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 s = scatter[i], t = trans[i];
+  const __half2 a = __floats2half2_rn(s.x, s.y), b = __floats2half2_rn(s.z, t.x), c = __floats2half2_rn(t.y, t.z);
+  uint4 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&a), o.y = *reinterpret_cast<const uint32_t*>(&b), o.z = *reinterpret_cast<const uint32_t*>(&c), o.w = 0u;
+  out[i] = o;
+}
+cudaError_t vrt_launch_pack_sky(const float4* scatter, const float4* trans, uint4* out, size_t n, cudaStream_t st) {
+  k_pack_sky<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scatter, trans, out, n);
+  return cudaGetLastError();
 }
 
 size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem) { return smem_bytes(P, upper_in_smem); }

@@ -2,6 +2,8 @@
 // and :428-455 (project_sky / unproject_sky). Tables are float4 texels [x][y] (y fastest), so a
 // bilinear footprint is two 32-byte pairs per table: (x, y..y+1) and (x+1, y..y+1).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "vrt_common.cuh"
 
 // Polynomial atan2 / acos (max abs error 1.7e-7 / 3.3e-7 rad = 1e-4 / 2e-4 sky texels at 3840^2;
@@ -85,4 +87,25 @@ HD f3 sky_fetch(const float4* __restrict__ tab, const SkyTap& t) {
   f3 a = mix3(f3{bl.x, bl.y, bl.z}, f3{br.x, br.y, br.z}, t.wx);
   f3 b = mix3(f3{tl.x, tl.y, tl.z}, f3{tr.x, tr.y, tr.z}, t.wx);
   return mix3(a, b, t.wy);
+}
+
+// Format-1 table: one 16-byte texel holds scattering and transmittance as binary16, so an escaped
+// segment needs 4 loads instead of 8 and a visible sun sample reads the same 4 texels.
+HD void sky_unpack(uint4 t, f3& sc, f3& tr) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y)),
+               c = __half22float2(*reinterpret_cast<const __half2*>(&t.z));
+  sc = f3{a.x, a.y, b.x};
+  tr = f3{b.y, c.x, c.y};
+}
+HD uint4 sky_ld_packed(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+HD void sky_fetch_packed(const uint4* __restrict__ tab, const SkyTap& t, f3& sc, f3& tr) {
+  const uint4 bl = sky_ld_packed(tab + t.i00), br = sky_ld_packed(tab + t.i10), tl = sky_ld_packed(tab + t.i01), trr = sky_ld_packed(tab + t.i11);
+  f3 s0, t0, s1, t1, s2, t2, s3, t3;
+  sky_unpack(bl, s0, t0), sky_unpack(br, s1, t1), sky_unpack(tl, s2, t2), sky_unpack(trr, s3, t3);
+  sc = mix3(mix3(s0, s1, t.wx), mix3(s2, s3, t.wx), t.wy);
+  tr = mix3(mix3(t0, t1, t.wx), mix3(t2, t3, t.wx), t.wy);
 }

@@ -37,7 +37,7 @@ class Renderer:
     cloud_passes (32, scene.py:199), device, seed, jitter (TAA jitter on/off)."""
 
     def __init__(self, dx=1 / 64, image_res=(1920, 1080), up=(0, 1, 0), voxel_edges=0.06, exposure=3, *,
-                 grid_res=128, max_depth=4, sky_res=3840, cloud_passes=32, device=0, seed=0, jitter=True):
+                 grid_res=128, max_depth=4, sky_res=3840, cloud_passes=32, device=0, seed=0, jitter=True, sky_format=None):
         self._lib = _cabi.load()
         self.image_res = (int(image_res[0]), int(image_res[1]))
         self.voxel_grid_res = int(grid_res)
@@ -60,6 +60,13 @@ class Renderer:
         if rc != 0:
             raise RuntimeError("vrt_create failed (%d): %s" % (rc, self._lib.vrt_last_error(None).decode()))
         self._h = h
+        # compact sky tables: "f32" (default, the reference's layout) or "f16" (one packed binary16
+        # table for the static-camera path kernel); VRT_SKY_FORMAT sets the default for scripts that cannot pass it
+        self.sky_format = (sky_format or os.environ.get("VRT_SKY_FORMAT", "f32")).lower()
+        if self.sky_format not in ("f32", "f16"):
+            raise ValueError("sky_format must be 'f32' or 'f16'")
+        if self.sky_format == "f16" and self.sky_res > 0:
+            self._check(self._lib.vrt_set_sky_format(self._h, 1))
         # reference defaults (pathtracer.py:89-93, scene.py:28-30,127)
         self.fov = math.radians(50.0)
         self._camera_pos = np.array((0.4, 0.5, 2.0), np.float64)
