@@ -172,6 +172,13 @@ int vrt_fetch_ldr_merged(vrt_ctx* ctx, const void* const* peer_ptrs, int32_t n_p
 int vrt_fetch_hdr(vrt_ctx* ctx, float* rgba);
 /* Renderer.fetch_image / _render_to_image (pathtracer.py:634-662,1321-1323) */
 int vrt_fetch_ldr(vrt_ctx* ctx, float* rgba);
+/* Pipelined fetch_image for a frame loop (no upstream counterpart: the reference blits its texture on
+ * the device): the tonemap pass runs on the context's stream, the device-to-host copy on a separate
+ * copy-engine stream, and the call returns without waiting for it, so the copy of frame k overlaps the
+ * rendering of frame k+1. rgba_pinned must be page-locked host memory that stays valid until
+ * vrt_fetch_wait (or the next vrt_fetch_* call, which waits first) returns. */
+int vrt_fetch_ldr_async(vrt_ctx* ctx, float* rgba_pinned);
+int vrt_fetch_wait(vrt_ctx* ctx);
 /* Same pass, result left on the device (no copy): returns the device pointer. */
 int vrt_resolve_ldr_device(vrt_ctx* ctx, void** ptr);
 

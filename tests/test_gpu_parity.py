@@ -702,3 +702,27 @@ def test_compact_sky_table_format_within_rmse_budget(vrt):
     assert not np.array_equal(a, b)
     g0 = vrt.Renderer(dx=2.0 / R, image_res=(64, 64), grid_res=R, sky_res=0)  # no sky tables: format 1 is refused, 2 is unknown
     assert g0._lib.vrt_set_sky_format(g0._h, 1) != 0 and g0._lib.vrt_set_sky_format(g0._h, 2) != 0 and g0._lib.vrt_set_sky_format(g0._h, 0) == 0
+
+
+def test_pipelined_fetch_equals_synchronous_fetch(vrt):
+    """vrt_fetch_ldr_async + vrt_fetch_wait: the image copied by the copy-engine stream while the next
+    batch renders is bit-identical to the synchronous fetch of the same accumulation state."""
+    import torch
+
+    R = 32
+    g = vrt.Renderer(dx=2.0 / R, image_res=(256, 128), grid_res=R, sky_res=0, seed=4)
+    g.set_voxels(*scenes.random_grid(R, 0.3, 9))
+    g.set_directional_light((1, 1, 0.5), 0.05, (1.2, 1.1, 1.0))
+    g.set_background_color((0.3, 0.4, 0.6))
+    g.prepare_data()
+    bufs = [torch.empty((128, 256, 4), dtype=torch.float32, pin_memory=True).numpy() for _ in range(2)]
+    g.accumulate(2)
+    sync0 = g.fetch_image()
+    g.fetch_image_async(bufs[0])          # frame 0 in flight ...
+    g.accumulate(2)                       # ... while the next batch renders
+    g.fetch_image_async(bufs[1])          # waits for frame 0's copy first, then queues frame 1
+    assert np.array_equal(bufs[0], sync0)
+    g.wait_image()
+    assert np.array_equal(bufs[1], g.fetch_image()) and not np.array_equal(bufs[1], bufs[0])
+    with pytest.raises(ValueError):
+        g.fetch_image_async(np.zeros((4, 4, 4), np.float32))

@@ -11,7 +11,7 @@ EXPORTS = [
     "vrt_set_light", "vrt_set_floor", "vrt_set_background", "vrt_set_sky", "vrt_set_materials",
     "vrt_set_cloud_texture", "vrt_prepare", "vrt_get_sky_tables", "vrt_set_sky_tables", "vrt_set_sky_format", "vrt_get_trans_lut",
     "vrt_trace_primary", "vrt_accumulate", "vrt_accumulate_restir", "vrt_accumulate_moving", "vrt_get_reservoirs", "vrt_set_tile_shard", "vrt_reset", "vrt_accum_device_ptr",
-    "vrt_fetch_hdr", "vrt_fetch_ldr", "vrt_accum_ipc_handle", "vrt_open_peer_accum", "vrt_close_peer_accum", "vrt_fetch_ldr_merged", "vrt_resolve_ldr_device", "vrt_get_stats", "vrt_synchronize",
+    "vrt_fetch_hdr", "vrt_fetch_ldr", "vrt_fetch_ldr_async", "vrt_fetch_wait", "vrt_accum_ipc_handle", "vrt_open_peer_accum", "vrt_close_peer_accum", "vrt_fetch_ldr_merged", "vrt_resolve_ldr_device", "vrt_get_stats", "vrt_synchronize",
 ]
 
 
@@ -70,6 +70,8 @@ def load():
     lib.vrt_get_sky_tables.argtypes = [P, fp, fp]
     lib.vrt_set_sky_tables.argtypes = [P, fp, fp]
     lib.vrt_set_sky_format.argtypes = [P, C.c_int32]
+    lib.vrt_fetch_ldr_async.argtypes = [P, fp]
+    lib.vrt_fetch_wait.argtypes = [P]
     lib.vrt_get_trans_lut.argtypes = [P, P]
     lib.vrt_trace_primary.argtypes = [P, P]
     lib.vrt_accumulate.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]

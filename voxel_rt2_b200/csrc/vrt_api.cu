@@ -73,6 +73,10 @@ struct vrt_ctx {
   int tile_rank = 0, tile_n = 1;
   vrt_stats stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // pipelined image fetch (vrt_fetch_ldr_async): copy engine stream + events, created on first use
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_resolved = nullptr, ev_copied = nullptr;
+  bool copy_pending = false;
 };
 
 static thread_local std::string g_create_err;
@@ -219,6 +223,10 @@ void vrt_destroy(vrt_ctx* ctx) {
   cudaFree(ctx->mv.col_d), cudaFree(ctx->mv.col_s), cudaFree(ctx->mv.out), cudaFree(ctx->mv.full), cudaFree(ctx->mv.refl), cudaFree(ctx->mv.refl_blur);
   for (int k = 0; k < 2; k++) cudaFree(ctx->mv.hd[k]), cudaFree(ctx->mv.hs[k]), cudaFree(ctx->mv.hsd[k]), cudaFree(ctx->mv.depth[k]), cudaFree(ctx->mv.attr[k]);
   cudaFree(ctx->rb.reservoirs), cudaFree(ctx->rb.gpos), cudaFree(ctx->rb.gattr), cudaFree(ctx->rb.col_d), cudaFree(ctx->rb.col_s);
+  if (ctx->copy_pending) cudaEventSynchronize(ctx->ev_copied);
+  if (ctx->ev_resolved) cudaEventDestroy(ctx->ev_resolved);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -792,8 +800,17 @@ int vrt_accum_device_ptr(vrt_ctx* ctx, void** ptr, uint64_t* bytes) {
   return VRT_OK;
 }
 
+static int wait_pending_copy(vrt_ctx* ctx) {
+  if (ctx->copy_pending) {
+    CK(cudaEventSynchronize(ctx->ev_copied));
+    ctx->copy_pending = false;
+  }
+  return VRT_OK;
+}
+
 static int resolve(vrt_ctx* ctx, bool ldr, float* host) {
   CK(cudaSetDevice(ctx->device));
+  if (int rc = wait_pending_copy(ctx)) return rc;  // d_out may still be the source of a pipelined copy
   const int W = ctx->cfg.width, H = ctx->cfg.height;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const float4* src = ctx->d_accum;
@@ -818,6 +835,39 @@ int vrt_fetch_ldr(vrt_ctx* ctx, float* rgba) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(rgba, "vrt_fetch_ldr: null pointer");
   return resolve(ctx, true, rgba);
+}
+// Pipelined variant of vrt_fetch_ldr: the tonemap pass runs on the context's stream, the device-to-host
+// copy on a separate copy-engine stream, and the call returns without waiting for it, so the copy of
+// frame k overlaps the rendering of frame k+1. The image is complete after vrt_fetch_wait (or the next
+// vrt_fetch_* call, which waits first: the device image buffer is single).
+int vrt_fetch_ldr_async(vrt_ctx* ctx, float* rgba_pinned) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(rgba_pinned, "vrt_fetch_ldr_async: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_resolved, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+  }
+  if (int rc = wait_pending_copy(ctx)) return rc;
+  const int W = ctx->cfg.width, H = ctx->cfg.height;
+  const float4* src = ctx->d_accum;
+  if (ctx->mv.active) {
+    CK(vrt_launch_moving_upsample(ctx->mv.out, ctx->mv.full, W, H, ctx->mv.scale, ctx->stream));
+    src = ctx->mv.full;
+  }
+  CK(vrt_launch_resolve(src, nullptr, ctx->d_out, W, H, ctx->cfg.exposure, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_resolved, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_resolved, 0));
+  CK(cudaMemcpyAsync(rgba_pinned, ctx->d_out, (size_t)W * H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+  ctx->copy_pending = true;
+  return VRT_OK;
+}
+int vrt_fetch_wait(vrt_ctx* ctx) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return wait_pending_copy(ctx);
 }
 int vrt_resolve_ldr_device(vrt_ctx* ctx, void** ptr) {
   if (!ctx) return VRT_ERR_BAD_ARG;

@@ -262,6 +262,19 @@ class Renderer:
         self._check(self._lib.vrt_fetch_ldr(self._h, _fp(out)))
         return out
 
+    def fetch_image_async(self, out_pinned):
+        """Pipelined fetch_image for frame loops: tonemap on the render stream, device-to-host copy on a
+        copy-engine stream, returns at once (the copy of frame k overlaps the rendering of frame k+1).
+        `out_pinned` is a float32 [H, W, 4] array in page-locked memory; it is complete after
+        wait_image() or the next fetch call."""
+        if out_pinned.dtype != np.float32 or out_pinned.size != self.image_res[0] * self.image_res[1] * 4 or not out_pinned.flags["C_CONTIGUOUS"]:
+            raise ValueError("fetch_image_async needs a contiguous float32 [H, W, 4] buffer")
+        self._check(self._lib.vrt_fetch_ldr_async(self._h, _fp(out_pinned)))
+        return out_pinned
+
+    def wait_image(self):
+        self._check(self._lib.vrt_fetch_wait(self._h))
+
     def fetch_hdr(self):
         """Mean linear radiance, float32 [H, W, 4] (w = samples accumulated)."""
         out = np.empty((self.image_res[1], self.image_res[0], 4), np.float32)
