@@ -516,9 +516,12 @@ ceil = _f1(np.ceil)
 rsqrt = _f1(lambda a: 1 / np.sqrt(a))
 
 
-def round(x):  # ti.round: half away from zero (C roundf)
+def round(x):  # ti.round: half away from zero (C roundf), exact: floor(|a| + 0.5) would round 0.49999997f up
     a, _ = _float_in(x)
-    return _wrap((np.sign(a) * np.floor(np.abs(a) + a.dtype.type(0.5))).astype(a.dtype))
+    m = np.abs(a)
+    f = np.floor(m)
+    r = f + ((m - f) >= a.dtype.type(0.5)).astype(a.dtype)  # m - f is exact in floating point
+    return _wrap(np.copysign(r, a).astype(a.dtype))
 
 
 def abs_(x):

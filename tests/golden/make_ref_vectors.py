@@ -465,6 +465,40 @@ def section_frame():
     np.savez_compressed(os.path.join(HERE, "ref_frame.npz"), **out)
 
 
+# ----------------------------------------------------------------- voxel authoring (row a1)
+def section_voxel():
+    """Scene.round_idx (scene.py:131-137) and Renderer.set_voxel / get_voxel (pathtracer.py:1325-1334,
+    math_utils.py:86-100): index rounding (ti.round: half away from zero), the i8 material cast and
+    the u8 colour quantisation, on 96 hand-picked and random (index, material, colour) triples."""
+    import scene as ref_scene  # /root/reference/scene.py; only the class is used, no window is opened
+
+    R = 32
+    cfg = dict(voxel_edges=0.06, light_dir=(1, 1, 1), light_cone=0.1, light_color=(0, 0, 0), floor_height=0.0, floor_color=(1, 1, 1),
+               floor_material=1, background=(0, 0, 0))
+    r = make_reference_renderer(32, 16, R, np.zeros((R, R, R), np.int8), np.zeros((R, R, R, 3), np.uint8), cfg)
+    rng = np.random.default_rng(55)
+    n = 96
+    idx = rng.uniform(-R / 2 + 0.6, R / 2 - 1.6, (n, 3))
+    idx[:12] = np.round(idx[:12]) + rng.choice([0.5, -0.5, 0.49999997, 0.0], (12, 3))   # ties and near-ties
+    idx[12:20] = np.round(idx[12:20])                                                    # integer-valued
+    idx = idx.astype(np.float32)
+    mats = rng.choice(np.array([0, 1, 2, 11, 54, 82, 127, 128, 200, 255, -1]), n).astype(np.int32)
+    cols = rng.uniform(-0.2, 1.2, (n, 3)).astype(np.float32)
+    cols[:6] = [[0, 0, 0], [1, 1, 1], [0.5, 0.25, 0.125], [0.999999, 0.003921569, 0.00392], [254.5 / 255, 1 / 255, 2 / 255], [0.2, 0.4, 0.6]]
+    rounded = np.zeros((n, 3), np.int32)
+    got_mat = np.zeros(n, np.int32)
+    got_col = np.zeros((n, 3), np.float32)
+    for i in range(n):
+        ri = ref_scene.Scene.round_idx(vec(idx[i]))
+        rounded[i] = ri.data
+        r.set_voxel(ri, np.int32(mats[i]), vec(cols[i]))
+        m, c = r.get_voxel(ri)
+        got_mat[i], got_col[i] = m, c.data
+    np.savez_compressed(os.path.join(HERE, "ref_voxel.npz"), R=np.int32(R), idx=idx, mat=mats, color=cols, rounded=rounded, get_mat=got_mat,
+                        get_color=got_col, material_field=r.world.voxel_material.arr.copy(), color_field=r.world.voxel_color.arr.copy())
+    print("voxel: %d set/get round trips, %d distinct cells" % (n, len({tuple(x) for x in rounded})))
+
+
 # ------------------------------------------------------------ moving-camera temporal path
 class _SnapshotReads:
     """Field proxy: reads see the array as it was when the proxy was made, writes go to the field.
@@ -781,7 +815,7 @@ def section_sky():
 
 
 SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render, "frame": section_frame,
-            "shift": section_shift, "moving": section_moving, "example1": section_example1, "sky": section_sky}
+            "shift": section_shift, "voxel": section_voxel, "moving": section_moving, "example1": section_example1, "sky": section_sky}
 
 if __name__ == "__main__":
     for s in (sys.argv[1:] or list(SECTIONS)):

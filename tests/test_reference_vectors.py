@@ -290,3 +290,26 @@ def test_moving_camera_path_matches_reference_filters(oracle):
         assert (err < 1e-4).mean() >= 0.98 and err.max() < 2e-2, "frame %d: %.4f within 1e-4, worst %.3e" % (f, (err < 1e-4).mean(), err.max())
         if f < 2:
             assert err.max() < 1e-5
+
+
+def test_voxel_authoring_matches_reference_set_get_voxel(monkeypatch):
+    """Scene.round_idx + Renderer.set_voxel / get_voxel run by the reference source on 96 (index,
+    material, colour) triples (ties of ti.round, materials >= 128 wrapping in i8, colours outside
+    [0,1]): the host Scene of the product produces the same cells, material bytes, colour bytes and
+    read-back values."""
+    monkeypatch.setenv("VRT_GRID", "32")
+    import voxel_rt2_b200.scene as S
+
+    z = np.load(os.path.join(G, "ref_voxel.npz"))
+    R = int(z["R"])
+    sc = S.Scene(renderer_factory=lambda **kw: None)
+    assert sc.grid_res == R
+    for i in range(len(z["idx"])):
+        idx = [float(x) for x in z["idx"][i]]
+        assert list(S.Scene.round_idx(idx)) == [int(x) for x in z["rounded"][i]]
+        sc.set_voxel(idx, int(z["mat"][i]), tuple(float(x) for x in z["color"][i]))
+        m, c = sc.get_voxel(idx)
+        assert int(m) == int(z["get_mat"][i])
+        assert [np.float32(x) for x in c] == [x for x in z["get_color"][i]]
+    assert np.array_equal(sc.voxel_material, z["material_field"]) and np.array_equal(sc.voxel_color, z["color_field"])
+    assert (z["material_field"] < 0).any() and (z["get_mat"] == 127).any()

@@ -86,6 +86,7 @@ def test_integer_wraparound_promotion_and_matrix_helpers(ti):
     assert ti.binop("*", np.int32(3), 0.5).dtype == np.float32               # int * float literal -> f32
     assert ti.binop("+", np.uint8(200), np.int32(100)) == np.int32(300)
     assert ti.cast(np.float32(-2.7), ti.i32) == -2                           # C truncation
+    assert ti.round(np.float32(0.49999997)) == 0.0 and ti.round(np.float32(2.5)) == 3.0 and ti.round(np.float32(-2.5)) == -3.0  # roundf
     assert np.isnan(ti.max(np.float32("nan"), np.float32("nan"))) and ti.max(np.float32("nan"), np.float32(2.0)) == 2.0
     v = ti.Vector([3.0, 4.0, 12.0], ti.f32)
     n = v.normalized()
