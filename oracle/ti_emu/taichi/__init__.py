@@ -25,7 +25,6 @@ import ast
 import builtins
 import inspect
 import itertools
-import math as _pymath
 import sys
 import textwrap
 import types as _pytypes
@@ -986,12 +985,6 @@ class Texture:
 
 
 # ------------------------------------------------------------------------------------ atomics
-def _atomic(fn):
-    def g(target_get_set, v):
-        raise NotImplementedError
-    return g
-
-
 def atomic_or(x, v):  # rewritten by the AST pass into a read-modify-write of the target expression
     return binop("|", x, v)
 

@@ -15,9 +15,7 @@ EMU = os.path.join(ROOT, "oracle", "ti_emu")
 
 @pytest.fixture(scope="module")
 def ti():
-    # the product shim is also called `taichi`; load the emulator under a private name
-    import importlib.util
-
+    # the product shim is also called `taichi`: drop it from sys.modules while the emulator is loaded
     for k in [k for k in sys.modules if k == "taichi" or k.startswith("taichi.")]:
         saved = sys.modules.pop(k)
         assert saved is not None
