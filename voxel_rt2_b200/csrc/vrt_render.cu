@@ -10,7 +10,7 @@
 //              and a main loop that fits the SM's instruction cache):
 //                (0) retire finished paths   (1) refill idle lanes, start paths
 //                (2) trace pass 0: every lane's current ray; classify (escape / emissive / surface)
-//                    trace pass 1: the shadow rays spawned by pass 0, if >= 12 lanes have one
+//                    trace pass 1: the shadow rays spawned by pass 0, if >= 14 lanes have one
 //                (3b) ONE sky-table site for escaped segments and visible sun samples
 //                (4) shade: NEE term + BSDF sample (rare lobes in out-of-line functions)
 //   k_resolve  mean + vignette + exposure + Uchimura + gamma (renderer/pathtracer.py:634-662,
@@ -95,7 +95,7 @@ enum { ST_SEGMENT = 0, ST_SHADOW = 1 };
 enum { PIX_IDLE = -1, PIX_DONE = -2 };
 
 #ifndef VRT_PASS1_MIN_LANES
-#define VRT_PASS1_MIN_LANES 12 // lanes with a fresh shadow ray that justify a second trace pass in the same iteration
+#define VRT_PASS1_MIN_LANES 14 // lanes with a fresh shadow ray that justify a second trace pass in the same iteration
 #endif
 #ifndef VRT_PATH_MIN_BLOCKS
 #define VRT_PATH_MIN_BLOCKS 5  // resident CTAs per SM the register allocation is tuned for
