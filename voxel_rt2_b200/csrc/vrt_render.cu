@@ -299,8 +299,9 @@ __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_pa
         d = get_cast_dir_scaled(P, (float)u, (float)v, MO.scale);
       } else {
         const float2 j = P.jitter[s_i];
-        // MODE 0 integrates the jittered pixel footprint: SFU arithmetic (+2.7 %); the G-buffer modes keep the IEEE ray
-        d = MODE == 0 ? get_cast_dir_fast(P, (float)u, (float)v, j.x, j.y) : get_cast_dir(P, (float)u, (float)v, j.x, j.y);
+        // IEEE camera ray in every mode: an SFU-arithmetic variant was 2.7 % faster but flipped 1-2 edge pixels per
+        // 10^4 against the oracle (profiles/r01e_ifetch_experiments.md); per-pixel parity is worth more
+        d = get_cast_dir(P, (float)u, (float)v, j.x, j.y);
       }
       pos = P.cam_pos;
       thr = mk3(1.0f), contrib = mk3(0.0f), fnee_d = mk3(0.0f), fnee_s = mk3(0.0f);

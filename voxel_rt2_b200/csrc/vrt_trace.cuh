@@ -275,21 +275,6 @@ HD f3 get_cast_dir(const Params& P, float u, float v, float jx, float jy) {
   return f3{w[0], w[1], w[2]};
 }
 
-// Same ray for the path kernel's jittered samples: the pixel footprint is integrated statistically,
-// so the three IEEE divisions and the IEEE normalisation (needed only where hit buffers must be
-// bit-identical, k_primary) are replaced by SFU reciprocal / rsqrt (direction error ~1e-7).
-HD f3 get_cast_dir_fast(const Params& P, float u, float v, float jx, float jy) {
-  const float tx = (u + 0.5f) * P.inv_w + jx * 0.5f, ty = (v + 0.5f) * P.inv_h + jy * 0.5f;
-  const float px = tx * 2.0f - 1.0f, py = ty * 2.0f - 1.0f;
-  float q[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) q[i] = ((P.inv_proj[i * 4 + 0] * px + P.inv_proj[i * 4 + 1] * py) + P.inv_proj[i * 4 + 2]) + P.inv_proj[i * 4 + 3];
-  const float iw = frcp(q[3]);
-  const f3 dv = normalize(f3{q[0] * iw, q[1] * iw, q[2] * iw});
-  return f3{(P.inv_view[0] * dv.x + P.inv_view[1] * dv.y) + P.inv_view[2] * dv.z, (P.inv_view[4] * dv.x + P.inv_view[5] * dv.y) + P.inv_view[6] * dv.z,
-            (P.inv_view[8] * dv.x + P.inv_view[9] * dv.y) + P.inv_view[10] * dv.z};
-}
-
 // Moving camera (pathtracer.py:307-309): texcoord / render_scale, no TAA jitter.
 HD f3 get_cast_dir_scaled(const Params& P, float u, float v, float scale) {
   const float tx = xdiv(xmul(xadd(u, 0.5f), P.inv_w), scale);
