@@ -53,6 +53,8 @@ def load():
     lib.orc_get_cloud_ambient.argtypes = [P, fp]
     lib.orc_sample_skybox.argtypes = [P, C.c_int, fp, fp, fp, fp]
     lib.orc_shift_probe.argtypes = [P, C.c_int, fp, fp]
+    lib.orc_reservoir_probe.argtypes = [C.c_int, fp, fp]
+    lib.orc_gris_probe.argtypes = [P, C.c_uint32, fp, fp, fp, fp, C.c_int, ip, fp]
     lib.orc_set_tile_shard.argtypes = [P, C.c_int, C.c_int]
     lib.orc_trace_primary.argtypes = [P, P]
     lib.orc_accumulate.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -244,6 +246,17 @@ class OracleRenderer:
         self._lib.orc_shift_probe(self._h, rows.shape[0], _fp(rows), _fp(out))
         return out
 
+    def gris_probe(self, frame, samples, gbuf, col_d, col_s, pixels):
+        """orc_gris_probe: spatial_GRIS on caller-built reservoirs / G-buffer (see oracle.cpp) -> [n][6]."""
+        self._sync_camera()
+        npx = self.image_res[0] * self.image_res[1]
+        samples, gbuf = _f32(samples, 23 * npx), _f32(gbuf, 7 * npx)
+        col_d, col_s = _f32(col_d, 3 * npx), _f32(col_s, 3 * npx)
+        pixels = np.ascontiguousarray(pixels, np.int32)
+        out = np.empty((pixels.size, 6), np.float32)
+        self._lib.orc_gris_probe(self._h, int(frame), _fp(samples), _fp(gbuf), _fp(col_d), _fp(col_s), pixels.size, _ip(pixels), _fp(out))
+        return out
+
     def get_cloud_ambient(self):
         a = np.empty(3, np.float32)
         self._lib.orc_get_cloud_ambient(self._h, _fp(a))
@@ -370,6 +383,15 @@ def math_probe(kind, a, b=None, out_per=3):
     b = np.ascontiguousarray(b if b is not None else np.zeros((n, 3)), np.float32)
     out = np.zeros((n, out_per) if out_per > 1 else (n,), np.float32)
     lib.orc_math_probe(int(kind), n, _fp(a), _fp(b), _fp(out))
+    return out
+
+
+def reservoir_probe(rows):
+    """orc_reservoir_probe: rows[n][53] float32 (see oracle.cpp) -> [n][28]."""
+    lib = load()
+    rows = np.ascontiguousarray(rows, np.float32)
+    out = np.empty((rows.shape[0], 28), np.float32)
+    lib.orc_reservoir_probe(rows.shape[0], _fp(rows), _fp(out))
     return out
 
 

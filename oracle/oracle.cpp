@@ -12,9 +12,11 @@
 // The restatement is pinned by (1) vectors computed by the reference's own renderer/*.py source
 // executed through oracle/ti_emu, a float32 Taichi emulator (tests/golden/make_ref_vectors.py ->
 // tests/golden/ref_*.npz -> tests/test_reference_vectors.py: traversal and hit buffers bit-exact,
-// render() per pixel to 3e-5, the static frame loop to 1.4e-6, BSDF to 1.5e-7, sky precompute),
+// render() per pixel to 3e-5, the static frame loop to 1.4e-6, BSDF to 1.5e-7, sky precompute, the
+// moving-camera filter chain to 5e-3 worst pixel; ReSTIR shift() / reservoir packing / spatial_GRIS
+// bit-exact on inputs free of the zero-vector encodings upstream leaves undefined),
 // (2) hand-derived known-answer tests and a brute-force traversal twin (tests/test_oracle_kat.py).
-// The ReSTIR and moving-camera restatements are pinned by (2) only (DESIGN.md "ReSTIR pins").
+// The ReSTIR branch of render() that fills the reservoirs is pinned by (2) only (DESIGN.md "ReSTIR pins").
 #include <omp.h>
 
 #include <algorithm>
@@ -1276,6 +1278,79 @@ void orc_shift_probe(void* p, int n, const float* in, float* out) {
     shift_sample(*c, v3(0), v3(3), dst_mat, v3(6), src, d, s, j);
     float* o = out + 7 * i;
     o[0] = d.x, o[1] = d.y, o[2] = d.z, o[3] = s.x, o[4] = s.y, o[5] = s.z, o[6] = j;
+  }
+}
+// Reservoir bookkeeping and the 56-byte record (reservoir.py:41-141) on caller-built samples with
+// NON-zero vectors (the zero-vector markers are the part upstream leaves undefined):
+// init -> input_sample(wA, A) -> input_sample(wB, B) -> update_cached_jacobian_term(x1) ->
+// merge({z = B, M = M_other}, wm) -> finalize_without_M -> encode -> decode.
+// in[n][53]: A (21) | B (21) | wA wB uA uB | x1 (3) | wm um | M_other weight_other. A sample is
+// F, rc_pos, rc_normal, rc_incident_dir, rc_incident_L, rc_NEE_dir (3 each), rc_mat_info (bits),
+// cached_jacobian_term, lobes. out[n][28]: selA selB selM M weight (before encode) | decoded M W |
+// decoded sample in the same 21-float layout.
+void orc_reservoir_probe(int n, const float* in, float* out) {
+  auto sample_of = [](const float* a) {
+    Sample z;
+    auto v3 = [&](int k) { return V3{a[k], a[k + 1], a[k + 2]}; };
+    z.F = v3(0), z.rc_pos = v3(3), z.rc_normal = v3(6), z.rc_incident_dir = v3(9), z.rc_incident_L = v3(12), z.rc_NEE_dir = v3(15);
+    std::memcpy(&z.rc_mat_info, a + 18, 4);
+    z.cached_jacobian_term = a[19];
+    z.lobes = (int)a[20];
+    return z;
+  };
+  for (int i = 0; i < n; i++) {
+    const float* a = in + 53 * i;
+    float* o = out + 28 * i;
+    const Sample A = sample_of(a), B = sample_of(a + 21);
+    Reservoir r;
+    o[0] = r.input_sample(a[42], A, a[44]) ? 1.0f : 0.0f;
+    o[1] = r.input_sample(a[43], B, a[45]) ? 1.0f : 0.0f;
+    r.update_cached_jacobian_term(V3{a[46], a[47], a[48]});
+    Reservoir other;
+    other.z = B, other.M = a[51], other.weight = a[52];
+    o[2] = r.merge(other, a[49], a[50]) ? 1.0f : 0.0f;
+    r.finalize_without_M();
+    o[3] = r.M, o[4] = r.weight;
+    const Reservoir d = decode_reservoir(encode_reservoir(r));
+    o[5] = d.M, o[6] = d.weight;
+    float* z = o + 7;
+    auto put = [&](int k, V3 v) { z[k] = v.x, z[k + 1] = v.y, z[k + 2] = v.z; };
+    put(0, d.z.F), put(3, d.z.rc_pos), put(6, d.z.rc_normal), put(9, d.z.rc_incident_dir), put(12, d.z.rc_incident_L), put(15, d.z.rc_NEE_dir);
+    std::memcpy(z + 18, &d.z.rc_mat_info, 4);
+    z[19] = d.z.cached_jacobian_term;
+    z[20] = (float)d.z.lobes;
+  }
+}
+// spatial_GRIS (pathtracer.py:815-989) on caller-built buffers: per pixel a reservoir (sample in the
+// 21-float layout of orc_reservoir_probe + M + W = 23 floats, packed with encode_reservoir as
+// render() would, :607), a G-buffer entry (position 3, octahedral normal 2, material info bits, sky
+// flag = 7 floats) and the canonical sample's diffuse / specular integrand (:631-632). Runs the
+// pass for the listed pixels (index = v * W + u); out[k] = colour buffers after the pass (6 floats).
+void orc_gris_probe(void* p, uint32_t frame, const float* samples, const float* gbuf, const float* col_d, const float* col_s, int n,
+                    const int* pixels, float* out) {
+  Ctx* c = (Ctx*)p;
+  const size_t npx = (size_t)c->scene.W * c->scene.H;
+  c->reservoirs.resize(npx), c->gbuf.resize(npx), c->col_d.resize(npx), c->col_s.resize(npx);
+  for (size_t i = 0; i < npx; i++) {
+    const float* a = samples + 23 * i;
+    auto v3 = [&](const float* q) { return V3{q[0], q[1], q[2]}; };
+    Reservoir r;
+    r.z.F = v3(a), r.z.rc_pos = v3(a + 3), r.z.rc_normal = v3(a + 6), r.z.rc_incident_dir = v3(a + 9), r.z.rc_incident_L = v3(a + 12),
+    r.z.rc_NEE_dir = v3(a + 15);
+    std::memcpy(&r.z.rc_mat_info, a + 18, 4);
+    r.z.cached_jacobian_term = a[19], r.z.lobes = (int)a[20], r.M = a[21], r.weight = a[22];
+    c->reservoirs[i] = encode_reservoir(r);
+    const float* g = gbuf + 7 * i;
+    GBufferPx& G = c->gbuf[i];
+    G.position = v3(g), G.n_oct[0] = g[3], G.n_oct[1] = g[4], G.sky = g[6] != 0.0f;
+    std::memcpy(&G.mat_info, g + 5, 4);
+    c->col_d[i] = v3(col_d + 3 * i), c->col_s[i] = v3(col_s + 3 * i);
+  }
+  for (int k = 0; k < n; k++) {
+    V3 d, s;
+    spatial_gris_pixel(*c, pixels[k] % c->scene.W, pixels[k] / c->scene.W, frame, d, s);
+    float* o = out + 6 * k;
+    o[0] = d.x, o[1] = d.y, o[2] = d.z, o[3] = s.x, o[4] = s.y, o[5] = s.z;
   }
 }
 // sample_skybox (atmos.py:94-115) with the three jitter numbers supplied

@@ -705,6 +705,208 @@ def section_shift():
     print("shift: %d probes, %d with non-zero Jacobian" % (n, int((out[:, 6] != 0).sum())))
 
 
+# ------------------------------------------------------------------------- reservoir.py
+def reservoir_probe_rows(n, seed):
+    """Inputs of orc_reservoir_probe (oracle.cpp): two samples whose vectors are all non-zero, RIS
+    weights (some zero, exercising the in_w > 0 branch), the random numbers of the three selection
+    draws, a primary position and the neighbour's M."""
+    rng = np.random.default_rng(seed)
+    rows = np.zeros((n, 53), np.float32)
+    for i in range(n):
+        for k in (0, 21):
+            rows[i, k:k + 3] = rng.uniform(0.0, 3.0, 3) * (0.0 if i % 16 == 15 and k == 21 else 1.0)  # F (black: finalize's p_hat < 1e-6)
+            rows[i, k + 3:k + 6] = rng.uniform(-2.0, 2.0, 3)  # rc_pos
+            rows[i, k + 6:k + 9], rows[i, k + 9:k + 12] = unit(rng, 1)[0], unit(rng, 1)[0]
+            rows[i, k + 12:k + 15] = rng.uniform(0.0, 4.0, 3)
+            rows[i, k + 15:k + 18] = unit(rng, 1)[0]
+            rows[i, k + 18:k + 19] = np.array([rng.integers(0, 2 ** 32)], np.uint32).view(np.float32)
+            rows[i, k + 19] = rng.uniform(0.01, 40.0)
+            rows[i, k + 20] = float(int(rng.integers(0, 3)) * 10 + int(rng.integers(0, 3)))
+        rows[i, 42:44] = rng.uniform(0.0, 2.0, 2) * (rng.random(2) > 0.15)
+        rows[i, 44:46] = rng.random(2)
+        rows[i, 46:49] = rng.uniform(-2.0, 2.0, 3)
+        rows[i, 49] = rng.uniform(0.0, 2.0) * (rng.random() > 0.15)
+        rows[i, 50] = rng.random()
+        rows[i, 51], rows[i, 52] = float(rng.integers(1, 33)), rng.uniform(0.0, 5.0)
+    return rows
+
+
+def section_reservoir():
+    """Reservoir.init / input_sample / update_cached_jacobian_term / merge / finalize_without_M /
+    encode / decode (reservoir.py:41-141) on 192 reservoirs whose sample vectors are all non-zero
+    (octahedral encodings of zero vectors, the part the upstream mode leaves undefined, are not
+    exercised). ti.random() answers with the row's three selection numbers in call order."""
+    sys.path.insert(0, ROOT)
+    from renderer.reservoir import Reservoir, Sample
+
+    rows = reservoir_probe_rows(192, 77)
+    out = np.zeros((rows.shape[0], 28), np.float32)
+
+    def sample_of(a):
+        return Sample(F=vec(a[0:3]), rc_pos=vec(a[3:6]), rc_normal=vec(a[6:9]), rc_incident_dir=vec(a[9:12]), rc_incident_L=vec(a[12:15]),
+                      rc_NEE_dir=vec(a[15:18]), rc_mat_info=a[18:19].view(np.uint32)[0], cached_jacobian_term=np.float32(a[19]),
+                      lobes=np.int32(int(a[20])))
+
+    for i, a in enumerate(rows):
+        draws = [a[44], a[45], a[50]]
+        ti.set_random_source(lambda name, q=draws: q.pop(0))
+        A, B = sample_of(a), sample_of(a[21:])
+        r = Reservoir()
+        r.init()
+        sel_a = r.input_sample(np.float32(a[42]), A)
+        if a[42] <= 0:
+            draws.pop(0)  # the draw sits inside the in_w > 0 branch
+        sel_b = r.input_sample(np.float32(a[43]), B)
+        if a[43] <= 0:
+            draws.pop(0)
+        r.update_cached_jacobian_term(vec(a[46:49]))
+        other = Reservoir()
+        other.init()
+        other.z, other.M, other.weight = B, np.float32(a[51]), np.float32(a[52])
+        sel_m = r.merge(other, np.float32(a[49]))
+        r.finalize_without_M()
+        out[i, 0:5] = float(sel_a), float(sel_b), float(sel_m), r.M, r.weight
+        d = Reservoir()
+        d.init()
+        d.decode(r.encode())
+        z = d.z
+        out[i, 5:7] = d.M, d.weight
+        out[i, 7:10], out[i, 10:13], out[i, 13:16] = z.F.data, z.rc_pos.data, z.rc_normal.data
+        out[i, 16:19], out[i, 19:22], out[i, 22:25] = z.rc_incident_dir.data, z.rc_incident_L.data, z.rc_NEE_dir.data
+        out[i, 25:26] = np.array([z.rc_mat_info], np.uint32).view(np.float32)
+        out[i, 26], out[i, 27] = z.cached_jacobian_term, float(z.lobes)
+    ti.set_random_source(None)
+    np.savez_compressed(os.path.join(HERE, "ref_reservoir.npz"), rows=rows, out=out)
+    print("reservoir: %d probes, selections %s, %d zero weights" % (rows.shape[0], out[:, 0:3].sum(0).astype(int).tolist(), int((out[:, 4] == 0).sum())))
+
+
+# ------------------------------------------------------------------------- spatial_GRIS
+def section_gris():
+    """Renderer.spatial_GRIS(0, 24.0, 32, 1) (pathtracer.py:815-989, the call of accumulate() :1313)
+    on hand-built buffers. The G-buffer is the reference's own: get_cast_dir + next_hit per pixel,
+    then the writes of render() (:535-541). Every pixel's reservoir holds a sample whose vectors are
+    all non-zero (a reconnection vertex with a continuation and a visible sun), packed with
+    Reservoir.encode() as render() does (:607): the octahedral encodings of zero vectors, the part
+    upstream leaves undefined, do not occur. The camera looks down so that no pixel sees the sky
+    (the other hole). Out-of-image taps read zeros (Field.oob_zero) and fail the distance test.
+    ti.random(): dimension 65 = radius shift, 66 + i = merge draw of tap i, 98 = canonical merge
+    of the oracle's sampler, key (pixel, frame). The pass is run for every seventh pixel."""
+    sys.path.insert(0, ROOT)
+    import renderer.math_utils as mu
+    from renderer.math_utils import eps, inf
+    from renderer.reservoir import Reservoir, Sample
+    from renderer.space_transformations import screen_to_view, view_to_screen, view_to_world, world_to_view
+    from voxel_rt2_b200.camera import default_camera_matrices
+
+    W, H, R, seed, frame, S = 48, 24, 32, 31, 5, 16
+    cfg = dict(voxel_edges=0.06, light_dir=(0.4, 0.8, 0.45), light_cone=0.05, light_color=(1.2, 1.1, 0.9), floor_height=-0.5,
+               floor_color=(0.9, 0.85, 0.8), floor_material=1, background=(0.1, 0.1, 0.1))
+    mat, col = render_scene(R, 3)
+    keep = np.random.default_rng(8).random(mat.shape) < 0.15  # mostly open floor: neighbouring pixels share a surface
+    keep[R // 3: 2 * R // 3, : R // 4, R // 3: 2 * R // 3] = True
+    mat = np.where(keep, mat, 0).astype(np.int8)
+    r = make_reference_renderer(W, H, R, mat, col, cfg)
+    sc, tr = synthetic_sky_tables(S)  # shift() looks the sun transmittance up for the reconnection vertex (:775-779)
+    r.use_physical_atmosphere[None] = 1
+    r.atmos.skybox_res = ti.Vector([S, S])
+    r.atmos.skybox_fres = ti.Vector([1.0 / S, 1.0 / S])
+    r.atmos.skybox_scattering = ti.Vector.field(3, dtype=ti.f32, shape=(S, S))
+    r.atmos.skybox_transmittance = ti.Vector.field(3, dtype=ti.f32, shape=(S, S))
+    r.atmos.skybox_scattering.arr[...] = sc
+    r.atmos.skybox_transmittance.arr[...] = tr
+    pos, view, proj = default_camera_matrices(W, H, pos=(0.5, 2.2, 1.1))
+    set_reference_camera(r, pos, view, proj)
+    r.current_frame = frame
+    tex = r.world.voxel_color_texture
+    cam = r.camera_pos[None].copy()
+    rng = np.random.default_rng(4242)
+    ids = np.array([1, 2, 11, 21, 32, 40, 50, 52, 54, 80, 82], np.int32)
+    sun = np.asarray(cfg["light_dir"]) / np.linalg.norm(cfg["light_dir"])
+    npx = W * H
+    samples = np.zeros((npx, 23), np.float32)
+    gbuf = np.zeros((npx, 7), np.float32)
+    col_d = rng.uniform(0.0, 1.5, (npx, 3)).astype(np.float32)
+    col_s = rng.uniform(0.0, 0.5, (npx, 3)).astype(np.float32)
+    for f in (r.gbuff_normals, r.gbuff_depth, r.gbuff_mat_id, r.spatial_reservoirs):
+        for g in (f.fields.values() if hasattr(f, "fields") else [f]):
+            g.oob_zero = True
+    for v in range(H):
+        for u in range(W):
+            i = v * W + u
+            d = r.get_cast_dir(np.int32(u), np.int32(v))
+            closest, normal, albedo, hl, iters, mid = r.next_hit(cam, d, inf, tex, shadow_ray=False)
+            assert closest < inf, (u, v)
+            hit_pos = cam + closest * d + normal * eps
+            n_oct = mu.encode_unit_vector_3x16(normal)
+            info = mu.encode_material(mid, albedo)
+            depth = view_to_screen(world_to_view(hit_pos, r.view_mat[None]).xyz, r.proj_mat[None]).z
+            r.gbuff_normals[u, v], r.gbuff_depth[u, v], r.gbuff_position[u, v], r.gbuff_mat_id[u, v] = n_oct, depth, hit_pos, info
+            texcoord = (ti.Vector([np.int32(u), np.int32(v)]) + 0.5) * r.inv_image_res / r.render_scale[None]  # :823
+            x1 = view_to_world(screen_to_view(texcoord, depth, r.proj_mat_inv[None]), r.view_mat_inv[None])  # :850-852
+            gbuf[i, 0:3], gbuf[i, 3:5] = x1.data, n_oct.data.astype(np.float32)
+            gbuf[i, 5:6] = np.array([info], np.uint32).view(np.float32)
+            # the pixel's reservoir: a reconnection vertex above the surface, facing it
+            p, n = np.asarray(hit_pos.data, np.float64), np.asarray(normal.data, np.float64)
+            rc_pos = p + n * rng.uniform(0.5, 1.2) + rng.normal(0, 0.15, 3)
+            rc_n = (p - rc_pos) / np.linalg.norm(p - rc_pos) - n + rng.normal(0, 0.3, 3)  # faces the pixel and, roughly, its neighbours
+            rc_n /= np.linalg.norm(rc_n)
+            if i % 8 == 7:
+                rc_n = unit(rng, 1)[0]  # some reconnections fail the N.L checks
+            inc = unit(rng, 1)[0]
+            if np.dot(inc, rc_n) < 0:
+                inc = -inc
+            nee = sun + rng.normal(0, 0.01, 3)
+            nee /= np.linalg.norm(nee)
+            z = Sample(F=vec(rng.uniform(0.02, 1.5, 3)), rc_pos=vec(rc_pos), rc_normal=vec(rc_n), rc_incident_dir=vec(inc),
+                       rc_incident_L=vec(rng.uniform(0.0, 2.0, 3)), rc_NEE_dir=vec(nee),
+                       rc_mat_info=mu.encode_material(np.int32(rng.choice(ids)), vec(rng.uniform(0.1, 1.0, 3))),
+                       cached_jacobian_term=np.float32(1.0), lobes=np.int32(int(rng.integers(0, 3)) * 10 + int(rng.integers(0, 3))))
+            res = Reservoir()
+            res.init()
+            res.z, res.M, res.weight = z, np.float32(1.0), np.float32(rng.uniform(0.0, 3.0) * (rng.random() > 0.1))
+            res.update_cached_jacobian_term(hit_pos)  # :553
+            r.spatial_reservoirs[u, v, 0] = res.encode()
+            r.color_buffer[u, v], r.color_buffer_specular[u, v] = vec(col_d[i]), vec(col_s[i])
+            samples[i, 0:3], samples[i, 3:6], samples[i, 6:9] = res.z.F.data, res.z.rc_pos.data, res.z.rc_normal.data
+            samples[i, 9:12], samples[i, 12:15], samples[i, 15:18] = res.z.rc_incident_dir.data, res.z.rc_incident_L.data, res.z.rc_NEE_dir.data
+            samples[i, 18:19] = np.array([res.z.rc_mat_info], np.uint32).view(np.float32)
+            samples[i, 19], samples[i, 20], samples[i, 21], samples[i, 22] = res.z.cached_jacobian_term, float(res.z.lobes), res.M, res.weight
+    pixels = np.arange(1, npx, int(os.environ.get("GRIS_STEP", "7")), dtype=np.int32)
+    r.gbuff_position._struct_for = lambda: iter([(np.int32(i % W), np.int32(i // W)) for i in pixels])
+    state = {}
+
+    def source(name, fr):
+        f = fr
+        while f is not None and f.f_code.co_name != "spatial_GRIS":
+            f = f.f_back
+        assert f is not None, name
+        u, v = int(f.f_locals["u"]), int(f.f_locals["v"])
+        if name == "spatial_GRIS":
+            k = state[(u, v)] = state.get((u, v), 0) + 1
+            assert k <= 2
+            return 0.5 if k == 1 else sampler_rnd(v * W + u, frame, seed, 65)  # start_index (unused upstream), radius_shift
+        assert name == "merge", name
+        canonical = np.array_equal(fr.f_locals["in_r"].z.rc_pos.data, f.f_locals["center_reservoir"].z.rc_pos.data)  # rc_pos is unique per pixel
+        dim = 98 if canonical else 66 + int(f.f_locals["i"])
+        state[(u, v, dim)] = state.get((u, v, dim), 0) + 1
+        assert state[(u, v, dim)] == 1, (u, v, dim)
+        return sampler_rnd(v * W + u, frame, seed, dim)
+
+    ti.set_random_source(source, with_frame=True)
+    r.spatial_GRIS(0, 24.0, 32, 1, tex)
+    ti.set_random_source(None)
+    out_d = np.stack([r.color_buffer.arr[i % W, i // W] for i in pixels])
+    out_s = np.stack([r.color_buffer_specular.arr[i % W, i // W] for i in pixels])
+    merges = sum(1 for k in state if len(k) == 3 and k[2] != 98)
+    print("gris: %d pixels, %d neighbour merges drawn, mean out %.4f (in %.4f)" % (len(pixels), merges, float((out_d + out_s).mean()),
+                                                                                  float((col_d + col_s)[pixels].mean())))
+    out = dict(material=mat, color=col, cam_pos=pos, view=view, proj=proj, seed=np.int32(seed), frame=np.int32(frame), W=np.int32(W),
+               H=np.int32(H), sky_res=np.int32(S), sky_scatter=sc, sky_trans=tr, samples=samples, gbuf=gbuf, col_d=col_d, col_s=col_s, pixels=pixels, out_d=out_d, out_s=out_s)
+    for k, v in cfg.items():
+        out["cfg_" + k] = np.asarray(v, np.float32)
+    np.savez_compressed(os.path.join(HERE, "ref_gris.npz"), **out)
+
+
 # ------------------------------------------------------------------------- atmos.py (sky)
 def section_sky():
     """renderer/atmos.py: (1) 640 entries of the transmittance LUT from generate_transmittance_lut,
@@ -815,7 +1017,7 @@ def section_sky():
 
 
 SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render, "frame": section_frame,
-            "shift": section_shift, "voxel": section_voxel, "moving": section_moving, "example1": section_example1, "sky": section_sky}
+            "shift": section_shift, "voxel": section_voxel, "moving": section_moving, "example1": section_example1, "sky": section_sky, "reservoir": section_reservoir, "gris": section_gris}
 
 if __name__ == "__main__":
     for s in (sys.argv[1:] or list(SECTIONS)):

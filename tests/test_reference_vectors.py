@@ -251,6 +251,56 @@ def test_restir_shift_matches_reference(oracle):
     assert np.abs(ref[live, :6]).max() > 0.01
 
 
+def test_restir_reservoir_bookkeeping_and_packing_match_reference(oracle):
+    """Reservoir.init / input_sample / update_cached_jacobian_term / merge / finalize_without_M and the
+    56-byte record's encode -> decode (reservoir.py:41-141), run by the reference source on 192
+    reservoirs with non-zero sample vectors: selections, M, W and every decoded field (f16 M / W /
+    Jacobian term, 8-bit and f16 octahedral directions, i8 lobes) are BIT-identical. Rows in which
+    nothing was selected keep the all-zero init sample: there upstream decodes the octahedral
+    encoding of (0,0,0) (a 0/0) into a spurious (0,0,-1) normal and NaN incident direction, the
+    hazard the oracle's flag bits close; the oracle returns the zero vectors the algorithm tests for."""
+    z = np.load(os.path.join(G, "ref_reservoir.npz"))
+    got, ref = oracle.reservoir_probe(z["rows"]), z["out"]
+    gb, rb = got.view(np.uint32), ref.view(np.uint32)
+    assert (gb[:, :7] == rb[:, :7]).all()  # selections, M, weight, decoded M / W
+    assert ref[:, 0].sum() > 100 and ref[:, 1].sum() > 50 and ref[:, 2].sum() > 30 and (ref[:, 4] == 0).sum() >= 5
+    empty = ref[:, :3].sum(1) == 0
+    assert 1 <= empty.sum() <= 8
+    assert (gb[~empty] == rb[~empty]).all(), np.argwhere(gb[~empty] != rb[~empty])[:5]
+    assert np.isnan(ref[empty, 16:19]).all() and (ref[empty, 15] == -1).all()  # the upstream hazard, as recorded
+    assert (got[empty, 13:19] == 0).all() and (got[empty, 22:25] == 0).all()
+    keep = [c for c in range(7, 28) if c not in (*range(13, 19), *range(22, 25))]
+    assert (gb[empty][:, keep] == rb[empty][:, keep]).all()
+
+
+def test_restir_spatial_gris_matches_reference(oracle):
+    """Renderer.spatial_GRIS(0, 24.0, 32, 1) (pathtracer.py:815-989) run by the reference source on
+    hand-built buffers: the reference's own G-buffer of a 48 x 24 view (no sky pixels), one packed
+    reservoir per pixel whose sample vectors are all non-zero (so the zero-vector encodings upstream
+    leaves undefined do not occur), random canonical integrands; ti.random() answered from the shared
+    sampler (dimension 65 radius shift, 66 + i tap merges, 98 canonical merge). Pins the tap spiral
+    (hash3 seed, golden angle), the similarity rejection, both shift() directions, the pairwise MIS
+    weights, the merge order, the visibility ray and the finalisation, with the physical-sky lookup
+    of shift() on: the colour buffers after the pass agree on every processed pixel."""
+    from util import renderer_from_reference_fixture
+    from voxel_rt2_b200.materials import material_table
+
+    z = np.load(os.path.join(G, "ref_gris.npz"))
+    o = renderer_from_reference_fixture(oracle.OracleRenderer, z, materials=material_table())
+    o.set_use_physical_sky(True, False)
+    o.set_sky_tables(z["sky_scatter"], z["sky_trans"])
+    px = z["pixels"]
+    got = o.gris_probe(int(z["frame"]), z["samples"], z["gbuf"], z["col_d"], z["col_s"], px)
+    ref = np.concatenate([z["out_d"], z["out_s"]], 1)
+    assert len(px) >= 150 and np.isfinite(ref).all()
+    # the pass did resample: many pixels end on a neighbour's shifted sample, not on W x their own integrand
+    own = np.concatenate([z["col_d"][px], z["col_s"][px]], 1)
+    ratio = ref / own
+    resampled = (ratio.max(1) - ratio.min(1)) > 1e-3 * np.abs(ratio).max(1)
+    assert resampled.sum() >= 20 and (~resampled).sum() >= 20, resampled.sum()
+    assert _close(got, ref, 1e-5, 1e-7).all(), (np.abs(got - ref) / (np.abs(ref) + 1e-6)).max()  # measured: identical bits
+
+
 def test_config1_example1_hit_buffer_matches_reference(oracle):
     """BASELINE config 1 at 64 x 64: the example1.py scene in the Renderer exactly as shipped (128^3
     grid built by the reference's _update_lods / _make_texture), primary ray + sun shadow ray per

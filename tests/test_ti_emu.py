@@ -1,6 +1,6 @@
 """Self-tests of oracle/ti_emu (the float32 Taichi emulator that executes the reference's source to
 produce tests/golden/ref_*.npz): the Taichi semantics the golden vectors depend on, checked on small
-kernels, plus — when /root/reference is mounted — a regeneration of two vector sections that must
+kernels, plus — when /root/reference is mounted — a regeneration of three vector sections that must
 reproduce the committed files bit for bit."""
 import os
 import subprocess
@@ -109,11 +109,11 @@ def test_dense_fields_with_offsets_and_struct_for(ti):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/renderer"), reason="needs the reference tree (authoring container only)")
 def test_regenerating_vectors_from_the_reference_reproduces_the_committed_files(tmp_path):
-    """make_ref_vectors.py math + bsdf re-run against /root/reference: identical arrays."""
+    """make_ref_vectors.py math + bsdf + reservoir re-run against /root/reference: identical arrays."""
     gold = os.path.join(ROOT, "tests", "golden")
-    before = {n: dict(np.load(os.path.join(gold, n + ".npz"))) for n in ("ref_math", "ref_bsdf")}
+    before = {n: dict(np.load(os.path.join(gold, n + ".npz"))) for n in ("ref_math", "ref_bsdf", "ref_reservoir")}
     env = dict(os.environ)
-    r = subprocess.run([sys.executable, os.path.join(gold, "make_ref_vectors.py"), "math", "bsdf"], capture_output=True, text=True, env=env,
+    r = subprocess.run([sys.executable, os.path.join(gold, "make_ref_vectors.py"), "math", "bsdf", "reservoir"], capture_output=True, text=True, env=env,
                        timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     for n, old in before.items():
