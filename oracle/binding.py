@@ -54,6 +54,7 @@ def load():
     lib.orc_sample_skybox.argtypes = [P, C.c_int, fp, fp, fp, fp]
     lib.orc_shift_probe.argtypes = [P, C.c_int, fp, fp]
     lib.orc_reservoir_probe.argtypes = [C.c_int, fp, fp]
+    lib.orc_restir_render_probe.argtypes = [P, C.c_int, fp, fp, fp, fp]
     lib.orc_gris_probe.argtypes = [P, C.c_uint32, fp, fp, fp, fp, C.c_int, ip, fp]
     lib.orc_set_tile_shard.argtypes = [P, C.c_int, C.c_int]
     lib.orc_trace_primary.argtypes = [P, P]
@@ -256,6 +257,15 @@ class OracleRenderer:
         out = np.empty((pixels.size, 6), np.float32)
         self._lib.orc_gris_probe(self._h, int(frame), _fp(samples), _fp(gbuf), _fp(col_d), _fp(col_s), pixels.size, _ip(pixels), _fp(out))
         return out
+
+    def restir_render_probe(self, sample):
+        """orc_restir_render_probe: (reservoirs before encode [npx][23], gbuf [npx][7], col_d, col_s) of one sample."""
+        self._sync_camera()
+        npx = self.image_res[0] * self.image_res[1]
+        samples, gbuf = np.empty((npx, 23), np.float32), np.empty((npx, 7), np.float32)
+        col_d, col_s = np.empty((npx, 3), np.float32), np.empty((npx, 3), np.float32)
+        self._lib.orc_restir_render_probe(self._h, int(sample), _fp(samples), _fp(gbuf), _fp(col_d), _fp(col_s))
+        return samples, gbuf, col_d, col_s
 
     def get_cloud_ambient(self):
         a = np.empty(3, np.float32)

@@ -13,10 +13,11 @@
 // executed through oracle/ti_emu, a float32 Taichi emulator (tests/golden/make_ref_vectors.py ->
 // tests/golden/ref_*.npz -> tests/test_reference_vectors.py: traversal and hit buffers bit-exact,
 // render() per pixel to 3e-5, the static frame loop to 1.4e-6, BSDF to 1.5e-7, sky precompute, the
-// moving-camera filter chain to 5e-3 worst pixel; ReSTIR shift() / reservoir packing / spatial_GRIS
-// bit-exact on inputs free of the zero-vector encodings upstream leaves undefined),
+// moving-camera filter chain to 5e-3 worst pixel; the ReSTIR branch of render() to 7.5e-6, ReSTIR
+// shift() / reservoir packing / spatial_GRIS bit-exact on inputs free of the zero-vector encodings
+// upstream leaves undefined),
 // (2) hand-derived known-answer tests and a brute-force traversal twin (tests/test_oracle_kat.py).
-// The ReSTIR branch of render() that fills the reservoirs is pinned by (2) only (DESIGN.md "ReSTIR pins").
+// Only the holes of the upstream ReSTIR mode (DESIGN.md "ReSTIR pins") are pinned by (2) alone.
 #include <omp.h>
 
 #include <algorithm>
@@ -1352,6 +1353,34 @@ void orc_gris_probe(void* p, uint32_t frame, const float* samples, const float* 
     float* o = out + 6 * k;
     o[0] = d.x, o[1] = d.y, o[2] = d.z, o[3] = s.x, o[4] = s.y, o[5] = s.z;
   }
+}
+// The ReSTIR branch of render() (pathtracer.py:355-632 with USE_RESTIR_PT = True) for every pixel of
+// one sample: the reservoir BEFORE encode() (23 floats: the 21-float sample layout of
+// orc_reservoir_probe + M + W), the G-buffer entry (7 floats as in orc_gris_probe) and the canonical
+// diffuse / specular integrands.
+void orc_restir_render_probe(void* p, int sample, float* samples, float* gbuf, float* col_d, float* col_s) {
+  Ctx* c = (Ctx*)p;
+  const Scene& s = c->scene;
+  set_jitter(*c, (uint32_t)sample);
+#pragma omp parallel for schedule(dynamic, 2)
+  for (int v = 0; v < s.H; v++)
+    for (int u = 0; u < s.W; u++) {
+      const size_t i = (size_t)v * s.W + u;
+      Reservoir r;
+      GBufferPx g;
+      V3 d, sp;
+      trace_path_restir(*c, u, v, (uint32_t)sample, nullptr, r, g, d, sp);
+      float* a = samples + 23 * i;
+      auto put = [](float* q, V3 x) { q[0] = x.x, q[1] = x.y, q[2] = x.z; };
+      put(a, r.z.F), put(a + 3, r.z.rc_pos), put(a + 6, r.z.rc_normal), put(a + 9, r.z.rc_incident_dir), put(a + 12, r.z.rc_incident_L),
+          put(a + 15, r.z.rc_NEE_dir);
+      std::memcpy(a + 18, &r.z.rc_mat_info, 4);
+      a[19] = r.z.cached_jacobian_term, a[20] = (float)r.z.lobes, a[21] = r.M, a[22] = r.weight;
+      float* q = gbuf + 7 * i;
+      put(q, g.position), q[3] = g.n_oct[0], q[4] = g.n_oct[1], q[6] = g.sky ? 1.0f : 0.0f;
+      std::memcpy(q + 5, &g.mat_info, 4);
+      put(col_d + 3 * i, d), put(col_s + 3 * i, sp);
+    }
 }
 // sample_skybox (atmos.py:94-115) with the three jitter numbers supplied
 void orc_sample_skybox(void* p, int n, const float* d, const float* jitter, float* scat, float* trans) {

@@ -5,12 +5,13 @@
 //   renderer/pathtracer.py:672-812         shift() (reconnection shift + Jacobian)
 //   renderer/pathtracer.py:815-989         spatial_GRIS (32-tap golden-angle spiral, pairwise MIS)
 //
-// PARITY: shift(), the reservoir bookkeeping / packing and spatial_GRIS are pinned BIT-IDENTICALLY
-// against the reference source run through oracle/ti_emu (tests/golden/ref_{shift,reservoir,gris}.npz)
-// on inputs with non-zero sample vectors and no sky pixels. UNPINNED: what the
-// upstream mode (compiled out, USE_RESTIR_PT = False) leaves undefined — octahedral encodings of
-// zero vectors = 0/0, out-of-image taps, sky pixels processed with NaN normals — and the ReSTIR
-// branch of render(). This file states the INTENDED algorithm with those holes pinned:
+// PARITY: the ReSTIR branch of render() (reservoir before packing: 7.5e-6), shift() (Jacobian
+// identical), the reservoir bookkeeping / packing and spatial_GRIS (both BIT-IDENTICAL) are pinned
+// against the reference source run through oracle/ti_emu (tests/golden/ref_{restir_render,shift,
+// reservoir,gris}.npz), the last three on inputs with non-zero sample vectors and no sky pixels.
+// UNPINNED: only what the upstream mode (compiled out, USE_RESTIR_PT = False) leaves
+// undefined — octahedral encodings of zero vectors = 0/0, out-of-image taps, sky pixels processed
+// with NaN normals. This file states the INTENDED algorithm with those holes pinned:
 //   * the "zero vector" markers of a Sample (escape vertex / last vertex / NEE invisible) travel
 //     through the packed reservoir as explicit flag bits (the spare byte of the 56-byte record);
 //   * primary-sky pixels pass their own sample through (the is_vec_zero(center_x1) branch);

@@ -907,6 +907,95 @@ def section_gris():
     np.savez_compressed(os.path.join(HERE, "ref_gris.npz"), **out)
 
 
+# ------------------------------------------------------------------------- render(), ReSTIR branch
+def section_restir_render():
+    """Renderer.render() with USE_RESTIR_PT = True (pathtracer.py:15,355-632): the branch that builds
+    each pixel's input reservoir (reconnection vertex bookkeeping :405-520, the NEE-vs-BSDF RIS at
+    the primary vertex :556-605) and writes the G-buffer and the canonical integrands. The module
+    constant is switched on for this section; Reservoir.encode is intercepted, so what is stored is
+    the reservoir BEFORE packing (zero-vector markers are exact zeros there, no 0/0 encodings).
+    ti.random(): the path dimensions of section_render plus dimension 40 for input_sample's draw."""
+    sys.path.insert(0, ROOT)
+    import renderer.pathtracer as pt
+    from renderer.reservoir import Reservoir, StorageReservoir
+    from voxel_rt2_b200.camera import default_camera_matrices
+
+    W, H, R, seed, n_samples, S = 32, 16, 32, 59, 2, 16
+    cfg = dict(voxel_edges=0.06, light_dir=(1.0, 1.0, 0.4), light_cone=0.06, light_color=(1.2, 1.1, 0.9), floor_height=-0.55,
+               floor_color=(0.8, 0.75, 0.7), floor_material=1, background=(0.25, 0.35, 0.55))
+    mat, col = render_scene(R, 6)
+    r = make_reference_renderer(W, H, R, mat, col, cfg)
+    sc, tr = synthetic_sky_tables(S)
+    r.use_physical_atmosphere[None] = 1
+    r.atmos.skybox_res = ti.Vector([S, S])
+    r.atmos.skybox_fres = ti.Vector([1.0 / S, 1.0 / S])
+    r.atmos.skybox_scattering = ti.Vector.field(3, dtype=ti.f32, shape=(S, S))
+    r.atmos.skybox_transmittance = ti.Vector.field(3, dtype=ti.f32, shape=(S, S))
+    r.atmos.skybox_scattering.arr[...] = sc
+    r.atmos.skybox_transmittance.arr[...] = tr
+    pos, view, proj = default_camera_matrices(W, H, pos=(0.9, 0.8, 1.9))
+    set_reference_camera(r, pos, view, proj)
+    tex = r.world.voxel_color_texture
+    npx = W * H
+    state = {"sample": 0, "count": {}}
+    path_source = path_random_source(W, seed, state)
+    captured = {}
+
+    def source(name, frame):
+        if name == "input_sample":
+            f = frame
+            while f.f_code.co_name != "render":
+                f = f.f_back
+            return sampler_rnd(int(f.f_locals["v"]) * W + int(f.f_locals["u"]), state["sample"], seed, 40)
+        return path_source(name, frame)
+
+    def capture(self):
+        f = sys._getframe(1)
+        while f.f_code.co_name != "render":
+            f = f.f_back
+        z = self.z
+        row = np.zeros(23, np.float32)
+        row[0:3], row[3:6], row[6:9], row[9:12] = z.F.data, z.rc_pos.data, z.rc_normal.data, z.rc_incident_dir.data
+        row[12:15], row[15:18] = z.rc_incident_L.data, z.rc_NEE_dir.data
+        row[18:19] = np.array([z.rc_mat_info], np.uint32).view(np.float32)
+        row[19], row[20], row[21], row[22] = z.cached_jacobian_term, float(z.lobes), self.M, self.weight
+        captured[int(f.f_locals["v"]) * W + int(f.f_locals["u"])] = row
+        return StorageReservoir()
+
+    samples = np.zeros((n_samples, npx, 23), np.float32)
+    gbuf = np.zeros((n_samples, npx, 7), np.float32)
+    col_d = np.zeros((n_samples, npx, 3), np.float32)
+    col_s = np.zeros((n_samples, npx, 3), np.float32)
+    saved_encode, saved_flag = Reservoir.encode, pt.USE_RESTIR_PT
+    Reservoir.encode, pt.USE_RESTIR_PT = capture, True
+    ti.set_random_source(source, with_frame=True)
+    try:
+        with np.errstate(all="ignore"):
+            for s in range(n_samples):
+                state["sample"], state["count"] = s, {}
+                captured.clear()
+                r.render(tex)
+                assert len(captured) == npx
+                for i in range(npx):
+                    u, v = i % W, i // W
+                    samples[s, i] = captured[i]
+                    gbuf[s, i, 0:3] = r.gbuff_position.arr[u, v]
+                    gbuf[s, i, 3:5] = r.gbuff_normals.arr[u, v].astype(np.float32)
+                    gbuf[s, i, 5:6] = np.array([r.gbuff_mat_id.arr[u, v]], np.uint32).view(np.float32)
+                    col_d[s, i], col_s[s, i] = r.color_buffer.arr[u, v], r.color_buffer_specular.arr[u, v]
+                esc = (np.abs(samples[s, :, 6:9]).sum(1) == 0).sum()
+                print("restir render sample %d: %d escape rc vertices, %d NEE-visible, mean W %.3f" % (
+                    s, int(esc), int((np.abs(samples[s, :, 15:18]).sum(1) > 0).sum()), float(np.nanmean(samples[s, :, 22]))))
+    finally:
+        ti.set_random_source(None)
+        Reservoir.encode, pt.USE_RESTIR_PT = saved_encode, saved_flag
+    out = dict(material=mat, color=col, cam_pos=pos, view=view, proj=proj, seed=np.int32(seed), W=np.int32(W), H=np.int32(H),
+               sky_res=np.int32(S), sky_scatter=sc, sky_trans=tr, samples=samples, gbuf=gbuf, col_d=col_d, col_s=col_s)
+    for k, v in cfg.items():
+        out["cfg_" + k] = np.asarray(v, np.float32)
+    np.savez_compressed(os.path.join(HERE, "ref_restir_render.npz"), **out)
+
+
 # ------------------------------------------------------------------------- atmos.py (sky)
 def section_sky():
     """renderer/atmos.py: (1) 640 entries of the transmittance LUT from generate_transmittance_lut,
@@ -1017,7 +1106,7 @@ def section_sky():
 
 
 SECTIONS = {"raytrace": section_raytrace, "math": section_math, "bsdf": section_bsdf, "render": section_render, "frame": section_frame,
-            "shift": section_shift, "voxel": section_voxel, "moving": section_moving, "example1": section_example1, "sky": section_sky, "reservoir": section_reservoir, "gris": section_gris}
+            "shift": section_shift, "voxel": section_voxel, "moving": section_moving, "example1": section_example1, "sky": section_sky, "reservoir": section_reservoir, "gris": section_gris, "restir_render": section_restir_render}
 
 if __name__ == "__main__":
     for s in (sys.argv[1:] or list(SECTIONS)):

@@ -613,6 +613,40 @@ def test_cuda_matches_reference_source_frame_loop(vrt):
     assert np.abs(ldr[..., :3] - z["ldr"][..., :3]).max() < 5e-3
 
 
+def test_cuda_restir_reservoirs_match_reference_source(vrt):
+    """The reservoirs the CUDA path kernel packs in ReSTIR mode against the reference's own
+    render() with USE_RESTIR_PT = True (tests/golden/ref_restir_render.npz holds every pixel's
+    reservoir before packing): material info, lobes, M and the zero-vector markers (escape vertex /
+    last vertex / NEE visible, our flag bits) identical on >= 99 % of the pixels, F / rc_pos / rc_L
+    within 1e-3 and the f16 W within 3e-3 on >= 97 % of those (the rest are discrete decisions
+    flipped by float rounding, as in test_restir_reservoirs_match_oracle)."""
+    import os
+
+    from util import renderer_from_reference_fixture
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_restir_render.npz"))
+    g = renderer_from_reference_fixture(vrt.Renderer, z)
+    g.set_use_physical_sky(True, False)
+    g.set_sky_tables(z["sky_scatter"], z["sky_trans"])
+    g.prepare_data()
+    g.accumulate_restir(1)
+    a = _unpack_reservoirs(g.get_reservoirs()).reshape(-1)
+    ref = z["samples"][0]
+    sky = np.abs(z["gbuf"][0][:, :3]).sum(1) == 0
+    flags = ((np.abs(ref[:, 6:9]).sum(1) == 0) * 1 + (np.abs(ref[:, 9:12]).sum(1) == 0) * 2 + (np.abs(ref[:, 15:18]).sum(1) > 0) * 4).astype(np.uint8)
+    same = (a["mat"] == ref[:, 18].view(np.uint32)) & (a["lobes"] == ref[:, 20].astype(np.int8)) & (a["flags"] == flags) & (a["M"] == ref[:, 21])
+    print("identical integer fields: %.4f (%.4f off the sky)" % (same.mean(), same[~sky].mean()))
+    assert same.mean() > 0.99
+    for f, c in (("F", 0), ("rc_pos", 3), ("L", 12)):
+        x, y = a[f][same].astype(np.float64), ref[same, c:c + 3].astype(np.float64)
+        close = np.all(np.abs(x - y) <= 1e-3 * np.maximum(np.abs(y), 1e-3) + 1e-5, axis=-1)
+        print(f, "close fraction %.4f" % close.mean())
+        assert close.mean() > 0.97
+    w, wr = a["W"][same].astype(np.float64), ref[same, 22].astype(np.float64)
+    fin = np.isfinite(w) & np.isfinite(wr) & (wr < 6e4)
+    assert np.mean(np.abs(w[fin] - wr[fin]) <= 3e-3 * np.maximum(np.abs(wr[fin]), 1e-2)) > 0.97
+
+
 def test_cuda_sky_precompute_matches_reference_source_vectors(vrt):
     """CUDA sky precompute (LUT, cloud accumulation, skybox) against the tables the reference's own
     atmos.py produced through the emulator on a 6 x 6 grid (tests/golden/ref_sky.npz; same per-texel

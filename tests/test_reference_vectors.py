@@ -301,6 +301,49 @@ def test_restir_spatial_gris_matches_reference(oracle):
     assert _close(got, ref, 1e-5, 1e-7).all(), (np.abs(got - ref) / (np.abs(ref) + 1e-6)).max()  # measured: identical bits
 
 
+def test_restir_render_branch_matches_reference(oracle):
+    """Renderer.render() with USE_RESTIR_PT = True (pathtracer.py:355-632) run by the reference
+    source, Reservoir.encode intercepted so the fixture holds every pixel's reservoir BEFORE packing
+    (the zero-vector markers are exact zeros there): reconnection vertex, incident direction /
+    radiance, NEE direction, lobes, cached Jacobian term, the NEE-vs-BSDF RIS at the primary vertex
+    (M, W, which sample was kept), the G-buffer and the canonical integrands agree per pixel for two
+    samples (measured 7.5e-6 worst). Sky pixels: upstream stores the octahedral encoding of a zero
+    normal (NaN, recorded in the fixture); the oracle stores zeros and a flag."""
+    from util import renderer_from_reference_fixture
+    from voxel_rt2_b200.materials import material_table
+
+    z = np.load(os.path.join(G, "ref_restir_render.npz"))
+    o = renderer_from_reference_fixture(oracle.OracleRenderer, z, materials=material_table())
+    o.set_use_physical_sky(True, False)
+    o.set_sky_tables(z["sky_scatter"], z["sky_trans"])
+    o.prepare_data()
+    for s in range(z["samples"].shape[0]):
+        sm, gb, cd, cs = o.restir_render_probe(s)
+        ref, g = z["samples"][s], z["gbuf"][s]
+        # exact parts: material info bits, lobes, M, zero-vector markers, geometric normals / sun directions
+        assert (sm[:, 18].view(np.uint32) == ref[:, 18].view(np.uint32)).all()
+        assert (sm[:, 20:22] == ref[:, 20:22]).all()
+        for k in (6, 9, 15):
+            assert ((np.abs(sm[:, k:k + 3]).sum(1) == 0) == (np.abs(ref[:, k:k + 3]).sum(1) == 0)).all(), k
+        assert (sm[:, 6:9] == ref[:, 6:9]).all() and (sm[:, 15:18] == ref[:, 15:18]).all()
+        # the cached Jacobian term of an escape vertex divides by |N| = 0 on both sides
+        assert (np.isfinite(sm) == np.isfinite(ref)).all()
+        fin = np.isfinite(ref)
+        cols = [c for c in range(23) if c != 18]
+        assert _close(sm[:, cols][fin[:, cols]], ref[:, cols][fin[:, cols]], 5e-5, 1e-6).all()
+        sky = gb[:, 6] == 1
+        assert (sky == (np.abs(g[:, :3]).sum(1) == 0)).all() and 20 < sky.sum() < 200
+        assert np.isnan(g[sky, 3:5]).all() and (gb[sky, 3:5] == 0).all()
+        assert (gb[:, :3] == g[:, :3]).all() and (gb[~sky, 3:5] == g[~sky, 3:5]).all()
+        assert (gb[:, 5].view(np.uint32) == g[:, 5].view(np.uint32)).all()
+        assert _close(cd, z["col_d"][s], 5e-5, 1e-6).all() and _close(cs, z["col_s"][s], 5e-5, 1e-6).all()
+        # coverage: escape and surface reconnection vertices, terminated paths, both outcomes of the RIS
+        surf = np.abs(ref[:, 6:9]).sum(1) > 0
+        assert surf.sum() > 80 and (surf & (np.abs(ref[:, 9:12]).sum(1) == 0)).sum() > 5 and (np.abs(ref[:, 15:18]).sum(1) > 0).sum() > 30
+        nee_kept = (~sky) & (ref[:, 20] == 99)  # LOBE_ALL * 10 + LOBE_ALL (bsdf.py:20) marks the light sample
+        assert nee_kept.sum() > 20 and ((~sky) & ~nee_kept).sum() > 100
+
+
 def test_config1_example1_hit_buffer_matches_reference(oracle):
     """BASELINE config 1 at 64 x 64: the example1.py scene in the Renderer exactly as shipped (128^3
     grid built by the reference's _update_lods / _make_texture), primary ray + sun shadow ray per
