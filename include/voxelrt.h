@@ -146,6 +146,16 @@ int vrt_accumulate_moving(vrt_ctx* ctx, int32_t sample, float render_scale, floa
 /* Packed reservoirs of the last ReSTIR frame: 56 bytes per pixel, row-major (reservoir.py:8-19
  * field order; byte 55 carries the escape / last-vertex / NEE-visible flags). */
 int vrt_get_reservoirs(vrt_ctx* ctx, void* out56_per_pixel);
+/* Renderer.spatial_GRIS(0, 24.0, 32, 1) (pathtracer.py:815-989, the call of accumulate() :1313) on
+ * caller-supplied per-pixel buffers instead of the ones the path kernel wrote: packed reservoirs
+ * (56 B each, the layout of vrt_get_reservoirs; spatial_reservoirs :108), gpos = float4 (primary
+ * position, sky flag; gbuff_position :116), gattr = 2 x u32 (octahedral f16x2 primary normal,
+ * packed material info; gbuff_normals / gbuff_mat_id :112-113), col_d / col_s = float4 canonical
+ * integrands (color_buffer / color_buffer_specular :39-40). frame = current_frame. The pass adds
+ * its result to the accumulation buffer like a rendered frame. Host pointers, row-major; the parity
+ * tests use it to hold the resampling kernel to reference-derived vectors. */
+int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs56, const float* gpos4, const uint32_t* gattr2, const float* col_d4,
+                     const float* col_s4);
 
 /* Only pixels in 8x4 tiles with tile_id % n == rank are rendered (tile sharding). Default 0,1. */
 int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n);

@@ -630,13 +630,7 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
   return VRT_OK;
 }
 
-int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, int32_t stride) {
-  if (!ctx) return VRT_ERR_BAD_ARG;
-  REQUIRE(n_frames > 0 && stride > 0 && first_sample >= 0, "vrt_accumulate_restir: bad sample range");
-  REQUIRE(ctx->tile_n == 1, "vrt_accumulate_restir: tile sharding needs a 24-pixel halo (not implemented); use sample sharding");
-  int rc = check_ready(ctx, "vrt_accumulate_restir");
-  if (rc) return rc;
-  CK(cudaSetDevice(ctx->device));
+static int ensure_restir_buffers(vrt_ctx* ctx) {
   const size_t npx = (size_t)ctx->cfg.width * ctx->cfg.height;
   if (!ctx->rb.reservoirs) {
     CK(cudaMalloc(&ctx->rb.reservoirs, npx * 56));
@@ -645,6 +639,18 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
     CK(cudaMalloc(&ctx->rb.col_d, npx * sizeof(float4)));
     CK(cudaMalloc(&ctx->rb.col_s, npx * sizeof(float4)));
   }
+  return VRT_OK;
+}
+
+int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, int32_t stride) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(n_frames > 0 && stride > 0 && first_sample >= 0, "vrt_accumulate_restir: bad sample range");
+  REQUIRE(ctx->tile_n == 1, "vrt_accumulate_restir: tile sharding needs a 24-pixel halo (not implemented); use sample sharding");
+  int rc = check_ready(ctx, "vrt_accumulate_restir");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_restir_buffers(ctx);
+  if (rc) return rc;
   if (ctx->jitter_cap < 1) {
     CK(cudaMalloc(&ctx->d_jitter, sizeof(float2)));
     ctx->jitter_cap = 1;
@@ -677,6 +683,37 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
   ctx->stats.last_render_ms = render_ms;
   ctx->stats.last_gris_ms = gris_ms;
   ctx->stats.kernel_launches = 2u * (uint32_t)n_frames;
+  return VRT_OK;
+}
+
+int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs, const float* gpos, const uint32_t* gattr, const float* col_d,
+                     const float* col_s) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(frame >= 0 && reservoirs && gpos && gattr && col_d && col_s, "vrt_spatial_gris: bad arguments");
+  REQUIRE(ctx->tile_n == 1, "vrt_spatial_gris: tile sharding is not supported (taps cross tiles)");
+  int rc = check_ready(ctx, "vrt_spatial_gris");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_restir_buffers(ctx);
+  if (rc) return rc;
+  const size_t npx = (size_t)ctx->cfg.width * ctx->cfg.height;
+  CK(cudaMemcpyAsync(ctx->rb.reservoirs, reservoirs, npx * 56, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->rb.gpos, gpos, npx * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->rb.gattr, gattr, npx * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->rb.col_d, col_d, npx * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->rb.col_s, col_s, npx * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  Params P;
+  fill_params(ctx, P);
+  P.first_sample = frame, P.n_samples = 1, P.stride = 1;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(vrt_launch_gris(P, ctx->rb, (uint32_t)frame, ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the host buffers may be freed on return
+  float ms = 0.0f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->stats.last_render_ms = 0.0f;
+  ctx->stats.last_gris_ms = ms;
+  ctx->stats.kernel_launches = 1u;
   return VRT_OK;
 }
 

@@ -252,6 +252,23 @@ class Renderer:
         self._check(self._lib.vrt_get_reservoirs(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def spatial_gris(self, frame, reservoirs, gpos, gattr, col_d, col_s):
+        """Renderer.spatial_GRIS(0, 24.0, 32, 1) (pathtracer.py:815-989) on caller-supplied buffers
+        (see vrt_spatial_gris in include/voxelrt.h): reservoirs uint8 [H, W, 56], gpos float32
+        [H, W, 4], gattr uint32 [H, W, 2], col_d / col_s float32 [H, W, 4]. The result is added to
+        the accumulation buffer like a rendered frame."""
+        W, H = self.image_res
+        self._sync_camera()
+        bufs = []
+        for a, dt, shape in ((reservoirs, np.uint8, (H, W, 56)), (gpos, np.float32, (H, W, 4)), (gattr, np.uint32, (H, W, 2)),
+                             (col_d, np.float32, (H, W, 4)), (col_s, np.float32, (H, W, 4))):
+            a = np.ascontiguousarray(a, dt)
+            if a.shape != shape:
+                raise ValueError("spatial_gris: expected %s of shape %s, got %s" % (np.dtype(dt).name, shape, a.shape))
+            bufs.append(a)
+        self._check(self._lib.vrt_spatial_gris(self._h, int(frame), *[b.ctypes.data_as(C.c_void_p) for b in bufs]))
+        self.current_spp += 1
+
     def reset_framebuffer(self):  # pathtracer.py:664-668
         self.current_spp = 0
         self._check(self._lib.vrt_reset(self._h))
