@@ -222,7 +222,7 @@ void vrt_destroy(vrt_ctx* ctx) {
   cudaFree(ctx->d_jitter), cudaFree(ctx->d_work), cudaFree(ctx->d_stats);
   cudaFree(ctx->mv.col_d), cudaFree(ctx->mv.col_s), cudaFree(ctx->mv.out), cudaFree(ctx->mv.full), cudaFree(ctx->mv.refl), cudaFree(ctx->mv.refl_blur);
   for (int k = 0; k < 2; k++) cudaFree(ctx->mv.hd[k]), cudaFree(ctx->mv.hs[k]), cudaFree(ctx->mv.hsd[k]), cudaFree(ctx->mv.depth[k]), cudaFree(ctx->mv.attr[k]);
-  cudaFree(ctx->rb.reservoirs), cudaFree(ctx->rb.gpos), cudaFree(ctx->rb.gattr), cudaFree(ctx->rb.col_d), cudaFree(ctx->rb.col_s);
+  cudaFree(ctx->rb.reservoirs), cudaFree(ctx->rb.gpos), cudaFree(ctx->rb.gattr), cudaFree(ctx->rb.col_d), cudaFree(ctx->rb.col_s), cudaFree(ctx->rb.rc_skyT);
   if (ctx->copy_pending) cudaEventSynchronize(ctx->ev_copied);
   if (ctx->ev_resolved) cudaEventDestroy(ctx->ev_resolved);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
@@ -638,6 +638,7 @@ static int ensure_restir_buffers(vrt_ctx* ctx) {
     CK(cudaMalloc(&ctx->rb.gattr, npx * sizeof(uint2)));
     CK(cudaMalloc(&ctx->rb.col_d, npx * sizeof(float4)));
     CK(cudaMalloc(&ctx->rb.col_s, npx * sizeof(float4)));
+    CK(cudaMalloc(&ctx->rb.rc_skyT, npx * sizeof(float4)));
   }
   return VRT_OK;
 }
@@ -682,7 +683,7 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
   }
   ctx->stats.last_render_ms = render_ms;
   ctx->stats.last_gris_ms = gris_ms;
-  ctx->stats.kernel_launches = 2u * (uint32_t)n_frames;
+  ctx->stats.kernel_launches = 3u * (uint32_t)n_frames;  // k_path, k_rc_sky, k_gris
   return VRT_OK;
 }
 
@@ -713,7 +714,7 @@ int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs, const 
   CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   ctx->stats.last_render_ms = 0.0f;
   ctx->stats.last_gris_ms = ms;
-  ctx->stats.kernel_launches = 1u;
+  ctx->stats.kernel_launches = 2u;  // k_rc_sky, k_gris
   return VRT_OK;
 }
 

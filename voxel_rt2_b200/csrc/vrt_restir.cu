@@ -39,8 +39,6 @@ struct GrisCtx {
   const float* unorm8;
   f3 cam_pos, light_dir, sun_rad;
   float light_cos_max, light_pdf_axis;
-  int use_sky, sky_res;
-  const float4* sky_trans;
 };
 
 HD Mat decode_material(const GrisCtx& G, uint32_t enc, int& mat_id) {  // math_utils.py:238-247
@@ -55,23 +53,22 @@ HD Mat decode_material(const GrisCtx& G, uint32_t enc, int& mat_id) {  // math_u
 struct RcPre {   // reconnection vertex of a sample (pathtracer.py:676-689)
   Mat rc_mat;
   int rc_mat_id;
-  f3 tang, bitang, sky_T;
-  bool esc, last, nee, sky_ready;
+  f3 tang, bitang;
+  const float4* sky_T;  // this reservoir's entry of RestirBuffers::rc_skyT (loaded only if the shift survives the early-out)
+  bool esc, last, nee;
 };
 struct DstPre {  // primary vertex the sample is shifted to (pathtracer.py:731-733)
   f3 tang, bitang, view;
 };
-HD f3 rc_sky_T(const GrisCtx& G, const RSample& z) {
-  return sky_fetch(G.sky_trans, sky_tap(G.sky_res, project_sky(z.rc_NEE_dir, 1.0f / (float)G.sky_res)));
+HD f3 rc_sky_T(const float4* sky_trans, int sky_res, const RSample& z) {  // shift(), pathtracer.py:780
+  return sky_fetch(sky_trans, sky_tap(sky_res, project_sky(z.rc_NEE_dir, 1.0f / (float)sky_res)));
 }
-HD RcPre prep_rc(const GrisCtx& G, const RSample& z, bool fetch_sky) {
+HD RcPre prep_rc(const GrisCtx& G, const RSample& z, const float4* sky_T) {
   RcPre r;
   r.esc = is_vec_zero(z.rc_normal), r.last = is_vec_zero(z.rc_incident_dir), r.nee = !is_vec_zero(z.rc_NEE_dir);
   make_orthonormal_basis(z.rc_normal, r.tang, r.bitang);
   r.rc_mat = decode_material(G, z.rc_mat_info, r.rc_mat_id);
-  r.sky_T = mk3(1.0f);
-  r.sky_ready = fetch_sky || !(r.nee && !r.esc && G.use_sky);
-  if (fetch_sky && r.nee && !r.esc && G.use_sky) r.sky_T = rc_sky_T(G, z);
+  r.sky_T = sky_T;
   return r;
 }
 HD DstPre prep_dst(const GrisCtx& G, f3 dst_pos, f3 dst_normal) {
@@ -115,7 +112,8 @@ HD void shift_sample(const GrisCtx& G, f3 dst_pos, f3 dst_normal, const Mat& dst
     eval_and_pdf(R.rc_mat, -dir, z.rc_normal, z.rc_NEE_dir, R.tang, R.bitang, bd, bs, lpdf);
     const f3 rc_nee_brdf = (bd + bs) * saturate(dot(z.rc_normal, z.rc_NEE_dir));
     const float w = power_heuristic(G.light_pdf_axis, lpdf);
-    const f3 sky_T = R.sky_ready ? R.sky_T : rc_sky_T(G, z);  // neighbours: fetched only if the shift survives the early-out
+    const float4 t4 = __ldg(R.sky_T);  // looked up once per reservoir by k_rc_sky (1,1,1 without the physical sky)
+    const f3 sky_T{t4.x, t4.y, t4.z};
     contrib += firefly_filter((w * rc_nee_brdf) * sky_T * G.sun_rad);
   }
   if (R.rc_mat_id == 2) contrib += R.rc_mat.base_col;
@@ -135,6 +133,24 @@ HD void load_reservoir(const uint2* __restrict__ base, size_t pidx, const float*
     w[2 * i] = t.x, w[2 * i + 1] = t.y;
   }
   decode_reservoir(w, unorm8, r);
+}
+
+// Sun transmittance at every reservoir's reconnection vertex (the sample_skybox_transmittance call
+// of shift(), pathtracer.py:780). shift() runs up to 64 times per pixel in spatial_GRIS but the
+// value depends on the reservoir alone, so it is looked up once per pixel here, between the path
+// kernel and k_gris, which then reads 16 bytes per surviving tap instead of projecting the
+// direction and fetching four texels of the 236 MB table.
+__global__ void __launch_bounds__(128) k_rc_sky(const __grid_constant__ Params P, RestirBuffers RB) {
+  __shared__ float s_unorm[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = xdiv((float)i, 255.0f);
+  __syncthreads();
+  const size_t pidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= (size_t)P.W * P.H) return;
+  RReservoir r;
+  load_reservoir(RB.reservoirs, pidx, s_unorm, r);
+  f3 T = mk3(1.0f);
+  if (P.use_sky && !is_vec_zero(r.z.rc_NEE_dir) && !is_vec_zero(r.z.rc_normal)) T = rc_sky_T(P.sky_trans, P.sky_res, r.z);
+  RB.rc_skyT[pidx] = make_float4(T.x, T.y, T.z, 0.0f);
 }
 
 #ifndef VRT_GRIS_MIN_BLOCKS
@@ -166,7 +182,6 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
   G.mats = s_mats, G.unorm8 = s_unorm;
   G.cam_pos = P.cam_pos, G.light_dir = P.light_dir, G.sun_rad = P.light_weight * P.light_color;
   G.light_cos_max = P.light_cos_max, G.light_pdf_axis = cone_sample_pdf(P.light_cos_max, 1.0f);
-  G.use_sky = P.use_sky, G.sky_res = P.sky_res, G.sky_trans = P.sky_trans;
 
   const float max_radius = 24.0f;
   const int max_taps = 32;
@@ -194,7 +209,7 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
     float canonical_mis_weight = 1.0f;
     f3 chosen_F_d = mk3(0.0f), chosen_F_s = mk3(0.0f);
     const float center_F_lum = luminance(center.z.F);
-    const RcPre center_rc = prep_rc(G, center.z, true);
+    const RcPre center_rc = prep_rc(G, center.z, RB.rc_skyT + pidx);
     const DstPre center_dst = prep_dst(G, center_x1, center_n1);
     // The tap loop is split in two so that each loop body inlines ONE copy of shift() (~17 KB of
     // BSDF code): with both shifts in one body the loop was 40 KB, beyond the SM's instruction
@@ -240,7 +255,7 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
       load_reservoir(RB.reservoirs, (size_t)ti, s_unorm, nb);
       f3 s_d, s_s;
       float jacobian;
-      shift_sample(G, center_x1, center_n1, center_mat, center_dst, nb, prep_rc(G, nb.z, false), s_d, s_s, jacobian);
+      shift_sample(G, center_x1, center_n1, center_mat, center_dst, nb, prep_rc(G, nb.z, RB.rc_skyT + tap_index[i]), s_d, s_s, jacobian);
       const float center_p_hat = tap_center_p_hat[i];
       float canonical_weight = center_p_hat * nb.M;
       canonical_weight = canonical_weight / (center_p_hat * nb.M + center_F_lum * center.M / (float)max_taps);
@@ -312,6 +327,7 @@ cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t f
   size_t sm = vrt_render_smem_bytes(P, &uis);
   const int fixed_words = 128 * MAT_ROW_F4 * 4 + 256;
   int blocks = (P.n_tiles * 32 + 127) / 128;
+  k_rc_sky<<<(P.W * P.H + 127) / 128, 128, 0, st>>>(P, RB);
   k_gris<<<blocks, 128, sm, st>>>(P, RB, frame, uis, fixed_words);
   return cudaGetLastError();
 }

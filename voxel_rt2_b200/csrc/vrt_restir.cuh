@@ -102,6 +102,7 @@ struct RestirBuffers {
   uint2* gattr;
   float4* col_d;
   float4* col_s;
+  float4* rc_skyT;  // sun transmittance at the reservoir's reconnection vertex (k_rc_sky), read by k_gris
 };
 
 // Outputs of the moving-camera variant of the path kernel (pathtracer.py:535-546,628-632).
