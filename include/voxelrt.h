@@ -62,7 +62,8 @@ typedef struct vrt_hit {
                        2 back-facing: no ray, 3 n/a); 16-23 material id; 24-31 is_light */
 } vrt_hit;
 
-/* Counters of the last vrt_accumulate with stats enabled. */
+/* Counters of the last vrt_accumulate with stats enabled, device times, launch counts.
+ * vrt_get_stats waits for the asynchronous launches still in flight before it answers. */
 typedef struct vrt_stats {
   uint64_t paths, rays, steps, queries, hits, sky_escapes, nee_visible, vertices;
   float last_render_ms;   /* device time of the path kernel(s) in the last vrt_accumulate */
@@ -70,6 +71,10 @@ typedef struct vrt_stats {
   float sky_precompute_ms;
   uint32_t kernel_launches; /* kernels launched by the last vrt_accumulate */
   float last_gris_ms;       /* device time of the spatial resampling kernel(s), ReSTIR mode */
+  float render_ms_sum;      /* device time of all vrt_accumulate path-kernel launches since the previous vrt_get_stats */
+  uint32_t render_launches; /* ... and how many launches that sum covers */
+  uint32_t launches_total;  /* kernels launched by the library since the previous vrt_get_stats */
+  float last_temporal_ms;   /* device time of the temporal reservoir reuse kernel(s), ReSTIR mode */
 } vrt_stats;
 
 /* Renderer.__init__ (pathtracer.py:28-136) */
@@ -127,7 +132,9 @@ int vrt_get_trans_lut(vrt_ctx* ctx, uint16_t* lut);
 int vrt_trace_primary(vrt_ctx* ctx, vrt_hit* out);
 
 /* Renderer.accumulate (pathtracer.py:1310-1319) for sample indices first, first+stride, ...
- * (n_samples of them). stats != 0 also fills the counters. */
+ * (n_samples of them). stats != 0 also fills the counters (and then waits for the launch). With
+ * stats == 0 the call is asynchronous: it enqueues the batch on the context's stream and returns;
+ * the fetch / stats / synchronize calls wait as needed. */
 int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_t stride, int32_t stats);
 
 /* Renderer.accumulate with USE_RESTIR_PT = True (pathtracer.py:15,1310-1319): per frame, render
@@ -160,8 +167,14 @@ int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs56, cons
 /* Only pixels in 8x4 tiles with tile_id % n == rank are rendered (tile sharding). Default 0,1. */
 int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n);
 
-/* Renderer.reset_framebuffer (pathtracer.py:664-668) */
+/* Renderer.reset_framebuffer (pathtracer.py:664-668). Deferred: if a full-frame vrt_accumulate follows, its
+ * kernel overwrites the buffer (no memset, no read-modify-write); any other use clears it first. */
 int vrt_reset(vrt_ctx* ctx);
+
+/* Two accumulation slots, each with its own image buffer (no upstream counterpart; the reference has one
+ * GPU): every call that reads or writes "the accumulation buffer" / "the image buffer" uses the current slot. With one process per GPU, batch k+1 renders into
+ * one slot while the partial sums of batch k in the other are still being merged by the peers. */
+int vrt_set_accum_slot(vrt_ctx* ctx, int32_t slot);
 
 /* Device pointer of the float4 [height][width] accumulation buffer (rgb sums, w = samples),
  * for device-side collectives (NCCL all-reduce through torch.distributed). */
@@ -177,6 +190,23 @@ int vrt_accum_ipc_handle(vrt_ctx* ctx, void* handle64);
 int vrt_open_peer_accum(vrt_ctx* ctx, const void* handle64, void** peer_ptr);
 int vrt_close_peer_accum(vrt_ctx* ctx, void* peer_ptr);
 int vrt_fetch_ldr_merged(vrt_ctx* ctx, const void* const* peer_ptrs, int32_t n_peers, float* ldr_rgba);
+/* The same merge spread over the ranks (reduce-scatter + tonemap in ONE kernel): this rank sums its own and
+ * the peers' partial sums (current slot) for pixels [first_pixel, first_pixel + n_pixels) and writes the
+ * tonemapped pixels (_render_to_image, pathtracer.py:634-662) to ldr_dst — a device pointer, typically the
+ * peer mapping of the displaying rank's image buffer (vrt_out_ipc_handle + vrt_open_peer_accum), or NULL
+ * for this context's own image buffer. write_sums != 0 also stores the merged float4 sums back into this
+ * rank's slice of its accumulation buffer. Asynchronous on the context's stream; the caller orders the
+ * ranks (all partial sums complete before, nobody overwrites them until every rank has merged).
+ * vrt_copy_ldr_async then moves the displaying rank's image buffer to pinned host memory as
+ * vrt_fetch_ldr_async does, without running the tonemap pass again. */
+int vrt_out_ipc_handle(vrt_ctx* ctx, void* handle64);
+int vrt_merge_slice(vrt_ctx* ctx, const void* const* peer_ptrs, int32_t n_peers, int32_t first_pixel, int32_t n_pixels, void* ldr_dst,
+                    int32_t write_sums);
+int vrt_copy_ldr_async(vrt_ctx* ctx, float* rgba_pinned);
+/* Device-side ordering for that protocol: work enqueued on the context's stream after this call runs after
+ * the pipelined image copy in flight (the displaying rank calls it before it lets the peers write the next
+ * frame into the image buffer being copied). Does not block the host. */
+int vrt_stream_wait_copy(vrt_ctx* ctx);
 
 /* Renderer.color_buffer after accumulate: mean linear radiance, float4 [height][width]. */
 int vrt_fetch_hdr(vrt_ctx* ctx, float* rgba);

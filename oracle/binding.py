@@ -90,6 +90,8 @@ def load():
     lib.orc_f16_to_f32.argtypes = [C.c_uint16]
     lib.orc_f16_to_f32.restype = C.c_float
     lib.orc_num_threads.restype = C.c_int
+    lib.orc_set_num_threads.argtypes = [C.c_int]
+    lib.orc_set_num_threads.restype = None
     _lib = lib
     return lib
 

@@ -1397,5 +1397,9 @@ float orc_rnd(uint32_t pixel, uint32_t sample, uint32_t seed, uint32_t dim) { re
 uint16_t orc_f32_to_f16(float f) { return f32_to_f16_bits(f); }
 float orc_f16_to_f32(uint16_t h) { return f16_bits_to_f32(h); }
 int orc_num_threads() { return omp_get_max_threads(); }
+// launchers such as torchrun export OMP_NUM_THREADS=1: the CPU baseline legs of bench.py ask for the cores explicitly
+void orc_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
 
 }  // extern "C"

@@ -1003,9 +1003,10 @@ def section_sky():
     compute_skybox, scene.py:243-253) on a 6 x 6 table, ti.random() answering from the oracle's
     per-texel counter sampler (key = (texel, pass), running counter) so tables compare per texel,
     (3) project_sky / unproject_sky / sample_skybox(_transmittance) lookups.
-    The pipeline reads the LUT at arbitrary entries; computing all 32768 through the emulator
-    would take ~45 min, so after (1) the reference's LUT field is filled from the oracle's table
-    (stored in the fixture: lut_full)."""
+    The pipeline reads the LUT at arbitrary entries: after (1) the reference's LUT field is filled
+    with the FULL table the reference's own generate_transmittance_lut produced through the emulator
+    (tests/golden/ref_lut_full.npz, made by make_ref_lut.py in parallel worker processes; stored
+    again in this fixture as lut_full). The oracle side of the comparison uses its own table."""
     sys.path.insert(0, ROOT)
     from oracle import binding as oracle
     from renderer.atmos import Atmos
@@ -1038,8 +1039,10 @@ def section_sky():
     o.set_directional_light(sun_dir, cone, sun_col)
     o.set_use_physical_sky(True, True)
     o.prepare_data()
-    lut = o.get_trans_lut()
+    lut = np.load(os.path.join(HERE, "ref_lut_full.npz"))["lut"]
+    assert np.array_equal(lut[idx[:, 0], idx[:, 1]].view(np.uint16), out["lut_val"].view(np.uint16))  # same code, same entries
     out["lut_full"] = lut
+    out["lut_oracle_diff"] = np.int32((o.get_trans_lut().view(np.uint16) != lut.view(np.uint16)).any(-1).sum())
     atm.trans_LUT.arr[...] = lut
     atm.skybox_res = ti.Vector([S, S])
     atm.skybox_fres = ti.Vector([1.0 / S, 1.0 / S])

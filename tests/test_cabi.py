@@ -34,7 +34,7 @@ def test_struct_layouts(vrt):
 
     assert C.sizeof(_cabi.vrt_hit) == 32 == HIT_DTYPE.itemsize
     assert C.sizeof(_cabi.vrt_config) == 16 * 4
-    assert C.sizeof(_cabi.vrt_stats) == 8 * 8 + 6 * 4  # 5 x 4-byte fields + tail padding to 8
+    assert C.sizeof(_cabi.vrt_stats) == 8 * 8 + 10 * 4  # 9 x 4-byte fields + tail padding to 8
 
 
 def test_bad_arguments_are_rejected_without_touching_a_device(vrt):

@@ -2,8 +2,9 @@
 
 * primary-hit buffers (kind, voxel cell, face normal, f32 bits of t, shadow bit): bit-exact
 * radiance: the CUDA kernel and the oracle share the sampler specification (same counter RNG,
-  same dimensions), so per-pixel results agree far below Monte-Carlo noise; the tolerances are
-  written next to each assert.
+  same dimensions), so per-pixel results agree far below Monte-Carlo noise; every tolerance is
+  written next to its assert together with the value measured on a B200 (profiles/r0*_gpu_tests.log)
+  and is about ten times that value, so a regression of a per cent fails.
 """
 import numpy as np
 import pytest
@@ -102,7 +103,7 @@ def _check_radiance(g, o, tol_rmse, frac_close):
 
 def test_radiance_city_background_sky(vrt, oracle):
     g, o = _radiance_pair(vrt, oracle, scenes.city(64, seed=0, n=24), R=64, res=(128, 96), spp=16)
-    _check_radiance(g, o, tol_rmse=0.02, frac_close=0.97)
+    _check_radiance(g, o, tol_rmse=5e-6, frac_close=0.9998)  # measured 2.0e-7 / 1.00000
     # counters of the two implementations must tell the same story (early termination of
     # zero-throughput paths lets the GPU trace a few rays fewer)
     cg, co = g.stats(), o.counters()
@@ -113,7 +114,7 @@ def test_radiance_city_background_sky(vrt, oracle):
 
 def test_radiance_material_zoo_all_lobes(vrt, oracle):
     g, o = _radiance_pair(vrt, oracle, scenes.material_zoo(64), R=64, res=(128, 96), spp=16, floor=-1e5)
-    _check_radiance(g, o, tol_rmse=0.05, frac_close=0.93)
+    _check_radiance(g, o, tol_rmse=5e-4, frac_close=0.999)  # measured 4.6e-5 / 0.99992 (one discrete lobe / edge decision flips per ~10^4 pixels)
 
 
 def test_radiance_dense_random_physical_sky(vrt, oracle):
@@ -121,7 +122,7 @@ def test_radiance_dense_random_physical_sky(vrt, oracle):
     light = ((1, 1, 1), 0.025, (1.3, 0.949 * 1.3, 0.937 * 1.3))
     g, o = _radiance_pair(vrt, oracle, scenes.random_grid(64, 0.5, 1234), R=64, res=(128, 96), spp=8, sky=True, sky_res=64,
                           clouds=True, light=light, floor=-1e5)
-    _check_radiance(g, o, tol_rmse=0.02, frac_close=0.97)
+    _check_radiance(g, o, tol_rmse=7e-4, frac_close=0.998)  # measured 6.9e-5 / 0.99984
 
 
 def test_sky_tables_match_oracle(vrt, oracle):
@@ -143,7 +144,7 @@ def test_sky_tables_match_oracle(vrt, oracle):
         rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-4)
         frac = np.mean(rel < 2e-3)
         print(name, "fraction within 2e-3:", frac, "max rel", rel.max())
-        assert frac > 0.99
+        assert frac > 0.997  # measured 0.9990 for both tables (max rel 1.5e-2 / 2.1e-3 on the stochastic cloud sums)
 
 
 def test_tile_and_sample_sharding_merge(vrt, oracle):
@@ -217,23 +218,23 @@ def test_restir_reservoirs_match_oracle(vrt, oracle):
     a, b = _unpack_reservoirs(g.get_reservoirs()), _unpack_reservoirs(o.get_reservoirs())
     same_int = (a["mat"] == b["mat"]) & (a["lobes"] == b["lobes"]) & (a["flags"] == b["flags"]) & (a["M"] == b["M"])
     print("identical integer fields: %.4f" % same_int.mean())
-    assert same_int.mean() > 0.99
+    assert same_int.mean() > 0.999  # measured 1.0000
     for f, tol in (("F", 1e-3), ("rc_pos", 1e-3), ("L", 1e-3)):
         x, y = a[f][same_int].astype(np.float64), b[f][same_int].astype(np.float64)
         fin = np.isfinite(x).all(axis=-1) & np.isfinite(y).all(axis=-1)
         close = np.all(np.abs(x[fin] - y[fin]) <= tol * np.maximum(np.abs(y[fin]), 1e-3) + 1e-5, axis=-1)
         print(f, "close fraction %.4f" % close.mean())
-        assert close.mean() > 0.97
+        assert close.mean() > 0.999  # measured 0.9999 / 1.0000 / 1.0000
     w_a, w_b = a["W"][same_int].astype(np.float64), b["W"][same_int].astype(np.float64)
     fin = np.isfinite(w_a) & np.isfinite(w_b)
-    assert np.mean(np.abs(w_a[fin] - w_b[fin]) <= 2e-3 * np.maximum(np.abs(w_b[fin]), 1e-2)) > 0.97
+    assert np.mean(np.abs(w_a[fin] - w_b[fin]) <= 2e-3 * np.maximum(np.abs(w_b[fin]), 1e-2)) > 0.995
 
 
 def test_restir_radiance_matches_oracle(vrt, oracle):
     """render + spatial_GRIS(0, 24, 32, 1) + accumulation over 4 frames vs the oracle. The 33
     sequential RIS decisions per pixel amplify float differences, so the per-pixel tolerance is
-    looser than in path-tracing mode: >= 85 % of pixels within 1 %, image mean within 1 %,
-    rel-RMSE <= 10 %."""
+    looser than in path-tracing mode: >= 99.5 % of pixels within 1 %, image mean within 0.1 %,
+    rel-RMSE <= 2 % (measured: every pixel, 0.0000)."""
     g, o = _restir_pair(vrt, oracle, scenes.material_zoo(64), R=64, res=(128, 96), frames=4)
     a, b = g.fetch_hdr(), o.fetch_hdr()
     assert np.isfinite(a).all() and (a[..., 3] == 4).all()
@@ -242,9 +243,9 @@ def test_restir_radiance_matches_oracle(vrt, oracle):
     close = np.mean(err <= 1e-2 * scale + 1e-5)
     r = rel_rmse(a, b)
     print("restir: close %.4f rel-RMSE %.4f mean ratio %.4f" % (close, r, a[..., :3].mean() / b[..., :3].mean()))
-    assert close >= 0.85
-    assert r <= 0.10
-    assert abs(a[..., :3].mean() / b[..., :3].mean() - 1.0) < 0.01
+    assert close >= 0.995   # measured 1.0000: a flipped RIS decision changes a whole pixel, none flipped here
+    assert r <= 0.02        # measured 0.0000 (one flipped pixel of 12 288 would read ~1e-2)
+    assert abs(a[..., :3].mean() / b[..., :3].mean() - 1.0) < 1e-3
 
 
 def test_restir_converges_to_path_traced_image(vrt):
@@ -342,7 +343,10 @@ def test_path_depth_parameter(vrt, oracle, depth):
     apply_both(both, "prepare_data")
     g.accumulate(8, stats=True)
     o.accumulate(8, stats=True)
-    _check_radiance(g, o, tol_rmse=0.05, frac_close=0.93)
+    # measured (depth 1 / 2 / 8): 3.6e-7 / 1.00000, 2.9e-2 / 0.99854, 2.3e-2 / 0.98535 — at 64 x 32 pixels one flipped
+    # specular-lobe decision on a mirror-like material (ids 50, 21) is a whole pixel of a 2048-pixel image
+    tol, frac = {1: (5e-6, 0.9995), 2: (0.06, 0.995), 8: (0.06, 0.975)}[depth]
+    _check_radiance(g, o, tol_rmse=tol, frac_close=frac)
     assert g.stats()["rays"] <= 2 * depth * g.stats()["paths"]
 
 
@@ -416,7 +420,7 @@ def test_scene_api_end_to_end_on_gpu(vrt, oracle, tmp_path, monkeypatch):
     ldr_o = o.fetch_image()
     close = np.mean(np.abs(img[..., :3] - ldr_o[..., :3]).max(axis=-1) < 2e-3)
     print("Scene.finish vs oracle: fraction of LDR pixels within 2e-3: %.4f" % close)
-    assert close > 0.97
+    assert close > 0.999  # measured 1.0000
 
 
 # ------------------------------------------------------------------------------ moving camera
@@ -445,7 +449,7 @@ def test_moving_camera_temporal_path_matches_oracle(vrt, oracle):
         close = np.mean(err <= 1e-2 * scale + 1e-5)
         r = rel_rmse(a, b)
         print("frame %d: close %.4f rel-RMSE %.4f" % (k, close, r))
-        assert close >= 0.97 and r <= 0.03
+        assert close >= 0.995 and r <= 0.03  # measured: close 0.9999 ... 0.9987, rel-RMSE 0.0056 ... 0.0014 over the six frames
     # sanity of the restated algorithm itself: the reprojected accumulation is unbiased in the mean
     g2 = vrt.Renderer(dx=2.0 / R, image_res=(128, 80), grid_res=R, sky_res=0, seed=60)
     g2.set_voxels(*scenes.material_zoo(R))
@@ -547,6 +551,65 @@ def test_full_size_properties_1080p_256(vrt):
     assert (np.abs(n).sum(axis=-1) >= 1).all()
 
 
+def _full_size_pair(vrt, oracle, *, R, mat, col, floor, light, voxel_edges, exposure, sky_res, spp, every):
+    """GPU: the whole 1920x1080 frame. Oracle: every `every`-th 8x4 tile of the SAME frame (tile sharding selects
+    pixels, the camera and the per-pixel sample keys are those of the full frame), same sky tables."""
+    import os
+
+    from voxel_rt2_b200.materials import material_table
+
+    W, H = 1920, 1080
+    kw = dict(dx=2.0 / R, image_res=(W, H), grid_res=R, sky_res=sky_res, exposure=exposure, seed=1, voxel_edges=voxel_edges)
+    g = vrt.Renderer(**kw)
+    tex = np.load(os.path.join(os.path.dirname(vrt.__file__), "assets", "cloud_texture.npz"))["tex"]
+    o = oracle.OracleRenderer(materials=material_table(), cloud_tex=tex, **kw)
+    for r in (g, o):
+        r.set_voxels(mat, col)
+        r.set_floor(floor, (1.0, 1.0, 1.0))
+        r.set_directional_light(*light)
+    g.set_use_physical_sky(True, True)
+    g.prepare_data()
+    o.set_use_physical_sky(True, True)
+    o.set_sky_tables(*g.get_sky_tables())   # the 3840^2 precompute is not a CPU job; the tables are compared separately
+    o.prepare_data()
+    o.set_tile_shard(0, every)
+    g.accumulate(spp)
+    o.accumulate(spp)
+    a, b = g.fetch_hdr(), o.fetch_hdr()
+    sel = b[..., 3] > 0
+    assert sel.sum() >= W * H // every - 32 and (a[..., 3] == spp).all() and (b[..., 3][sel] == spp).all()
+    a, b = a[sel], b[sel]
+    err = np.abs(a[..., :3] - b[..., :3]).max(axis=-1)
+    scale = np.maximum(np.abs(b[..., :3]).max(axis=-1), 1e-3)
+    close = float(np.mean(err <= 1e-3 * scale + 1e-5))
+    r = rel_rmse(a, b)
+    print("full size: %d pixels of the 1080p frame, rel-RMSE %.3e, within 1e-3: %.5f" % (sel.sum(), r, close))
+    return r, close
+
+
+def test_full_size_parity_config3_vs_oracle(vrt, oracle):
+    """BASELINE config 3 AT ITS FULL SIZE (1920x1080, 256^3 dense random grid, depth 4, physical sky + clouds at
+    3840^2): the CUDA frame against the oracle on every 64th 8x4 tile of that frame (32 400 pixels spread over the
+    whole image, 8 samples each, same sampler). Tolerance: rel-RMSE <= 1e-3, >= 99.9 % of the
+    pixels within 1e-3 relative. bench.py reports the same figure over ALL pixels in its `parity` object."""
+    r, close = _full_size_pair(vrt, oracle, R=256, mat=scenes.random_grid(256, 0.5, 1234)[0], col=scenes.random_grid(256, 0.5, 1234)[1],
+                               floor=-1e5, light=((1, 1, 1), 0.025, (1.3, 0.949 * 1.3, 0.937 * 1.3)), voxel_edges=0.06, exposure=2.0,
+                               sky_res=3840, spp=8, every=64)
+    assert r <= 1e-3 and close >= 0.999
+
+
+def test_full_size_parity_config2_vs_oracle(vrt, oracle):
+    """BASELINE config 2 at its full size (example6 fixture scene, 1920x1080, physical sky + clouds at 3840^2, 64 spp):
+    CUDA against the oracle on every 128th tile (16 200 pixels x 64 samples), same tolerances."""
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example6_seed0.npz"))
+    r, close = _full_size_pair(vrt, oracle, R=128, mat=z["material"], col=z["color"], floor=-0.85,
+                               light=((1, 1, -1), 0.025, (1.3, 0.949 * 1.3, 0.937 * 1.3)), voxel_edges=0.0, exposure=2.0, sky_res=3840,
+                               spp=64, every=128)
+    assert r <= 1e-3 and close >= 0.999
+
+
 def test_merged_resolve_without_peers_equals_fetch_image(vrt):
     """vrt_fetch_ldr_merged with zero peers is the plain tonemap pass (the N-GPU behaviour is checked
     by tools/peer_merge_check.py under torchrun)."""
@@ -588,8 +651,8 @@ def test_cuda_matches_reference_source_vectors(vrt):
         err = np.abs(a - b).max(-1) / np.maximum(np.abs(b).max(-1), 1e-3)
         close = np.mean(err <= 2e-3)
         print("sample %d: within 2e-3 on %.4f of the pixels, worst %.3e" % (s, close, err.max()))
-        assert close >= 0.99
-        assert abs(a.mean() - b.mean()) <= 1e-3 * b.mean()
+        assert close >= 0.9995 and err.max() < 5e-3  # measured: every pixel, worst 4.3e-4
+        assert abs(a.mean() - b.mean()) <= 1e-4 * b.mean()
 
 
 def test_cuda_matches_reference_source_frame_loop(vrt):
@@ -609,8 +672,8 @@ def test_cuda_matches_reference_source_frame_loop(vrt):
     err = np.abs(hdr[..., :3] - z["hdr"]).max(-1) / np.maximum(np.abs(z["hdr"]).max(-1), 1e-3)
     print("HDR: within 2e-3 on %.4f of the pixels, worst %.3e; LDR worst abs %.3e" % (np.mean(err <= 2e-3), err.max(),
                                                                                       np.abs(ldr[..., :3] - z["ldr"][..., :3]).max()))
-    assert np.mean(err <= 2e-3) >= 0.99
-    assert np.abs(ldr[..., :3] - z["ldr"][..., :3]).max() < 5e-3
+    assert np.mean(err <= 2e-3) >= 0.9995 and err.max() < 4e-4  # measured: every pixel, worst 3.9e-5
+    assert np.abs(ldr[..., :3] - z["ldr"][..., :3]).max() < 1.5e-4  # measured 1.4e-5
 
 
 def test_cuda_restir_reservoirs_match_reference_source(vrt):
@@ -636,15 +699,15 @@ def test_cuda_restir_reservoirs_match_reference_source(vrt):
     flags = ((np.abs(ref[:, 6:9]).sum(1) == 0) * 1 + (np.abs(ref[:, 9:12]).sum(1) == 0) * 2 + (np.abs(ref[:, 15:18]).sum(1) > 0) * 4).astype(np.uint8)
     same = (a["mat"] == ref[:, 18].view(np.uint32)) & (a["lobes"] == ref[:, 20].astype(np.int8)) & (a["flags"] == flags) & (a["M"] == ref[:, 21])
     print("identical integer fields: %.4f (%.4f off the sky)" % (same.mean(), same[~sky].mean()))
-    assert same.mean() > 0.99
+    assert same.mean() > 0.998  # measured 1.0000 (512 pixels)
     for f, c in (("F", 0), ("rc_pos", 3), ("L", 12)):
         x, y = a[f][same].astype(np.float64), ref[same, c:c + 3].astype(np.float64)
         close = np.all(np.abs(x - y) <= 1e-3 * np.maximum(np.abs(y), 1e-3) + 1e-5, axis=-1)
         print(f, "close fraction %.4f" % close.mean())
-        assert close.mean() > 0.97
+        assert close.mean() > 0.998  # measured 1.0000
     w, wr = a["W"][same].astype(np.float64), ref[same, 22].astype(np.float64)
     fin = np.isfinite(w) & np.isfinite(wr) & (wr < 6e4)
-    assert np.mean(np.abs(w[fin] - wr[fin]) <= 3e-3 * np.maximum(np.abs(wr[fin]), 1e-2)) > 0.97
+    assert np.mean(np.abs(w[fin] - wr[fin]) <= 3e-3 * np.maximum(np.abs(wr[fin]), 1e-2)) > 0.995
 
 
 def test_cuda_spatial_gris_matches_reference_source(vrt, oracle):
@@ -688,7 +751,7 @@ def test_cuda_spatial_gris_matches_reference_source(vrt, oracle):
     total = ref[:, :3] + ref[:, 3:]
     err = np.abs(got - total).max(1) / np.maximum(np.abs(total).max(1), 1e-3)
     print("spatial_GRIS vs reference: within 1e-3 on %.4f of %d pixels, median %.2e" % (np.mean(err <= 1e-3), len(px), np.median(err)))
-    assert np.mean(err <= 1e-3) >= 0.97
+    assert np.mean(err <= 1e-3) >= 0.99  # measured 1.0000 of 165 pixels, median error 0
 
 
 def test_cuda_sky_precompute_matches_reference_source_vectors(vrt):
@@ -745,8 +808,10 @@ def test_cuda_moving_camera_path_matches_reference_source_vectors(vrt):
         b = z["frames"][f][: H // 2, : W // 2]
         err = np.abs(a - b).max(-1) / np.maximum(np.abs(b).max(-1), 1e-3)
         print("frame %d: within 2e-3 on %.4f of the pixels, worst %.3e" % (f, np.mean(err <= 2e-3), err.max()))
-        assert np.mean(err <= 2e-3) >= 0.97
-        assert abs(a.mean() - b.mean()) <= 5e-3 * b.mean()
+        # measured: every pixel within 2e-3 on frames 0-2 (worst 1.4e-5 / 3.9e-4 / 7.6e-5), 0.9961 on frame 3 (worst 4.7e-3:
+        # a few rejection-threshold flips, as in the oracle-vs-reference comparison of the same frame)
+        assert np.mean(err <= 2e-3) >= (0.9995 if f < 3 else 0.99)
+        assert abs(a.mean() - b.mean()) <= 5e-4 * b.mean()
 
 
 def test_compact_sky_table_format_within_rmse_budget(vrt):
@@ -776,7 +841,7 @@ def test_compact_sky_table_format_within_rmse_budget(vrt):
     a, b = imgs["f16"], imgs["f32"]
     err = np.abs(a - b).max(-1) / np.maximum(np.abs(b).max(-1), 1e-3)
     print("f16 sky tables: within 2e-3 on %.4f of the pixels, rel-RMSE %.2e" % (np.mean(err <= 2e-3), rel_rmse(a, b)))
-    assert np.mean(err <= 2e-3) >= 0.99 and rel_rmse(a, b) <= 1e-3
+    assert np.mean(err <= 2e-3) >= 0.9995 and rel_rmse(a, b) <= 1e-3  # measured 1.0000, 1.25e-4
     assert not np.array_equal(a, b)
     g0 = vrt.Renderer(dx=2.0 / R, image_res=(64, 64), grid_res=R, sky_res=0)  # no sky tables: format 1 is refused, 2 is unknown
     assert g0._lib.vrt_set_sky_format(g0._h, 1) != 0 and g0._lib.vrt_set_sky_format(g0._h, 2) != 0 and g0._lib.vrt_set_sky_format(g0._h, 0) == 0
@@ -804,3 +869,59 @@ def test_pipelined_fetch_equals_synchronous_fetch(vrt):
     assert np.array_equal(bufs[1], g.fetch_image()) and not np.array_equal(bufs[1], bufs[0])
     with pytest.raises(ValueError):
         g.fetch_image_async(np.zeros((4, 4, 4), np.float32))
+
+
+def test_accum_slots_deferred_reset_and_merge_slice(vrt):
+    """Round-2 plumbing of the multi-GPU step at N = 1: (a) reset_framebuffer is deferred — a fetch right after it
+    sees zeros, a batch right after it overwrites (bit-identical to a fresh context); (b) the two accumulation /
+    image slots are independent; (c) vrt_merge_slice without peers over the whole frame + vrt_copy_ldr_async is the
+    plain tonemap pass; (d) vrt_accumulate is asynchronous and the stats ring reports every launch."""
+    import torch
+
+    R, res = 32, (128, 64)
+
+    def mk():
+        g = vrt.Renderer(dx=2.0 / R, image_res=res, grid_res=R, sky_res=0, seed=4)
+        g.set_voxels(*scenes.random_grid(R, 0.3, 9))
+        g.set_directional_light((1, 1, 0.5), 0.05, (1.2, 1.1, 1.0))
+        g.set_background_color((0.3, 0.4, 0.6))
+        g.prepare_data()
+        return g
+
+    g, fresh = mk(), mk()
+    fresh.accumulate(4)
+    want = fresh.fetch_hdr()
+    g.accumulate(3)
+    g.reset_framebuffer()
+    assert (g.fetch_hdr() == 0).all()            # (a) the deferred reset is visible to a fetch
+    g.reset_framebuffer()
+    g.accumulate(4)                              # ... and a full-frame batch overwrites instead of clearing first
+    assert np.array_equal(g.fetch_hdr(), want)
+    img0 = g.fetch_image()
+    g.set_accum_slot(1)                          # (b) second slot: starts empty, independent of slot 0
+    assert (g.fetch_hdr()[..., 3] == 0).all()
+    g.reset_framebuffer()
+    g.accumulate(2)
+    h1 = g.fetch_hdr()
+    assert (h1[..., 3] == 2).all() and not np.array_equal(h1[..., :3], want[..., :3])
+    pinned = torch.empty((res[1], res[0], 4), dtype=torch.float32, pin_memory=True).numpy()
+    g.set_accum_slot(0)
+    assert np.array_equal(g.fetch_hdr(), want)
+    g.merge_slice([], 0, res[0] * res[1])        # (c) no peers, whole frame, own image buffer
+    g.copy_image_async(pinned)
+    g.wait_image()
+    assert np.array_equal(pinned, img0)
+    half = res[0] * res[1] // 2                  # two half-frame slices give the same image
+    g.merge_slice([], 0, half)
+    g.merge_slice([], half, res[0] * res[1] - half)
+    g.copy_image_async(pinned)
+    g.wait_image()
+    assert np.array_equal(pinned, img0)
+    with pytest.raises(RuntimeError, match="pixel range"):
+        g.merge_slice([], half, res[0] * res[1])
+    g.stats()                                    # (d) clears the since-last-query sums
+    for _ in range(40):                          # more launches than the event ring holds
+        g.accumulate(1)
+    st = g.stats()
+    assert st["render_launches"] == 40 and st["render_ms_sum"] > 0.0 and st["launches_total"] == 80
+    assert (g.fetch_hdr()[..., 3] == 44).all()

@@ -170,8 +170,9 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: the CPU arm must still use all host cores
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--res", "64x32",
-                        "--grid", "32", "--sky-res", "16"], capture_output=True, text=True, timeout=600)
+                        "--grid", "32", "--sky-res", "16"], capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -179,5 +180,6 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in j, k
-    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0

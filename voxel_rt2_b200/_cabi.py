@@ -11,7 +11,7 @@ EXPORTS = [
     "vrt_set_light", "vrt_set_floor", "vrt_set_background", "vrt_set_sky", "vrt_set_materials",
     "vrt_set_cloud_texture", "vrt_prepare", "vrt_get_sky_tables", "vrt_set_sky_tables", "vrt_set_sky_format", "vrt_get_trans_lut",
     "vrt_trace_primary", "vrt_accumulate", "vrt_accumulate_restir", "vrt_accumulate_moving", "vrt_get_reservoirs", "vrt_spatial_gris", "vrt_set_tile_shard", "vrt_reset", "vrt_accum_device_ptr",
-    "vrt_fetch_hdr", "vrt_fetch_ldr", "vrt_fetch_ldr_async", "vrt_fetch_wait", "vrt_accum_ipc_handle", "vrt_open_peer_accum", "vrt_close_peer_accum", "vrt_fetch_ldr_merged", "vrt_resolve_ldr_device", "vrt_get_stats", "vrt_synchronize",
+    "vrt_fetch_hdr", "vrt_fetch_ldr", "vrt_fetch_ldr_async", "vrt_fetch_wait", "vrt_accum_ipc_handle", "vrt_open_peer_accum", "vrt_close_peer_accum", "vrt_fetch_ldr_merged", "vrt_set_accum_slot", "vrt_out_ipc_handle", "vrt_merge_slice", "vrt_copy_ldr_async", "vrt_stream_wait_copy", "vrt_resolve_ldr_device", "vrt_get_stats", "vrt_synchronize",
 ]
 
 
@@ -33,7 +33,8 @@ class vrt_stats(C.Structure):
         ("paths", C.c_uint64), ("rays", C.c_uint64), ("steps", C.c_uint64), ("queries", C.c_uint64),
         ("hits", C.c_uint64), ("sky_escapes", C.c_uint64), ("nee_visible", C.c_uint64), ("vertices", C.c_uint64),
         ("last_render_ms", C.c_float), ("last_resolve_ms", C.c_float), ("sky_precompute_ms", C.c_float),
-        ("kernel_launches", C.c_uint32), ("last_gris_ms", C.c_float),
+        ("kernel_launches", C.c_uint32), ("last_gris_ms", C.c_float), ("render_ms_sum", C.c_float), ("render_launches", C.c_uint32),
+        ("launches_total", C.c_uint32), ("last_temporal_ms", C.c_float),
     ]
 
 
@@ -86,6 +87,11 @@ def load():
     lib.vrt_open_peer_accum.argtypes = [P, P, C.POINTER(P)]
     lib.vrt_close_peer_accum.argtypes = [P, P]
     lib.vrt_fetch_ldr_merged.argtypes = [P, C.POINTER(P), C.c_int32, fp]
+    lib.vrt_set_accum_slot.argtypes = [P, C.c_int32]
+    lib.vrt_out_ipc_handle.argtypes = [P, P]
+    lib.vrt_merge_slice.argtypes = [P, C.POINTER(P), C.c_int32, C.c_int32, C.c_int32, P, C.c_int32]
+    lib.vrt_copy_ldr_async.argtypes = [P, fp]
+    lib.vrt_stream_wait_copy.argtypes = [P]
     lib.vrt_fetch_hdr.argtypes = [P, fp]
     lib.vrt_fetch_ldr.argtypes = [P, fp]
     lib.vrt_resolve_ldr_device.argtypes = [P, C.POINTER(P)]

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvoxelrt.so")
-SOURCES = ["vrt_api.cu", "vrt_render.cu", "vrt_pool.cu", "vrt_restir.cu", "vrt_temporal.cu", "vrt_build.cu", "vrt_sky_precompute.cu"]
+SOURCES = ["vrt_api.cu", "vrt_render.cu", "vrt_restir.cu", "vrt_temporal.cu", "vrt_build.cu", "vrt_sky_precompute.cu"]
 HEADERS = ["vrt_common.cuh", "vrt_trace.cuh", "vrt_bsdf.cuh", "vrt_sky.cuh", "vrt_restir.cuh", "vrt_internal.h",
            os.path.join("..", "..", "include", "voxelrt.h")]
 NVCC_FLAGS = [

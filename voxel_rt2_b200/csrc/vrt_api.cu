@@ -49,9 +49,14 @@ struct vrt_ctx {
   float* d_cloud_ambient = nullptr;
   bool sky_valid = false, cloud_tex_set = false, lut_valid = false;
 
-  // frame buffers
-  float4* d_accum = nullptr;
-  float4* d_out = nullptr;  // resolve target (hdr or ldr)
+  // frame buffers. Two accumulation slots (the second allocated on first use, vrt_set_accum_slot): while the
+  // partial sums of batch k are being merged across GPUs, batch k+1 renders into the other slot.
+  float4* d_accum = nullptr;  // == accum_slot[cur_slot]
+  float4* accum_slot[2] = {nullptr, nullptr};
+  bool zero_pending[2] = {false, false};  // reset_framebuffer deferred: the next full-frame batch overwrites instead of adding
+  int cur_slot = 0;
+  float4* d_out = nullptr;  // resolve target (hdr or ldr) == out_slot[cur_slot]
+  float4* out_slot[2] = {nullptr, nullptr};
   vrt_hit* d_hits = nullptr;
   float2* d_jitter = nullptr;
   int jitter_cap = 0;
@@ -73,6 +78,13 @@ struct vrt_ctx {
   int tile_rank = 0, tile_n = 1;
   vrt_stats stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // vrt_accumulate is asynchronous: the device time of each launch is bracketed by an event pair from this ring
+  // and read back lazily (vrt_get_stats, or when the ring wraps onto a pair that has not been read yet)
+  static constexpr int EV_RING = 32;
+  cudaEvent_t ring_a[EV_RING] = {nullptr}, ring_b[EV_RING] = {nullptr};
+  bool ring_pending[EV_RING] = {false};
+  int ring_head = 0;
+  std::vector<cudaEvent_t> frame_events;  // ReSTIR mode: 3 events per frame of a call
   // pipelined image fetch (vrt_fetch_ldr_async): copy engine stream + events, created on first use
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_resolved = nullptr, ev_copied = nullptr;
@@ -208,6 +220,34 @@ static void fill_params(const vrt_ctx* ctx, Params& P) {
   P.jitter = ctx->d_jitter;
 }
 
+// The deferred reset_framebuffer of the current slot becomes a real memset: needed before anything
+// other than a full-frame path-tracing batch touches the buffer.
+static int flush_pending_zero(vrt_ctx* ctx) {
+  if (ctx->zero_pending[ctx->cur_slot]) {
+    CK(cudaMemsetAsync(ctx->d_accum, 0, (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4), ctx->stream));
+    ctx->zero_pending[ctx->cur_slot] = false;
+  }
+  return VRT_OK;
+}
+
+// Read back the event pairs of finished asynchronous launches (blocking on the ones still in flight).
+static int drain_ring_slot(vrt_ctx* ctx, int i) {
+  if (!ctx->ring_pending[i]) return VRT_OK;
+  CK(cudaEventSynchronize(ctx->ring_b[i]));
+  float ms = 0.0f;
+  CK(cudaEventElapsedTime(&ms, ctx->ring_a[i], ctx->ring_b[i]));
+  ctx->ring_pending[i] = false;
+  ctx->stats.last_render_ms = ms;
+  ctx->stats.render_ms_sum += ms;
+  ctx->stats.render_launches += 1;
+  return VRT_OK;
+}
+static int drain_ring(vrt_ctx* ctx) {
+  for (int k = 0; k < vrt_ctx::EV_RING; k++)  // oldest first, so last_render_ms ends up being the newest launch
+    if (int rc = drain_ring_slot(ctx, (ctx->ring_head + k) % vrt_ctx::EV_RING)) return rc;
+  return VRT_OK;
+}
+
 extern "C" {
 
 const char* vrt_last_error(const vrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -218,7 +258,7 @@ void vrt_destroy(vrt_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_mat), cudaFree(ctx->d_rgb), cudaFree(ctx->d_bricks), cudaFree(ctx->d_color), cudaFree(ctx->d_upper);
   cudaFree(ctx->d_mats), cudaFree(ctx->d_sky_scatter), cudaFree(ctx->d_sky_trans), cudaFree(ctx->d_sky_packed), cudaFree(ctx->d_trans_lut);
-  cudaFree(ctx->d_cloud_tex), cudaFree(ctx->d_cloud_ambient), cudaFree(ctx->d_accum), cudaFree(ctx->d_out), cudaFree(ctx->d_hits);
+  cudaFree(ctx->d_cloud_tex), cudaFree(ctx->d_cloud_ambient), cudaFree(ctx->accum_slot[0]), cudaFree(ctx->accum_slot[1]), cudaFree(ctx->out_slot[0]), cudaFree(ctx->out_slot[1]), cudaFree(ctx->d_hits);
   cudaFree(ctx->d_jitter), cudaFree(ctx->d_work), cudaFree(ctx->d_stats);
   cudaFree(ctx->mv.col_d), cudaFree(ctx->mv.col_s), cudaFree(ctx->mv.out), cudaFree(ctx->mv.full), cudaFree(ctx->mv.refl), cudaFree(ctx->mv.refl_blur);
   for (int k = 0; k < 2; k++) cudaFree(ctx->mv.hd[k]), cudaFree(ctx->mv.hs[k]), cudaFree(ctx->mv.hsd[k]), cudaFree(ctx->mv.depth[k]), cudaFree(ctx->mv.attr[k]);
@@ -229,6 +269,11 @@ void vrt_destroy(vrt_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < vrt_ctx::EV_RING; i++) {
+    if (ctx->ring_a[i]) cudaEventDestroy(ctx->ring_a[i]);
+    if (ctx->ring_b[i]) cudaEventDestroy(ctx->ring_b[i]);
+  }
+  for (cudaEvent_t e : ctx->frame_events) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -286,6 +331,10 @@ int vrt_create(const vrt_config* cfg, vrt_ctx** out) {
   ctx->own_stream = true;
   CKC(cudaEventCreate(&ctx->ev0));
   CKC(cudaEventCreate(&ctx->ev1));
+  for (int i = 0; i < vrt_ctx::EV_RING; i++) {
+    CKC(cudaEventCreate(&ctx->ring_a[i]));
+    CKC(cudaEventCreate(&ctx->ring_b[i]));
+  }
 
   const size_t nvox = (size_t)R * R * R;
   ctx->n_lods = 0;
@@ -303,10 +352,14 @@ int vrt_create(const vrt_config* cfg, vrt_ctx** out) {
   CKC(cudaMalloc(&ctx->d_upper, (size_t)(ctx->upper_words > 0 ? ctx->upper_words : 1) * 4));
   CKC(cudaMalloc(&ctx->d_mats, 128 * 20 * sizeof(float)));
   const size_t npx = (size_t)cfg->width * cfg->height;
-  CKC(cudaMalloc(&ctx->d_accum, npx * sizeof(float4)));
-  CKC(cudaMalloc(&ctx->d_out, npx * sizeof(float4)));
+  CKC(cudaMalloc(&ctx->accum_slot[0], npx * sizeof(float4)));
+  ctx->d_accum = ctx->accum_slot[0];
+  CKC(cudaMalloc(&ctx->out_slot[0], npx * sizeof(float4)));
+  ctx->d_out = ctx->out_slot[0];
   CKC(cudaMemsetAsync(ctx->d_accum, 0, npx * sizeof(float4), ctx->stream));
   CKC(cudaMalloc(&ctx->d_work, sizeof(unsigned int)));
+  ctx->jitter_cap = 64;
+  CKC(cudaMalloc(&ctx->d_jitter, (size_t)ctx->jitter_cap * sizeof(float2)));
   CKC(cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)));
   CKC(cudaMalloc(&ctx->d_cloud_ambient, 3 * sizeof(float)));
   CKC(cudaMalloc(&ctx->d_cloud_tex, 256 * 256 * 3));
@@ -580,46 +633,40 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
   if (n_samples > ctx->jitter_cap) {
+    CK(cudaStreamSynchronize(ctx->stream));  // a launch in flight may still read the old buffer
     if (ctx->d_jitter) cudaFree(ctx->d_jitter);
     ctx->d_jitter = nullptr;
+    ctx->jitter_cap = 0;
     CK(cudaMalloc(&ctx->d_jitter, (size_t)n_samples * sizeof(float2)));
     ctx->jitter_cap = n_samples;
   }
-  // pathtracer.py:264-265: taa_jitter = (rand*2-1) * inv_image_res, one value per frame. Ours
-  // is a Halton(2,3) point per sample index so the pixel footprint is stratified.
-  std::vector<float2> jit((size_t)n_samples);
-  for (int k = 0; k < n_samples; k++) {
-    uint32_t s = (uint32_t)(first_sample + k * stride);
-    if (ctx->cfg.jitter_mode == 1)
-      jit[k] = make_float2((float)((halton(s + 1, 2) * 2.0 - 1.0) / (double)ctx->cfg.width),
-                           (float)((halton(s + 1, 3) * 2.0 - 1.0) / (double)ctx->cfg.height));
-    else
-      jit[k] = make_float2(0.0f, 0.0f);
-  }
-  CK(cudaMemcpyAsync(ctx->d_jitter, jit.data(), jit.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
-  if (stats) CK(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
   ctx->mv.active = false;
   Params P;
   fill_params(ctx, P);
   P.first_sample = first_sample, P.n_samples = n_samples, P.stride = stride;
   P.stats = stats ? ctx->d_stats : nullptr;
   if (P.n_tiles <= 0) return VRT_OK;
-  CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  {
-    // VRT_KERNEL=pool selects the experimental shared-memory wavefront kernel (vrt_pool.cu): correct,
-    // but measured 25-40 % slower than the per-lane kernel in round 1 (profiles/r01_pool_experiment.md)
-    const char* k = getenv("VRT_KERNEL");
-    if (k && !strcmp(k, "pool"))
-      CK(vrt_launch_path_pool(P, stats != 0, ctx->sm_count, ctx->stream, nullptr));
-    else
-      CK(vrt_launch_path(P, stats != 0, ctx->sm_count, ctx->stream, nullptr));
+  // reset_framebuffer + full-frame batch: the kernel writes every texel, so the memset (and the read) is skipped
+  if (ctx->zero_pending[ctx->cur_slot] && ctx->tile_n == 1) {
+    P.accum_overwrite = 1;
+    ctx->zero_pending[ctx->cur_slot] = false;
+  } else if (int rcz = flush_pending_zero(ctx)) {
+    return rcz;
   }
-  CK(cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->stats.kernel_launches = 1;
-  // the jitter vector is read by the async copy above: wait before it goes out of scope
-  CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaEventElapsedTime(&ctx->stats.last_render_ms, ctx->ev0, ctx->ev1));
+  // pathtracer.py:264-265: taa_jitter = (rand*2-1) * inv_image_res, one value per frame. Ours is a Halton(2,3)
+  // point per sample index (stratified pixel footprint), computed on the device (k_jitter also clears the tile
+  // queue counter): nothing on the host outlives the call, so it returns without synchronising.
+  CK(vrt_launch_jitter(ctx->d_jitter, first_sample, stride, n_samples, ctx->cfg.width, ctx->cfg.height, ctx->cfg.jitter_mode, ctx->d_work, ctx->stream));
+  if (stats) CK(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  const int slot = ctx->ring_head;
+  if (int rcd = drain_ring_slot(ctx, slot)) return rcd;
+  CK(cudaEventRecord(ctx->ring_a[slot], ctx->stream));
+  CK(vrt_launch_path(P, stats != 0, ctx->sm_count, ctx->stream, nullptr));
+  CK(cudaEventRecord(ctx->ring_b[slot], ctx->stream));
+  ctx->ring_pending[slot] = true;
+  ctx->ring_head = (slot + 1) % vrt_ctx::EV_RING;
+  ctx->stats.kernel_launches = 2;  // k_jitter, k_path
+  ctx->stats.launches_total += 2;
   if (stats) {
     unsigned long long h[8];
     CK(cudaMemcpyAsync(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -652,38 +699,38 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
   CK(cudaSetDevice(ctx->device));
   rc = ensure_restir_buffers(ctx);
   if (rc) return rc;
-  if (ctx->jitter_cap < 1) {
-    CK(cudaMalloc(&ctx->d_jitter, sizeof(float2)));
-    ctx->jitter_cap = 1;
+  if (int rcz = flush_pending_zero(ctx)) return rcz;  // the resampling pass adds its frame to the buffer
+  ctx->mv.active = false;
+  while (ctx->frame_events.size() < 3u * (size_t)n_frames) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    ctx->frame_events.push_back(e);
   }
-  float render_ms = 0.0f, gris_ms = 0.0f;
   for (int k = 0; k < n_frames; k++) {
     const uint32_t s = (uint32_t)(first_sample + k * stride);
-    float2 jit = make_float2(0.0f, 0.0f);
-    if (ctx->cfg.jitter_mode == 1)
-      jit = make_float2((float)((halton(s + 1, 2) * 2.0 - 1.0) / (double)ctx->cfg.width), (float)((halton(s + 1, 3) * 2.0 - 1.0) / (double)ctx->cfg.height));
-    CK(cudaMemcpyAsync(ctx->d_jitter, &jit, sizeof jit, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
+    CK(vrt_launch_jitter(ctx->d_jitter, (int)s, 1, 1, ctx->cfg.width, ctx->cfg.height, ctx->cfg.jitter_mode, ctx->d_work, ctx->stream));
     Params P;
     fill_params(ctx, P);
     P.first_sample = (int)s, P.n_samples = 1, P.stride = 1;
-    cudaEvent_t evm;
-    CK(cudaEventCreate(&evm));
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaEvent_t* ev = &ctx->frame_events[3 * (size_t)k];
+    CK(cudaEventRecord(ev[0], ctx->stream));
     CK(vrt_launch_path_restir(P, ctx->rb, ctx->sm_count, ctx->stream));
-    CK(cudaEventRecord(evm, ctx->stream));
+    CK(cudaEventRecord(ev[1], ctx->stream));
     CK(vrt_launch_gris(P, ctx->rb, s, ctx->stream));
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // jit lives on the stack
+    CK(cudaEventRecord(ev[2], ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  float render_ms = 0.0f, gris_ms = 0.0f;
+  for (int k = 0; k < n_frames; k++) {
     float a = 0.0f, b = 0.0f;
-    CK(cudaEventElapsedTime(&a, ctx->ev0, evm));
-    CK(cudaEventElapsedTime(&b, evm, ctx->ev1));
-    cudaEventDestroy(evm);
+    CK(cudaEventElapsedTime(&a, ctx->frame_events[3 * (size_t)k], ctx->frame_events[3 * (size_t)k + 1]));
+    CK(cudaEventElapsedTime(&b, ctx->frame_events[3 * (size_t)k + 1], ctx->frame_events[3 * (size_t)k + 2]));
     render_ms += a, gris_ms += b;
   }
   ctx->stats.last_render_ms = render_ms;
   ctx->stats.last_gris_ms = gris_ms;
-  ctx->stats.kernel_launches = 3u * (uint32_t)n_frames;  // k_path, k_rc_sky, k_gris
+  ctx->stats.kernel_launches = 4u * (uint32_t)n_frames;  // k_jitter, k_path, k_rc_sky, k_gris
+  ctx->stats.launches_total += ctx->stats.kernel_launches;
   return VRT_OK;
 }
 
@@ -697,6 +744,8 @@ int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs, const 
   CK(cudaSetDevice(ctx->device));
   rc = ensure_restir_buffers(ctx);
   if (rc) return rc;
+  if (int rcz = flush_pending_zero(ctx)) return rcz;
+  ctx->mv.active = false;
   const size_t npx = (size_t)ctx->cfg.width * ctx->cfg.height;
   CK(cudaMemcpyAsync(ctx->rb.reservoirs, reservoirs, npx * 56, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->rb.gpos, gpos, npx * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
@@ -715,6 +764,7 @@ int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs, const 
   ctx->stats.last_render_ms = 0.0f;
   ctx->stats.last_gris_ms = ms;
   ctx->stats.kernel_launches = 2u;  // k_rc_sky, k_gris
+  ctx->stats.launches_total += 2;
   return VRT_OK;
 }
 
@@ -764,10 +814,6 @@ int vrt_accumulate_moving(vrt_ctx* ctx, int32_t sample, float render_scale, floa
   m.scale = render_scale;
   m.active = true;
   const int cur = m.cur, prev = cur ^ 1;
-  if (ctx->jitter_cap < 1) {
-    CK(cudaMalloc(&ctx->d_jitter, sizeof(float2)));
-    ctx->jitter_cap = 1;
-  }
   CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
   Params P;
   fill_params(ctx, P);
@@ -794,6 +840,7 @@ int vrt_accumulate_moving(vrt_ctx* ctx, int32_t sample, float render_scale, floa
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaEventElapsedTime(&ctx->stats.last_render_ms, ctx->ev0, ctx->ev1));
   ctx->stats.kernel_launches = 3;
+  ctx->stats.launches_total += 3;
   // copy_prev_matrices (pathtracer.py:284-287) and the slot swap
   memcpy(m.prev_view, ctx->view, sizeof m.prev_view);
   memcpy(m.prev_proj, ctx->proj, sizeof m.prev_proj);
@@ -817,6 +864,16 @@ int vrt_get_reservoirs(vrt_ctx* ctx, void* out) {
 int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(n >= 1 && rank >= 0 && rank < n, "vrt_set_tile_shard: need 0 <= rank < n");
+  if (n != 1) {  // a sharded batch covers only its own tiles: pending resets must really clear the buffers
+    CK(cudaSetDevice(ctx->device));
+    const int keep = ctx->cur_slot;
+    for (int k = 0; k < 2; k++)
+      if (ctx->accum_slot[k]) {
+        ctx->cur_slot = k, ctx->d_accum = ctx->accum_slot[k];
+        if (int rcz = flush_pending_zero(ctx)) return rcz;
+      }
+    ctx->cur_slot = keep, ctx->d_accum = ctx->accum_slot[keep];
+  }
   ctx->tile_rank = rank, ctx->tile_n = n;
   return VRT_OK;
 }
@@ -824,7 +881,11 @@ int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
 int vrt_reset(vrt_ctx* ctx) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemsetAsync(ctx->d_accum, 0, (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4), ctx->stream));
+  // deferred: a full-frame path-tracing batch that follows overwrites the buffer (no memset, no read-modify-write);
+  // every other consumer turns the flag into the memset first (flush_pending_zero)
+  ctx->zero_pending[ctx->cur_slot] = true;
+  if (ctx->tile_n != 1)
+    if (int rcz = flush_pending_zero(ctx)) return rcz;
   ctx->mv.has_prev = false;
   ctx->mv.active = false;
   return VRT_OK;
@@ -833,6 +894,8 @@ int vrt_reset(vrt_ctx* ctx) {
 int vrt_accum_device_ptr(vrt_ctx* ctx, void** ptr, uint64_t* bytes) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(ptr, "vrt_accum_device_ptr: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  if (int rcz = flush_pending_zero(ctx)) return rcz;  // the caller is about to use the memory directly
   *ptr = ctx->d_accum;
   if (bytes) *bytes = (uint64_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4);
   return VRT_OK;
@@ -849,6 +912,7 @@ static int wait_pending_copy(vrt_ctx* ctx) {
 static int resolve(vrt_ctx* ctx, bool ldr, float* host) {
   CK(cudaSetDevice(ctx->device));
   if (int rc = wait_pending_copy(ctx)) return rc;  // d_out may still be the source of a pipelined copy
+  if (int rc = flush_pending_zero(ctx)) return rc;
   const int W = ctx->cfg.width, H = ctx->cfg.height;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const float4* src = ctx->d_accum;
@@ -888,6 +952,7 @@ int vrt_fetch_ldr_async(vrt_ctx* ctx, float* rgba_pinned) {
     CK(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
   }
   if (int rc = wait_pending_copy(ctx)) return rc;
+  if (int rc = flush_pending_zero(ctx)) return rc;
   const int W = ctx->cfg.width, H = ctx->cfg.height;
   const float4* src = ctx->d_accum;
   if (ctx->mv.active) {
@@ -921,6 +986,7 @@ int vrt_accum_ipc_handle(vrt_ctx* ctx, void* handle64) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   CK(cudaSetDevice(ctx->device));
   cudaIpcMemHandle_t h;
+  if (int rcz = flush_pending_zero(ctx)) return rcz;
   CK(cudaIpcGetMemHandle(&h, ctx->d_accum));
   memcpy(handle64, &h, sizeof h);
   return VRT_OK;
@@ -949,7 +1015,10 @@ int vrt_close_peer_accum(vrt_ctx* ctx, void* peer_ptr) {
 int vrt_fetch_ldr_merged(vrt_ctx* ctx, const void* const* peer_ptrs, int32_t n_peers, float* ldr_rgba) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_ptrs), "vrt_fetch_ldr_merged: 0..8 peers");
+  REQUIRE(!ctx->mv.active, "vrt_fetch_ldr_merged: the last frame came from the moving-camera path, which does not shard");
   CK(cudaSetDevice(ctx->device));
+  if (int rc = wait_pending_copy(ctx)) return rc;  // d_out may still be the source of a pipelined copy
+  if (int rc = flush_pending_zero(ctx)) return rc;
   const int W = ctx->cfg.width, H = ctx->cfg.height;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(vrt_launch_resolve_merged(ctx->d_accum, reinterpret_cast<const float4* const*>(peer_ptrs), n_peers, ctx->d_out, W, H, ctx->cfg.exposure, ctx->stream));
@@ -960,10 +1029,83 @@ int vrt_fetch_ldr_merged(vrt_ctx* ctx, const void* const* peer_ptrs, int32_t n_p
   return VRT_OK;
 }
 
+// ---- double-buffered accumulation and the fused multi-GPU merge (reduce-scatter + tonemap over peer memory)
+int vrt_set_accum_slot(vrt_ctx* ctx, int32_t slot) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(slot == 0 || slot == 1, "vrt_set_accum_slot: slot must be 0 or 1");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->accum_slot[slot]) {
+    const size_t bytes = (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4);
+    CK(cudaMalloc(&ctx->accum_slot[slot], bytes));
+    CK(cudaMemsetAsync(ctx->accum_slot[slot], 0, bytes, ctx->stream));
+    CK(cudaMalloc(&ctx->out_slot[slot], bytes));
+  }
+  ctx->cur_slot = slot;
+  ctx->d_accum = ctx->accum_slot[slot];
+  ctx->d_out = ctx->out_slot[slot];
+  return VRT_OK;
+}
+
+int vrt_out_ipc_handle(vrt_ctx* ctx, void* handle64) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(handle64, "vrt_out_ipc_handle: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->d_out));
+  memcpy(handle64, &h, sizeof h);
+  return VRT_OK;
+}
+
+int vrt_merge_slice(vrt_ctx* ctx, const void* const* peer_ptrs, int32_t n_peers, int32_t first_pixel, int32_t n_pixels, void* ldr_dst,
+                    int32_t write_sums) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  const int npx = ctx->cfg.width * ctx->cfg.height;
+  REQUIRE(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_ptrs), "vrt_merge_slice: 0..8 peers");
+  REQUIRE(first_pixel >= 0 && n_pixels >= 0 && first_pixel + n_pixels <= npx, "vrt_merge_slice: pixel range outside the frame");
+  REQUIRE(!ctx->mv.active, "vrt_merge_slice: the last frame came from the moving-camera path, which does not shard");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = flush_pending_zero(ctx)) return rc;
+  if (!ldr_dst)
+    if (int rc = wait_pending_copy(ctx)) return rc;  // own image buffer: it may still be the source of a pipelined copy
+  float4* ldr = ldr_dst ? reinterpret_cast<float4*>(ldr_dst) : ctx->d_out;
+  CK(vrt_launch_merge_slice(ctx->d_accum, reinterpret_cast<const float4* const*>(peer_ptrs), n_peers, write_sums ? ctx->d_accum : nullptr, ldr,
+                            first_pixel, n_pixels, ctx->cfg.width, ctx->cfg.height, ctx->cfg.exposure, ctx->stream));
+  ctx->stats.launches_total += 1;
+  return VRT_OK;
+}
+
+int vrt_copy_ldr_async(vrt_ctx* ctx, float* rgba_pinned) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(rgba_pinned, "vrt_copy_ldr_async: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_resolved, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+  }
+  if (int rc = wait_pending_copy(ctx)) return rc;
+  CK(cudaEventRecord(ctx->ev_resolved, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_resolved, 0));
+  CK(cudaMemcpyAsync(rgba_pinned, ctx->d_out, (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+  ctx->copy_pending = true;
+  return VRT_OK;
+}
+
+int vrt_stream_wait_copy(vrt_ctx* ctx) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->copy_pending) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+  return VRT_OK;
+}
+
 int vrt_get_stats(vrt_ctx* ctx, vrt_stats* out) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(out, "vrt_get_stats: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = drain_ring(ctx)) return rc;  // waits for the asynchronous launches still in flight
   *out = ctx->stats;
+  ctx->stats.render_ms_sum = 0.0f, ctx->stats.render_launches = 0, ctx->stats.launches_total = 0;  // "since the last query"
   return VRT_OK;
 }
 

@@ -165,6 +165,7 @@ struct Params {
   const float4* mats;
   // accumulation
   float4* accum;
+  int accum_overwrite;  // 1: first batch after a reset, the kernel writes the texel instead of adding to it
   // work description
   int first_sample, n_samples, stride;
   const float2* jitter;  // per sample of this batch

@@ -10,8 +10,9 @@
 // vrt_render.cu
 cudaError_t vrt_launch_primary(const Params& P, vrt_hit* out, cudaStream_t st);
 cudaError_t vrt_launch_path(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out);
-// vrt_pool.cu — shared-memory wavefront version of the path kernel (default for path tracing)
-cudaError_t vrt_launch_path_pool(const Params& P, bool stats, int sm_count, cudaStream_t st, int* blocks_out);
+cudaError_t vrt_launch_jitter(float2* out, int first_sample, int stride, int n, int W, int H, int mode, unsigned int* work_counter, cudaStream_t st);
+cudaError_t vrt_launch_merge_slice(const float4* accum, const float4* const* peers, int n_peers, float4* sum_out, float4* ldr_out, int first,
+                                   int count, int W, int H, float exposure, cudaStream_t st);
 cudaError_t vrt_launch_path_restir(const Params& P, const RestirBuffers& RB, int sm_count, cudaStream_t st);
 cudaError_t vrt_launch_path_moving(const Params& P, const MovingOut& MO, int sm_count, cudaStream_t st);
 // vrt_temporal.cu — moving-camera temporal filters (pathtracer.py:993-1303)

@@ -251,8 +251,10 @@ __global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_pa
         restart = true;
       } else {
         if (MODE == 0) {
+          // first batch after reset_framebuffer: the texel is written, not read-modified (no 33 MB memset, no read)
           float4* dst = P.accum + pidx;
-          float4 a = *dst;
+          float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (!P.accum_overwrite) a = *dst;
           a.x += acc.x, a.y += acc.y, a.z += acc.z, a.w += (float)P.n_samples;
           *dst = a;
         }
@@ -579,6 +581,74 @@ cudaError_t vrt_launch_resolve_merged(const float4* accum, const float4* const* 
   for (int k = 0; k < 8; k++) pp.p[k] = k < n_peers ? peers[k] : nullptr;
   const int n = W * H;
   k_resolve_merged<<<(n + 255) / 256, 256, 0, st>>>(accum, pp, ldr, W, H, exposure);
+  return cudaGetLastError();
+}
+
+// Per-sample TAA jitter of a batch, computed on the device so that vrt_accumulate needs neither a host
+// buffer nor a host-to-device copy (the call is fully asynchronous). pathtracer.py:264-265 draws one
+// (rand*2-1) * inv_image_res pair per frame; ours is the Halton(2,3) point of the sample index. Same double
+// arithmetic, op for op, as the host / oracle formulation (halton() in oracle.cpp), no contraction.
+__device__ double halton_dev(uint32_t i, uint32_t b) {
+  double f = 1.0, r = 0.0;
+  while (i > 0) {
+    f = __ddiv_rn(f, (double)b);
+    r = __dadd_rn(r, __dmul_rn(f, (double)(i % b)));
+    i /= b;
+  }
+  return r;
+}
+__global__ void k_jitter(float2* __restrict__ out, int first_sample, int stride, int n, int W, int H, int mode, unsigned int* work_counter) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0 && work_counter) *work_counter = 0u;  // the tile queue of the path kernel launched next on this stream
+  if (k >= n) return;
+  const uint32_t s = (uint32_t)(first_sample + k * stride);
+  float2 j = make_float2(0.0f, 0.0f);
+  if (mode == 1) {
+    j.x = __double2float_rn(__ddiv_rn(__dsub_rn(__dmul_rn(halton_dev(s + 1, 2), 2.0), 1.0), (double)W));
+    j.y = __double2float_rn(__ddiv_rn(__dsub_rn(__dmul_rn(halton_dev(s + 1, 3), 2.0), 1.0), (double)H));
+  }
+  out[k] = j;
+}
+cudaError_t vrt_launch_jitter(float2* out, int first_sample, int stride, int n, int W, int H, int mode, unsigned int* work_counter, cudaStream_t st) {
+  k_jitter<<<(n + 127) / 128, 128, 0, st>>>(out, first_sample, stride, n, W, H, mode, work_counter);
+  return cudaGetLastError();
+}
+
+// Fused multi-GPU reduce-scatter + tonemap (SURVEY.md §8e "fused variant", spread over the ranks): every rank
+// owns a contiguous slice of the pixels, sums the partial accumulation buffers of ALL ranks for that slice —
+// its own from HBM, the others through NVLink peer mappings (ld.global on cudaIpc-mapped pointers) — and
+// writes (a) the merged float4 sums to its own `sum_out` slice (optional) and (b) the tonemapped pixels
+// (pathtracer.py:634-662) to `ldr_out`, which may itself be a peer mapping of the displaying rank's image
+// buffer (st.global over NVLink). Per rank and frame that is (N-1)/N x 16 B/pixel of NVLink reads instead of
+// the 2 (N-1)/N x 16 B/pixel an all-reduce moves, and no rank handles more than 1/N of the frame.
+__global__ void __launch_bounds__(256) k_merge_slice(const float4* accum, PeerPtrs peers, float4* sum_out,
+                                                     float4* __restrict__ ldr_out, int first, int count, int W, int H, float exposure) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int idx = first + k;
+  float4 a = accum[idx];
+#pragma unroll 1
+  for (int p = 0; p < peers.n; p++) {
+    const float4 b = peers.p[p][idx];
+    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+  }
+  if (sum_out) sum_out[idx] = a;
+  if (ldr_out) {
+    const int i = idx % W, j = idx / W;
+    const float inv = a.w > 0.0f ? 1.0f / a.w : 0.0f;
+    const float ux = (float)i / (float)W - 0.5f, uy = (float)j / (float)H - 0.5f;
+    const float s = (1.0f - 0.9f * fmaxf(sqrtf(ux * ux + uy * uy), 0.0f)) * exposure;
+    ldr_out[idx] = make_float4(saturate(powf(uchimura1(a.x * inv * s), 1.0f / 2.2f)), saturate(powf(uchimura1(a.y * inv * s), 1.0f / 2.2f)),
+                               saturate(powf(uchimura1(a.z * inv * s), 1.0f / 2.2f)), 1.0f);
+  }
+}
+cudaError_t vrt_launch_merge_slice(const float4* accum, const float4* const* peers, int n_peers, float4* sum_out, float4* ldr_out, int first,
+                                   int count, int W, int H, float exposure, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  PeerPtrs pp;
+  pp.n = n_peers;
+  for (int k = 0; k < 8; k++) pp.p[k] = k < n_peers ? peers[k] : nullptr;
+  k_merge_slice<<<(count + 255) / 256, 256, 0, st>>>(accum, pp, sum_out, ldr_out, first, count, W, H, exposure);
   return cudaGetLastError();
 }
 

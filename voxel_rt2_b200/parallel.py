@@ -80,3 +80,98 @@ class PeerMerge:
         for p in self.peers:
             self.r.close_peer_accum(p)
         self.peers = []
+
+
+class FusedMerge:
+    """Per-frame merge of the sample- or tile-sharded accumulation buffers WITHOUT an all-reduce: a fused
+    reduce-scatter + tonemap over NVLink peer memory, spread evenly over the ranks (SURVEY.md §8e "fused
+    variant"). Rank r owns the contiguous pixel slice [r·npx/N, (r+1)·npx/N): one kernel
+    (`vrt_merge_slice`) adds the N partial sums of that slice — its own from HBM, the others through
+    CUDA-IPC peer mappings — applies the tonemap and stores the pixels straight into the displaying
+    rank's image buffer (a peer store). NVLink traffic per rank and frame: (N-1)/N x 16 B/pixel read +
+    16 B/pixel/N written, against 2 (N-1)/N x 16 B/pixel for an all-reduce, and the only collective
+    left is a 4-byte NCCL all-reduce used as a stream-ordered barrier.
+
+    Batches alternate between the two accumulation / image slots of the library, so batch k+1 renders
+    while the peers still read batch k. Per step, on every rank:
+
+        fm.begin(k)                 # slot k & 1, reset_framebuffer (deferred: the kernel overwrites)
+        r.accumulate(spp)
+        fm.merge()                  # barrier k (all partial sums of batch k complete) + merge of the own slice
+        if rank == 0: fm.copy_previous(pinned)   # image of batch k-1: complete since barrier k
+
+    Hazards and what orders them (all in stream order, no host synchronisation):
+      * peers read slot s of batch k only after barrier k;
+      * batch k+2 overwrites slot s on a rank only after barrier k+1, which completes after every rank's
+        merge of batch k;
+      * rank 0 copies image slot s of batch k after barrier k+1 (every rank's merge k precedes it) and
+        joins barrier k+2 only after that copy (`stream_wait_copy`), so the peers' stores of batch k+2
+        cannot overtake it.
+    """
+
+    def __init__(self, renderer, group=None, display_rank=0):
+        import torch
+        import torch.distributed as dist
+
+        self.r, self.group, self.dst = renderer, group, display_rank
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        W, H = renderer.image_res
+        npx = W * H
+        self.first = self.rank * npx // self.world
+        self.count = (self.rank + 1) * npx // self.world - self.first
+        mine = []
+        for s in (0, 1):
+            renderer.set_accum_slot(s)
+            mine.append((renderer.accum_ipc_handle(), renderer.out_ipc_handle()))
+        renderer.set_accum_slot(0)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.peer_accum = [[], []]   # per slot: the other ranks' accumulation buffers, in rank order
+        self.peer_out = [None, None]  # per slot: the displaying rank's image buffer (None on that rank itself)
+        for s in (0, 1):
+            for k, h in enumerate(everyone):
+                if k != self.rank:
+                    self.peer_accum[s].append(renderer.open_peer_accum(h[s][0]))
+            if self.rank != display_rank:
+                self.peer_out[s] = renderer.open_peer_accum(everyone[display_rank][s][1])
+        self._token = torch.zeros(1, device=torch.device("cuda", renderer.device))
+        self.slot, self.k = 0, -1
+
+    def begin(self, k):
+        self.k, self.slot = k, k & 1
+        self.r.set_accum_slot(self.slot)
+        self.r.reset_framebuffer()
+
+    def barrier(self):
+        """Stream-ordered barrier: a 4-byte NCCL all-reduce on the current torch stream."""
+        import torch.distributed as dist
+
+        dist.all_reduce(self._token, group=self.group)
+
+    def merge(self):
+        if self.rank == self.dst:
+            self.r.stream_wait_copy()
+        self.barrier()
+        self.r.merge_slice(self.peer_accum[self.slot], self.first, self.count, ldr_dst=self.peer_out[self.slot])
+
+    def copy_previous(self, out_pinned):
+        """Displaying rank, after merge() of batch k: image of batch k-1 -> pinned host memory (copy engine)."""
+        self.r.set_accum_slot(self.slot ^ 1)
+        self.r.copy_image_async(out_pinned)
+        self.r.set_accum_slot(self.slot)
+
+    def finish(self, out_pinned=None):
+        """After the last batch: one more barrier so every rank's last merge has landed; the displaying rank
+        then copies the last image."""
+        self.barrier()
+        if self.rank == self.dst and out_pinned is not None:
+            self.r.copy_image_async(out_pinned)
+            self.r.wait_image()
+
+    def close(self):
+        for s in (0, 1):
+            for p in self.peer_accum[s]:
+                self.r.close_peer_accum(p)
+            if self.peer_out[s]:
+                self.r.close_peer_accum(self.peer_out[s])
+        self.peer_accum, self.peer_out = [[], []], [None, None]

@@ -14,6 +14,8 @@ from . import _cabi
 from .camera import look_at, perspective
 from .materials import material_table
 
+# part of the sky-cache key: bump when vrt_sky_precompute.cu changes what it computes
+SKY_TABLE_VERSION = "sky-r02"
 HIT_DTYPE = np.dtype([("t", "<f4"), ("cell", "<i4", (3,)), ("normal", "<f4", (3,)), ("flags", "<u4")])
 _ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 
@@ -47,6 +49,7 @@ class Renderer:
         self.sky_res = int(sky_res)
         self.up = tuple(float(x) for x in up)
         self._cloud_passes, self._seed, self._cloud_tex_digest = int(cloud_passes), int(seed), ""
+        self.device = int(device)
         self.current_spp = 0
         self.current_frame = 0
         self.sample_stride = 1   # sample sharding: this renderer draws indices offset, offset+stride, ...
@@ -187,8 +190,8 @@ class Renderer:
             return None
         import hashlib
 
-        key = repr((self.light_direction, self.light_cone_angle, self.light_color, self.use_clouds, self.sky_res, self._cloud_passes,
-                    self._seed, self._cloud_tex_digest))
+        key = repr((SKY_TABLE_VERSION, self.light_direction, self.light_cone_angle, self.light_color, self.use_clouds, self.sky_res,
+                    self._cloud_passes, self._seed, self._cloud_tex_digest))
         return os.path.join(d, "sky_%s.npy" % hashlib.sha256(key.encode()).hexdigest()[:24])
 
     def prepare_data(self):
@@ -204,9 +207,18 @@ class Renderer:
         if path:
             os.makedirs(os.path.dirname(path), exist_ok=True)
             a, b = self.get_sky_tables()
-            tmp = path + ".tmp.npy"
-            np.save(tmp, np.stack([a, b]))
-            os.replace(tmp, path)
+            # one temp file per writer (several ranks may fill the same cache at once); the rename is atomic
+            import tempfile
+
+            fd, tmp = tempfile.mkstemp(prefix=os.path.basename(path) + ".", suffix=".tmp", dir=os.path.dirname(path))
+            try:
+                with os.fdopen(fd, "wb") as f:
+                    np.save(f, np.stack([a, b]))
+                os.replace(tmp, path)
+            except BaseException:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise
 
     def set_tile_shard(self, rank, n):
         self._check(self._lib.vrt_set_tile_shard(self._h, int(rank), int(n)))
@@ -330,6 +342,32 @@ class Renderer:
     def close_peer_accum(self, ptr):
         self._check(self._lib.vrt_close_peer_accum(self._h, C.c_void_p(ptr)))
 
+    def set_accum_slot(self, slot):
+        """Select which of the two accumulation buffers the following calls use (double buffering across GPUs)."""
+        self._check(self._lib.vrt_set_accum_slot(self._h, int(slot)))
+
+    def out_ipc_handle(self):
+        """64-byte cudaIpcMemHandle_t of the tonemapped image buffer (the target of the peers' merge_slice)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.vrt_out_ipc_handle(self._h, buf))
+        return bytes(buf.raw)
+
+    def merge_slice(self, peer_ptrs, first_pixel, n_pixels, ldr_dst=None, write_sums=False):
+        """Fused reduce-scatter + tonemap for this rank's pixel slice (vrt_merge_slice); asynchronous."""
+        n = len(peer_ptrs)
+        arr = (C.c_void_p * max(n, 1))(*peer_ptrs)
+        self._check(self._lib.vrt_merge_slice(self._h, arr, n, int(first_pixel), int(n_pixels), C.c_void_p(ldr_dst or None), 1 if write_sums else 0))
+
+    def copy_image_async(self, out_pinned):
+        """Image buffer as it is (filled by the ranks' merge_slice) -> pinned host memory, on the copy engine."""
+        if out_pinned.dtype != np.float32 or out_pinned.size != self.image_res[0] * self.image_res[1] * 4 or not out_pinned.flags["C_CONTIGUOUS"]:
+            raise ValueError("copy_image_async needs a contiguous float32 [H, W, 4] buffer")
+        self._check(self._lib.vrt_copy_ldr_async(self._h, _fp(out_pinned)))
+        return out_pinned
+
+    def stream_wait_copy(self):
+        self._check(self._lib.vrt_stream_wait_copy(self._h))
+
     def fetch_image_merged(self, peer_ptrs, out=None):
         """Tonemapped image of (own + peers') accumulation buffers, summed inside the tonemap kernel."""
         n = len(peer_ptrs)
@@ -352,7 +390,11 @@ class Renderer:
         w = _Wrap()
         w.__cuda_array_interface__ = {"shape": (self.image_res[1], self.image_res[0], 4), "typestr": "<f4",
                                       "data": (ptr, False), "version": 3}
-        return torch.as_tensor(w, device="cuda")
+        w.owner = self  # the memory belongs to the context: keep it alive as long as the tensor's base object
+        t = torch.as_tensor(w, device=torch.device("cuda", self.device))
+        if t.data_ptr() != ptr:
+            raise RuntimeError("accum_tensor: torch copied the buffer instead of aliasing it (device mismatch?)")
+        return t
 
     def get_sky_tables(self):
         S = self.sky_res
