@@ -925,3 +925,4 @@ def test_accum_slots_deferred_reset_and_merge_slice(vrt):
     st = g.stats()
     assert st["render_launches"] == 40 and st["render_ms_sum"] > 0.0 and st["launches_total"] == 80
     assert (g.fetch_hdr()[..., 3] == 44).all()
+

@@ -3,7 +3,7 @@ import numpy as np
 
 
 def make_pair(vrt, oracle, *, image_res, grid_res, dx=None, sky_res=0, cloud_passes=2, seed=7, jitter=True, max_depth=4,
-              voxel_edges=0.06, exposure=3.0):
+              voxel_edges=0.06, exposure=3.0, sky_format="f32"):
     """A CUDA Renderer and an OracleRenderer with identical configuration."""
     from voxel_rt2_b200.materials import material_table
     import os
@@ -11,7 +11,7 @@ def make_pair(vrt, oracle, *, image_res, grid_res, dx=None, sky_res=0, cloud_pas
     dx = dx if dx is not None else 2.0 / grid_res
     kw = dict(dx=dx, image_res=image_res, voxel_edges=voxel_edges, exposure=exposure, grid_res=grid_res, max_depth=max_depth,
               sky_res=sky_res, cloud_passes=cloud_passes, seed=seed, jitter=jitter)
-    g = vrt.Renderer(**kw)
+    g = vrt.Renderer(sky_format=sky_format, **kw)  # float sky tables: the oracle reads float tables (f16 has its own budget test)
     tex = np.load(os.path.join(os.path.dirname(vrt.__file__), "assets", "cloud_texture.npz"))["tex"]
     o = oracle.OracleRenderer(materials=material_table(), cloud_tex=tex, **kw)
     return g, o
@@ -35,6 +35,8 @@ def renderer_from_reference_fixture(factory, z, **kw):
     W, H = int(z["W"]), int(z["H"])
     R = z["material"].shape[0]
     sky_res = int(z["sky_res"]) if "sky_res" in z else 0
+    if factory.__name__ == "Renderer":
+        kw.setdefault("sky_format", "f32")  # reference vectors are held to the float-table path
     r = factory(dx=2.0 / R, image_res=(W, H), grid_res=R, sky_res=sky_res, seed=int(z["seed"]), jitter=False,
                 voxel_edges=float(z["cfg_voxel_edges"]), **kw)
     r.set_voxels(z["material"], z["color"])

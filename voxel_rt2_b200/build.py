@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvoxelrt.so")
 SOURCES = ["vrt_api.cu", "vrt_render.cu", "vrt_restir.cu", "vrt_temporal.cu", "vrt_build.cu", "vrt_sky_precompute.cu"]
-HEADERS = ["vrt_common.cuh", "vrt_trace.cuh", "vrt_bsdf.cuh", "vrt_sky.cuh", "vrt_restir.cuh", "vrt_internal.h",
+HEADERS = ["vrt_kshared.cuh", "vrt_common.cuh", "vrt_trace.cuh", "vrt_bsdf.cuh", "vrt_sky.cuh", "vrt_restir.cuh", "vrt_internal.h",
            os.path.join("..", "..", "include", "voxelrt.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -65,8 +65,9 @@ HD RayHit raytrace(const Params& P, const uint32_t* __restrict__ upper, f3 o, f3
   if (STATS) tc->rays++;
 
   // ray_aabb_intersection against [0,R]^3 (axes with d == 0 are skipped, as in the reference).
-  // (Skipping the three entry-side divisions for origins inside the box is exact but was measured
-  // 6 % slower: primary and secondary rays share warps, so both variants execute.)
+  // (Skipping the three entry-side divisions for origins inside the box is exact — for d > 0 the exit plane is
+  // always x = R, the entry plane x = 0 — but was measured 6 % slower in round 1 and 5 % slower in round 2 with
+  // the far side computed for every lane and the near side under a branch: profiles/r02d_ab_inside_f16.log.)
   float near_int = -VRT_INF, far_int = VRT_INF;
   slab_axis(o.x, d.x, Rf, near_int, far_int);
   slab_axis(o.y, d.y, Rf, near_int, far_int);
