@@ -270,6 +270,8 @@ def run_reference(args, rank, world):
     o = OracleRenderer(dx=2.0 / R, image_res=(W, H), grid_res=R, sky_res=S, cloud_passes=2, exposure=wl.exposure, seed=1,
                        voxel_edges=wl.voxel_edges, materials=material_table())
     wl.configure(o)
+    if wl.restir:
+        o.set_restir_temporal(True)
     o.prepare_data()
     if wl.sky and args.sky_res > S:
         tabs = [_upsample_table(t, args.sky_res) for t in o.get_sky_tables()]
@@ -339,6 +341,8 @@ def leg_path_or_restir(vrt, torch, name, W, H, device, sky_res, spp_per_step, st
                      voxel_edges=wl.voxel_edges, device=device)
     wl.configure(r)
     r.prepare_data()
+    if wl.restir:
+        r.set_restir_temporal(True)  # config 4: temporal + spatial resampling per frame
     run = (lambda: r.accumulate_restir(spp_per_step)) if wl.restir else (lambda: r.accumulate(spp_per_step))
     for _ in range(3):
         run()
@@ -503,6 +507,8 @@ def main():
     stream = torch.cuda.Stream()
     r.set_stream(stream.cuda_stream)
     wl.configure(r)
+    if wl.restir:
+        r.set_restir_temporal(True)  # config 4: temporal + spatial resampling per frame
     r.set_sample_shard(rank, world)
     t_prep = time.time()
     r.prepare_data()

@@ -142,6 +142,14 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
  * spatial_GRIS(0, 24.0, 32, 1) (pathtracer.py:815-989) resamples 32 neighbours; the frame is then
  * accumulated like a path-traced one. n_frames frames with sample indices first, first+stride... */
 int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, int32_t stride);
+/* Temporal reservoir reuse for vrt_accumulate_restir (BASELINE.json configs[3]: "temporal+spatial resampling per
+ * frame"). No upstream counterpart: the reference allocates two reservoir slots per pixel (pathtracer.py:108-109) and
+ * writes the second (:989) but never reads it. With enable != 0 every frame resamples, between render and
+ * spatial_GRIS, the pixel's canonical reservoir with its own reservoir of the previous frame kept in that second
+ * slot (same shift / pairwise-MIS / merge primitives as spatial_GRIS with one tap; see k_temporal in
+ * csrc/vrt_restir.cu). Static camera: vrt_reset, a changed camera, light or scene drop the history. Default 0
+ * (the reference's behaviour: spatial pass only). */
+int vrt_set_restir_temporal(vrt_ctx* ctx, int32_t enable);
 /* Renderer.accumulate with camera_is_moving = 1 (scene.py:214-228, pathtracer.py:146-150): one
  * frame rendered at render_scale (reference 0.5) with albedo-demodulated diffuse, then
  * temporal_filter_prepass / temporal_filter / temporal_filter_specular (pathtracer.py:1020-1303)

@@ -72,6 +72,8 @@ def load():
     lib.orc_last_ms.argtypes = [P]
     lib.orc_last_ms.restype = C.c_double
     lib.orc_reset.argtypes = [P]
+    lib.orc_set_restir_temporal.argtypes = [P, C.c_int]
+    lib.orc_drop_restir_history.argtypes = [P]
     lib.orc_get_counters.argtypes = [P, C.POINTER(C.c_uint64)]
     lib.orc_fetch_hdr.argtypes = [P, fp]
     lib.orc_fetch_ldr.argtypes = [P, fp]
@@ -297,6 +299,10 @@ class OracleRenderer:
         first = self.sample_offset + self.current_spp * self.sample_stride
         self._lib.orc_accumulate(self._h, first, int(spp), self.sample_stride, 1 if stats else 0, int(self.n_threads))
         self.current_spp += int(spp)
+
+    def set_restir_temporal(self, enable):
+        """Temporal reservoir reuse before the spatial pass (see temporal_reuse_pixel in oracle.cpp)."""
+        self._lib.orc_set_restir_temporal(self._h, 1 if enable else 0)
 
     def accumulate_restir(self, frames=1):
         """accumulate() with USE_RESTIR_PT = True (pathtracer.py:1310-1319): render + spatial_GRIS per frame."""

@@ -20,6 +20,7 @@ ap.add_argument("--sky", type=int, default=0)
 ap.add_argument("--sky-res", type=int, default=3840)
 ap.add_argument("--scene", default="dense")
 ap.add_argument("--restir", type=int, default=0, help="also time N ReSTIR frames")
+ap.add_argument("--temporal", type=int, default=0, help="ReSTIR: temporal reservoir reuse before the spatial pass")
 a = ap.parse_args()
 W, H = [int(x) for x in a.res.split("x")]
 t0 = time.time()
@@ -27,6 +28,10 @@ r = vrt.Renderer(dx=2.0 / a.R, image_res=(W, H), grid_res=a.R, sky_res=a.sky_res
 if a.scene == "dense":
     mat, col = scenes.random_grid(a.R, 0.5, 1234)
     r.set_floor(-1e5, (1, 1, 1))
+elif a.scene == "example3":
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "example3_seed0.npz"))
+    mat, col = z["material"], z["color"]
+    r.set_floor(0.0, (1, 1, 1))
 elif a.scene == "example6":
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "example6_seed0.npz"))
     mat, col = z["material"], z["color"]
@@ -35,7 +40,10 @@ else:
     mat, col = scenes.city(a.R, 0, 50)
     r.set_floor(-0.05, (1, 1, 1))
 r.set_voxels(mat, col)
-r.set_directional_light((1, 1, -1) if a.scene == "example6" else (1, 1, 1), 0.025, (1.3, 0.949 * 1.3, 0.937 * 1.3))
+if a.scene == "example3":
+    r.set_directional_light((1, 1, 1), 0.1, (0.0, 0.0, 0.0))
+else:
+    r.set_directional_light((1, 1, -1) if a.scene == "example6" else (1, 1, 1), 0.025, (1.3, 0.949 * 1.3, 0.937 * 1.3))
 r.set_background_color((0.3, 0.4, 0.6))
 if a.sky:
     r.set_use_physical_sky(True, True)
@@ -54,14 +62,15 @@ for spp in (1, a.spp):
     print("spp/launch=%d: %.3f ms/launch, %.3f ms/frame, %.3f Gpaths/s" % (spp, best, best / spp, W * H * spp / best / 1e6))
 if a.restir:
     r.reset_framebuffer()
+    r.set_restir_temporal(bool(a.temporal))
     r.accumulate_restir(2)
-    best = (1e9, 0, 0)
+    best = (1e9, 0, 0, 0)
     for i in range(a.iters):
         r.accumulate_restir(a.restir)
         st = r.stats()
-        tot = (st["last_render_ms"] + st["last_gris_ms"]) / a.restir
-        best = min(best, (tot, st["last_render_ms"] / a.restir, st["last_gris_ms"] / a.restir))
-    print("restir: %.3f ms/frame (path+reservoir %.3f, gris %.3f), %.3f Gpaths/s" % (best[0], best[1], best[2], W * H / best[0] / 1e6))
+        tot = (st["last_render_ms"] + st["last_gris_ms"] + st["last_temporal_ms"]) / a.restir
+        best = min(best, (tot, st["last_render_ms"] / a.restir, st["last_temporal_ms"] / a.restir, st["last_gris_ms"] / a.restir))
+    print("restir%s: %.3f ms/frame (path+reservoir %.3f, temporal %.3f, gris %.3f), %.3f Gpaths/s" % (" temporal" if a.temporal else "", best[0], best[1], best[2], best[3], W * H / best[0] / 1e6))
 img = r.fetch_image()
 print("resolve ms", r.stats()["last_resolve_ms"], "mean ldr", img[..., :3].mean())
 os.makedirs("gpurun_out", exist_ok=True)

@@ -62,7 +62,8 @@ struct vrt_ctx {
   int jitter_cap = 0;
   unsigned int* d_work = nullptr;
   unsigned long long* d_stats = nullptr;
-  RestirBuffers rb{nullptr, nullptr, nullptr, nullptr, nullptr};  // allocated on first ReSTIR frame
+  RestirBuffers rb{};  // allocated on first ReSTIR frame
+  bool restir_temporal = false, hist_valid = false;  // vrt_set_restir_temporal; history of the previous ReSTIR frame usable
   // moving-camera temporal path (allocated on the first moving frame)
   struct {
     float4 *col_d = nullptr, *col_s = nullptr, *hd[2] = {nullptr, nullptr}, *hs[2] = {nullptr, nullptr}, *out = nullptr, *full = nullptr;
@@ -263,6 +264,7 @@ void vrt_destroy(vrt_ctx* ctx) {
   cudaFree(ctx->mv.col_d), cudaFree(ctx->mv.col_s), cudaFree(ctx->mv.out), cudaFree(ctx->mv.full), cudaFree(ctx->mv.refl), cudaFree(ctx->mv.refl_blur);
   for (int k = 0; k < 2; k++) cudaFree(ctx->mv.hd[k]), cudaFree(ctx->mv.hs[k]), cudaFree(ctx->mv.hsd[k]), cudaFree(ctx->mv.depth[k]), cudaFree(ctx->mv.attr[k]);
   cudaFree(ctx->rb.reservoirs), cudaFree(ctx->rb.gpos), cudaFree(ctx->rb.gattr), cudaFree(ctx->rb.col_d), cudaFree(ctx->rb.col_s), cudaFree(ctx->rb.rc_skyT);
+  cudaFree(ctx->rb.hist_res), cudaFree(ctx->rb.hist_gpos), cudaFree(ctx->rb.hist_gattr), cudaFree(ctx->rb.hist_skyT);
   if (ctx->copy_pending) cudaEventSynchronize(ctx->ev_copied);
   if (ctx->ev_resolved) cudaEventDestroy(ctx->ev_resolved);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
@@ -411,6 +413,7 @@ int vrt_upload_voxels(vrt_ctx* ctx, const int8_t* material, const uint8_t* rgb) 
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->voxels_uploaded = true;
   ctx->prepared = false;
+  ctx->hist_valid = false;
   return VRT_OK;
 }
 
@@ -420,6 +423,9 @@ int vrt_set_camera(vrt_ctx* ctx, const float pos[3], const float view[16], const
   double v[16], p[16], vi[16], pi[16];
   for (int i = 0; i < 16; i++) v[i] = view[i], p[i] = proj[i];
   REQUIRE(invert4(v, vi) && invert4(p, pi), "vrt_set_camera: singular matrix");
+  // temporal reservoir reuse is defined for a static camera: a different camera drops the history
+  if (!ctx->camera_set || memcmp(ctx->view, view, sizeof ctx->view) || memcmp(ctx->proj, proj, sizeof ctx->proj) || memcmp(ctx->cam_pos, pos, sizeof ctx->cam_pos))
+    ctx->hist_valid = false;
   for (int i = 0; i < 16; i++) ctx->inv_view[i] = (float)vi[i], ctx->inv_proj[i] = (float)pi[i];
   memcpy(ctx->cam_pos, pos, sizeof ctx->cam_pos);
   memcpy(ctx->view, view, sizeof ctx->view);
@@ -439,6 +445,7 @@ int vrt_set_light(vrt_ctx* ctx, const float direction[3], float cone_angle, cons
   memcpy(ctx->light_color, rgb, sizeof ctx->light_color);
   ctx->sky_valid = false;  // the sky tables depend on the sun
   ctx->sky_packed_valid = false;
+  ctx->hist_valid = false;
   return VRT_OK;
 }
 
@@ -687,6 +694,14 @@ static int ensure_restir_buffers(vrt_ctx* ctx) {
     CK(cudaMalloc(&ctx->rb.col_s, npx * sizeof(float4)));
     CK(cudaMalloc(&ctx->rb.rc_skyT, npx * sizeof(float4)));
   }
+  if (ctx->restir_temporal && !ctx->rb.hist_res) {
+    CK(cudaMalloc(&ctx->rb.hist_res, npx * 56));
+    CK(cudaMalloc(&ctx->rb.hist_gpos, npx * sizeof(float4)));
+    CK(cudaMalloc(&ctx->rb.hist_gattr, npx * sizeof(uint2)));
+    CK(cudaMalloc(&ctx->rb.hist_skyT, npx * sizeof(float4)));
+    ctx->hist_valid = false;
+  }
+  ctx->rb.temporal = ctx->restir_temporal ? 1 : 0;
   return VRT_OK;
 }
 
@@ -701,7 +716,7 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
   if (rc) return rc;
   if (int rcz = flush_pending_zero(ctx)) return rcz;  // the resampling pass adds its frame to the buffer
   ctx->mv.active = false;
-  while (ctx->frame_events.size() < 3u * (size_t)n_frames) {
+  while (ctx->frame_events.size() < 4u * (size_t)n_frames) {
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
     ctx->frame_events.push_back(e);
@@ -712,25 +727,40 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
     Params P;
     fill_params(ctx, P);
     P.first_sample = (int)s, P.n_samples = 1, P.stride = 1;
-    cudaEvent_t* ev = &ctx->frame_events[3 * (size_t)k];
+    cudaEvent_t* ev = &ctx->frame_events[4 * (size_t)k];
     CK(cudaEventRecord(ev[0], ctx->stream));
     CK(vrt_launch_path_restir(P, ctx->rb, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ev[1], ctx->stream));
-    CK(vrt_launch_gris(P, ctx->rb, s, ctx->stream));
+    if (ctx->restir_temporal) {  // temporal reuse of the previous frame's reservoirs (k_rc_sky + k_temporal), in place
+      CK(vrt_launch_temporal(P, ctx->rb, s, ctx->hist_valid ? 1 : 0, ctx->stream));
+      ctx->hist_valid = true;
+    }
     CK(cudaEventRecord(ev[2], ctx->stream));
+    CK(vrt_launch_gris(P, ctx->rb, s, ctx->stream));
+    CK(cudaEventRecord(ev[3], ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  float render_ms = 0.0f, gris_ms = 0.0f;
+  float render_ms = 0.0f, gris_ms = 0.0f, temporal_ms = 0.0f;
   for (int k = 0; k < n_frames; k++) {
-    float a = 0.0f, b = 0.0f;
-    CK(cudaEventElapsedTime(&a, ctx->frame_events[3 * (size_t)k], ctx->frame_events[3 * (size_t)k + 1]));
-    CK(cudaEventElapsedTime(&b, ctx->frame_events[3 * (size_t)k + 1], ctx->frame_events[3 * (size_t)k + 2]));
-    render_ms += a, gris_ms += b;
+    float a = 0.0f, b = 0.0f, c = 0.0f;
+    const cudaEvent_t* ev = &ctx->frame_events[4 * (size_t)k];
+    CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+    CK(cudaEventElapsedTime(&c, ev[1], ev[2]));
+    CK(cudaEventElapsedTime(&b, ev[2], ev[3]));
+    render_ms += a, gris_ms += b, temporal_ms += c;
   }
   ctx->stats.last_render_ms = render_ms;
   ctx->stats.last_gris_ms = gris_ms;
-  ctx->stats.kernel_launches = 4u * (uint32_t)n_frames;  // k_jitter, k_path, k_rc_sky, k_gris
+  ctx->stats.last_temporal_ms = ctx->restir_temporal ? temporal_ms : 0.0f;
+  ctx->stats.kernel_launches = (ctx->restir_temporal ? 5u : 4u) * (uint32_t)n_frames;  // k_jitter, k_path, k_rc_sky, [k_temporal,] k_gris
   ctx->stats.launches_total += ctx->stats.kernel_launches;
+  return VRT_OK;
+}
+
+int vrt_set_restir_temporal(vrt_ctx* ctx, int32_t enable) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  ctx->restir_temporal = enable != 0;
+  ctx->hist_valid = false;
   return VRT_OK;
 }
 
@@ -888,6 +918,7 @@ int vrt_reset(vrt_ctx* ctx) {
     if (int rcz = flush_pending_zero(ctx)) return rcz;
   ctx->mv.has_prev = false;
   ctx->mv.active = false;
+  ctx->hist_valid = false;
   return VRT_OK;
 }
 

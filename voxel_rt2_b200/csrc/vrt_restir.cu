@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
       canonical_weight = canonical_weight / (center_p_hat * nb.M + center_F_lum * center.M / (float)max_taps);
       canonical_mis_weight += 1.0f - canonical_weight;
       const float p_hat = luminance(s_d + s_s);
-      const float p_hat_from_neighbour = p_hat / jacobian;
+      // the neighbour's own target value: upstream approximates it by the shifted one (pathtracer.py:936); with temporal
+      // reuse on, the integrand the neighbour's reservoir was stored with is used (see k_temporal)
+      const float p_hat_from_neighbour = (RB.temporal ? luminance(nb.z.F) : p_hat) / jacobian;
       float neighbour_mis_weight = p_hat_from_neighbour * nb.M;
       neighbour_mis_weight = neighbour_mis_weight / (p_hat_from_neighbour * nb.M + p_hat * center.M / (float)max_taps);
       if (isbad(neighbour_mis_weight)) neighbour_mis_weight = 0.0f;
@@ -320,6 +322,151 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
   P.accum[pidx] = a;
 }
 
+// Temporal reservoir reuse (vrt_set_restir_temporal). NOT in the reference — its second reservoir slot is written at
+// pathtracer.py:989 and never read — but BASELINE.json configs[3] asks for "temporal+spatial resampling per frame",
+// so the pass is built from the reference's own primitives: it runs between the path kernel and k_gris and is
+// spatial_GRIS (:815-989) with ONE tap, the same pixel's reservoir of the previous frame: the same similarity test
+// (:911), both reconnection shifts (:672-812), pairwise MIS with max_taps = 1 (:928-944), merge (reservoir.py:76-86),
+// a visibility ray for the resampled reconnection (:957-965), the canonical merge, finalize_without_M / 2.
+// Deliberate differences (oracle/oracle.cpp temporal_reuse_pixel states the same algorithm and the measurements):
+// the history slot holds this pass's output (a per-pixel chain; the spatial pass leaks shadowed sun samples and must
+// not be fed back), an escape / sun sample is occluded whenever its ray hits anything, the history's own target
+// value is the integrand it was stored with, and its confidence is capped at 20 x the canonical M.
+// One thread per pixel, no neighbour reads: the pixel's reservoir, canonical integrands and sun transmittance are
+// rewritten in place, the history slot and the previous G-buffer record are updated for the next frame.
+#define VRT_TEMPORAL_M_CAP 20.0f
+__global__ void __launch_bounds__(128, 4) k_temporal(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int hist_valid, int upper_in_smem,
+                                                     int fixed_words) {
+  extern __shared__ uint32_t smem[];
+  float4* s_mats = reinterpret_cast<float4*>(smem);
+  for (int i = threadIdx.x; i < 128 * MAT_ROW_F4; i += blockDim.x) s_mats[i] = P.mats[i];
+  float* s_unorm = reinterpret_cast<float*>(smem + 128 * MAT_ROW_F4 * 4);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = xdiv((float)i, 255.0f);
+  const uint32_t* upper = P.upper;
+  if (upper_in_smem) {
+    uint32_t* s_upper = smem + fixed_words;
+    for (int i = threadIdx.x; i < P.upper_words; i += blockDim.x) s_upper[i] = P.upper[i];
+    upper = s_upper;
+  }
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P.n_tiles) return;
+  const int tile = P.tile_rank + P.tile_n * warp;
+  const int u = (tile % P.tiles_x) * 8 + (lane & 7), v = (tile / P.tiles_x) * 4 + (lane >> 3);
+  const size_t pidx = (size_t)v * P.W + u;
+
+  const float4 gp = RB.gpos[pidx];
+  const uint2 ga = RB.gattr[pidx];
+  float4 pgp = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+  uint2 pga = make_uint2(0u, 0u);
+  if (hist_valid) pgp = RB.hist_gpos[pidx], pga = RB.hist_gattr[pidx];
+  RB.hist_gpos[pidx] = gp;
+  RB.hist_gattr[pidx] = ga;
+  bool reuse = gp.w == 0.0f && pgp.w == 0.0f;
+  RReservoir center, prev;
+  f3 center_x1 = mk3(0.0f), prev_x1 = mk3(0.0f), center_n1 = mk3(0.0f), prev_n1 = mk3(0.0f);
+  float center_dist = 0.0f;
+  if (reuse) {
+    load_reservoir(RB.reservoirs, pidx, s_unorm, center);
+    load_reservoir(RB.hist_res, pidx, s_unorm, prev);
+    prev.M = fminf(prev.M, VRT_TEMPORAL_M_CAP * center.M);
+    center_x1 = f3{gp.x, gp.y, gp.z}, prev_x1 = f3{pgp.x, pgp.y, pgp.z};
+    center_dist = length(center_x1 - P.cam_pos);
+    const float prev_dist = length(prev_x1 - P.cam_pos);
+    center_n1 = decode_unit_vector_3x16(h16val(ga.x), h16val(ga.x >> 16));
+    prev_n1 = decode_unit_vector_3x16(h16val(pga.x), h16val(pga.x >> 16));
+    reuse = prev.M > 0.0f && !(fabsf(prev_dist - center_dist) > 0.1f * center_dist) && !(dot(center_n1, prev_n1) < 0.5f);
+  }
+  if (!reuse) {  // nothing to reuse: the canonical reservoir starts the chain
+#pragma unroll
+    for (int i = 0; i < 7; i++) RB.hist_res[pidx * 7 + i] = RB.reservoirs[pidx * 7 + i];
+    RB.hist_skyT[pidx] = RB.rc_skyT[pidx];
+    return;
+  }
+  GrisCtx G;
+  G.mats = s_mats, G.unorm8 = s_unorm;
+  G.cam_pos = P.cam_pos, G.light_dir = P.light_dir, G.sun_rad = P.light_weight * P.light_color;
+  G.light_cos_max = P.light_cos_max, G.light_pdf_axis = cone_sample_pdf(P.light_cos_max, 1.0f);
+  const uint32_t key = path_key((uint32_t)pidx, frame, P.seed);
+  int center_mat_id, prev_mat_id;
+  const Mat center_mat = decode_material(G, ga.y, center_mat_id);
+  const Mat prev_mat = decode_material(G, pga.y, prev_mat_id);
+  f3 c_d, c_s, s_d, s_s;
+  float c_jacobian, jacobian;
+  shift_sample(G, prev_x1, prev_n1, prev_mat, prep_dst(G, prev_x1, prev_n1), center, prep_rc(G, center.z, RB.rc_skyT + pidx), c_d, c_s, c_jacobian);
+  shift_sample(G, center_x1, center_n1, center_mat, prep_dst(G, center_x1, center_n1), prev, prep_rc(G, prev.z, RB.hist_skyT + pidx), s_d, s_s, jacobian);
+  const float center_F_lum = luminance(center.z.F);
+  const float center_p_hat_at_prev = luminance(c_d + c_s) * c_jacobian;
+  float canonical_weight = center_p_hat_at_prev * prev.M;
+  canonical_weight = canonical_weight / (center_p_hat_at_prev * prev.M + center_F_lum * center.M);
+  if (isbad(canonical_weight)) canonical_weight = 0.0f;
+  const float canonical_mis_weight = 1.0f + (1.0f - canonical_weight);
+  const float p_hat = luminance(s_d + s_s);
+  const float p_hat_from_prev = luminance(prev.z.F) / jacobian;
+  float prev_mis_weight = p_hat_from_prev * prev.M;
+  prev_mis_weight = prev_mis_weight / (p_hat_from_prev * prev.M + p_hat * center.M);
+  if (isbad(prev_mis_weight)) prev_mis_weight = 0.0f;
+  RReservoir out;
+  rinit(out);
+  f3 chosen_F_d = mk3(0.0f), chosen_F_s = mk3(0.0f);
+  bool from_history = false;
+  {
+    const float in_w = prev.weight * p_hat * jacobian * prev_mis_weight;
+    out.M += prev.M;
+    if (in_w > 0.0f) {
+      out.weight += in_w;
+      if (rnd(key, 99) * out.weight <= in_w) {
+        out.z = prev.z;
+        out.z.F = s_d + s_s;
+        chosen_F_d = s_d, chosen_F_s = s_s;
+        from_history = true;
+      }
+    }
+  }
+  bool force_add_canonical = false;
+  if (out.weight > 0.0f) {
+    const bool esc = is_vec_zero(out.z.rc_normal);
+    const f3 dir = esc ? out.z.rc_pos : normalize(out.z.rc_pos - center_x1);
+    const f3 org = center_x1 + center_n1 * (0.003f * center_dist);
+    Hit sh = next_hit<false>(P, upper, s_unorm, org, dir, true, nullptr, nullptr);
+    const float actual_dist = esc ? VRT_INF : length(center_x1 - out.z.rc_pos);
+    if (sh.closest < VRT_INF && (esc || fabsf(sh.closest - actual_dist) > 0.1f * actual_dist)) {
+      out.weight = 0.0f;
+      force_add_canonical = true;
+    }
+  }
+  {
+    const float in_w = center.weight * center_F_lum * canonical_mis_weight;
+    out.M += center.M;
+    if (in_w > 0.0f) {
+      out.weight += in_w;
+      if (rnd(key, 100) * out.weight <= in_w || force_add_canonical) {
+        out.z = center.z;
+        const float4 cd = RB.col_d[pidx], cs4 = RB.col_s[pidx];
+        chosen_F_d = f3{cd.x, cd.y, cd.z};
+        chosen_F_s = f3{cs4.x, cs4.y, cs4.z};
+        from_history = false;
+      }
+    }
+  }
+  const float ph = luminance(out.z.F);  // finalize_without_M, then / (valid + 1)
+  out.weight = (ph < 1e-6f ? 0.0f : out.weight / ph) / 2.0f;
+  if (!is_vec_zero(out.z.rc_normal)) out.z.cached_jacobian_term = jacobian_term(out.z.rc_pos, out.z.rc_normal, center_x1);
+  uint32_t w[14];
+  encode_reservoir(out, w);
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    const uint2 t = make_uint2(w[2 * i], w[2 * i + 1]);
+    RB.reservoirs[pidx * 7 + i] = t;
+    RB.hist_res[pidx * 7 + i] = t;
+  }
+  RB.col_d[pidx] = make_float4(chosen_F_d.x, chosen_F_d.y, chosen_F_d.z, 0.0f);
+  RB.col_s[pidx] = make_float4(chosen_F_s.x, chosen_F_s.y, chosen_F_s.z, 0.0f);
+  const float4 T = from_history ? RB.hist_skyT[pidx] : RB.rc_skyT[pidx];
+  RB.rc_skyT[pidx] = T;
+  RB.hist_skyT[pidx] = T;
+}
+
 }  // namespace
 
 cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t frame, cudaStream_t st) {
@@ -327,7 +474,17 @@ cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t f
   size_t sm = vrt_render_smem_bytes(P, &uis);
   const int fixed_words = 128 * MAT_ROW_F4 * 4 + 256;
   int blocks = (P.n_tiles * 32 + 127) / 128;
-  k_rc_sky<<<(P.W * P.H + 127) / 128, 128, 0, st>>>(P, RB);
+  if (!RB.temporal) k_rc_sky<<<(P.W * P.H + 127) / 128, 128, 0, st>>>(P, RB);  // with temporal reuse on, vrt_launch_temporal ran it already
   k_gris<<<blocks, 128, sm, st>>>(P, RB, frame, uis, fixed_words);
+  return cudaGetLastError();
+}
+
+cudaError_t vrt_launch_temporal(const Params& P, const RestirBuffers& RB, uint32_t frame, int hist_valid, cudaStream_t st) {
+  int uis;
+  size_t sm = vrt_render_smem_bytes(P, &uis);
+  const int fixed_words = 128 * MAT_ROW_F4 * 4 + 256;
+  int blocks = (P.n_tiles * 32 + 127) / 128;
+  k_rc_sky<<<(P.W * P.H + 127) / 128, 128, 0, st>>>(P, RB);
+  k_temporal<<<blocks, 128, sm, st>>>(P, RB, frame, hist_valid, uis, fixed_words);
   return cudaGetLastError();
 }

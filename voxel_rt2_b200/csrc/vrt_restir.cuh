@@ -103,6 +103,13 @@ struct RestirBuffers {
   float4* col_d;
   float4* col_s;
   float4* rc_skyT;  // sun transmittance at the reservoir's reconnection vertex (k_rc_sky), read by k_gris
+  // temporal reuse (vrt_set_restir_temporal): the second reservoir slot of pathtracer.py:108-109 — the previous
+  // frame's temporally resampled reservoir of every pixel with its G-buffer record and sun transmittance
+  uint2* hist_res;
+  float4* hist_gpos;
+  uint2* hist_gattr;
+  float4* hist_skyT;
+  int temporal;  // 1: spatial_GRIS takes the neighbour's own target value from its stored integrand
 };
 
 // Outputs of the moving-camera variant of the path kernel (pathtracer.py:535-546,628-632).

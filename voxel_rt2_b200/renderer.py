@@ -238,6 +238,10 @@ class Renderer:
         self.current_spp += int(spp)
         self.current_frame += int(spp)
 
+    def set_restir_temporal(self, enable):
+        """Temporal reservoir reuse before the spatial pass of accumulate_restir (vrt_set_restir_temporal)."""
+        self._check(self._lib.vrt_set_restir_temporal(self._h, 1 if enable else 0))
+
     def accumulate_restir(self, frames=1):
         """accumulate() with USE_RESTIR_PT = True (pathtracer.py:15,1310-1319): per frame one path per
         pixel into a reservoir, then spatial_GRIS(0, 24.0, 32, 1), then accumulation."""
