@@ -65,8 +65,16 @@ enum { PIX_IDLE = -1, PIX_DONE = -2 };
 #ifndef VRT_PASS1_MIN_LANES
 #define VRT_PASS1_MIN_LANES 14 // lanes with a fresh shadow ray that justify a second trace pass in the same iteration
 #endif
+#ifndef VRT_PATH_THREADS
+#define VRT_PATH_THREADS 640   // threads per CTA of the static-camera path kernel: ONE CTA of 20 warps per SM instead of five of 4
+                               // (same occupancy; +1.2 % dense, +2.1 % example6, +4.3 % city: the staged tables are loaded once per SM
+                               // and co-scheduled warps share instruction-cache lines, profiles/r02h_ab_path.log)
+#endif
 #ifndef VRT_PATH_MIN_BLOCKS
-#define VRT_PATH_MIN_BLOCKS 5  // resident CTAs per SM the register allocation is tuned for
+#define VRT_PATH_MIN_BLOCKS (640 / VRT_PATH_THREADS)  // 20 resident warps per SM: the register allocation (96) is tuned for it
+#endif
+#ifndef VRT_RESTIR_THREADS
+#define VRT_RESTIR_THREADS 128  // ... of the ReSTIR / moving-camera variants (12 resident warps per SM)
 #endif
 
 // RESTIR = true is the USE_RESTIR_PT variant of render (pathtracer.py:15): besides the pixel
@@ -79,7 +87,7 @@ enum { PIX_IDLE = -1, PIX_DONE = -2 };
 // the G-buffer the reprojecting temporal filters need (NDC depth, octahedral normal, material,
 // virtual reflection depth; pathtracer.py:535-546) is written next to the two colour buffers.
 template <bool STATS, int MODE, bool SKY16 = false>
-__global__ void __launch_bounds__(128, MODE != 0 ? 3 : VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem, RestirBuffers RB, MovingOut MO) {
+__global__ void __launch_bounds__(MODE != 0 ? VRT_RESTIR_THREADS : VRT_PATH_THREADS, MODE != 0 ? 384 / VRT_RESTIR_THREADS : VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem, RestirBuffers RB, MovingOut MO) {
   constexpr bool RESTIR = MODE == 1;
   constexpr bool MOVING = MODE == 2;
   extern __shared__ uint32_t smem[];
@@ -641,14 +649,15 @@ static cudaError_t launch_path_t(const Params& P, int sm_count, cudaStream_t st,
   int uis;
   size_t sm = smem_bytes(P, &uis);
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<STATS, MODE, SKY16>, 128, sm);
+  constexpr int threads = MODE != 0 ? VRT_RESTIR_THREADS : VRT_PATH_THREADS;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<STATS, MODE, SKY16>, threads, sm);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   int blocks = sm_count * per_sm;  // persistent: one wave, a multiple of the SM count
-  int max_useful = (P.n_tiles + 3) / 4;
+  int max_useful = (P.n_tiles + threads / 32 - 1) / (threads / 32);
   if (blocks > max_useful) blocks = max_useful > 0 ? max_useful : 1;
   if (blocks_out) *blocks_out = blocks;
-  k_path<STATS, MODE, SKY16><<<blocks, 128, sm, st>>>(P, uis, RB, MO);
+  k_path<STATS, MODE, SKY16><<<blocks, threads, sm, st>>>(P, uis, RB, MO);
   return cudaGetLastError();
 }
 

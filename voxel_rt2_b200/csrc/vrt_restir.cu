@@ -153,10 +153,21 @@ __global__ void __launch_bounds__(128) k_rc_sky(const __grid_constant__ Params P
   RB.rc_skyT[pidx] = make_float4(T.x, T.y, T.z, 0.0f);
 }
 
-#ifndef VRT_GRIS_MIN_BLOCKS
-#define VRT_GRIS_MIN_BLOCKS 4  // 128 registers, 200 B of spills: measured 3.6 % faster than 2 or 3 blocks
+#ifndef VRT_GRIS_THREADS
+#define VRT_GRIS_THREADS 512  // ONE CTA of 16 warps per SM instead of four of 4: 5.19 -> 3.80 ms at 1080p (profiles/r02g_ab_gris.log)
 #endif
-__global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int upper_in_smem, int fixed_words) {
+#ifndef VRT_GRIS_MIN_BLOCKS
+#define VRT_GRIS_MIN_BLOCKS (512 / VRT_GRIS_THREADS)  // 128 registers, 200 B of spills: measured 3.6 % faster than fewer resident warps
+#endif
+// The kernel is instruction-fetch bound (ncu r02f: 4.5 no-instruction stalls per issued instruction, issue slots 35 %):
+// each tap-loop body is ~17 KB of BSDF code and the resident warps drift apart inside it. Launching the 16 resident warps
+// of an SM as ONE CTA (they start together and stay loosely in step) took 27 % off the kernel. VRT_GRIS_SYNC = k
+// additionally puts a CTA barrier after every k-th tap of both loops; measured slower for every k (the barrier waits
+// for the slowest warp of 16), so it is off.
+#ifndef VRT_GRIS_SYNC
+#define VRT_GRIS_SYNC 0
+#endif
+__global__ void __launch_bounds__(VRT_GRIS_THREADS, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int upper_in_smem, int fixed_words) {
   extern __shared__ uint32_t smem[];
   // same staging layout as the render kernels: materials, UNORM8 table, upper pyramid
   float4* s_mats = reinterpret_cast<float4*>(smem);
@@ -172,8 +183,13 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
   __syncthreads();
 
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+#if VRT_GRIS_SYNC
+  const bool in_range = warp < P.n_tiles;  // every thread of the CTA has to reach the barriers
+  const int tile = P.tile_rank + P.tile_n * (in_range ? warp : 0);
+#else
   if (warp >= P.n_tiles) return;
   const int tile = P.tile_rank + P.tile_n * warp;
+#endif
   const int u = (tile % P.tiles_x) * 8 + (lane & 7), v = (tile / P.tiles_x) * 4 + (lane >> 3);
   const int W = P.W, H = P.H;
   const size_t pidx = (size_t)v * W + u;
@@ -189,39 +205,55 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
   RReservoir center;
   load_reservoir(RB.reservoirs, pidx, s_unorm, center);
   const float4 gp = RB.gpos[pidx];
-  f3 out_d, out_s;
-  if (gp.w != 0.0f) {  // primary ray escaped: pass the sample through (pathtracer.py:854-856)
-    out_d = center.z.F;
-    out_s = mk3(0.0f);
-  } else {
-    const uint2 ga = RB.gattr[pidx];
-    const uint32_t seed = hash3((uint32_t)u >> 3, (uint32_t)v >> 3, frame * 2u);
-    const float angle_shift = (float)((seed & 0x007FFFFFu) | 0x3F800000u) / 4294967295.0f * VRT_PI;
-    const float radius_shift = rnd(key, 65);
-    RReservoir out;
-    rinit(out);
-    const f3 center_x1{gp.x, gp.y, gp.z};
-    const float center_dist = length(center_x1 - P.cam_pos);
-    const f3 center_n1 = decode_unit_vector_3x16(h16val(ga.x), h16val(ga.x >> 16));
-    int center_mat_id;
-    const Mat center_mat = decode_material(G, ga.y, center_mat_id);
-    int valid_samples = 0;
-    float canonical_mis_weight = 1.0f;
-    f3 chosen_F_d = mk3(0.0f), chosen_F_s = mk3(0.0f);
-    const float center_F_lum = luminance(center.z.F);
-    const RcPre center_rc = prep_rc(G, center.z, RB.rc_skyT + pidx);
-    const DstPre center_dst = prep_dst(G, center_x1, center_n1);
-    // The tap loop is split in two so that each loop body inlines ONE copy of shift() (~17 KB of
-    // BSDF code): with both shifts in one body the loop was 40 KB, beyond the SM's instruction
-    // cache, and the kernel was instruction-fetch bound (ncu: 3.0 no-instruction stalls per issue).
-    // Pass A shifts the centre sample to every accepted neighbour (needs the neighbour's G-buffer
-    // record only) and keeps p_hat(centre -> tap) and the tap's pixel index in local memory;
-    // pass B shifts each neighbour's sample to the centre and merges, in the reference's tap order.
-    float tap_center_p_hat[32];
-    int tap_index[32];
+  // a pixel whose primary ray escaped passes its sample through (pathtracer.py:854-856) and takes no part in the tap loops
+#if VRT_GRIS_SYNC
+  const bool live = in_range && gp.w == 0.0f;
+#else
+  const bool live = gp.w == 0.0f;
+#endif
+  f3 out_d = center.z.F, out_s = mk3(0.0f);
+  const uint2 ga = RB.gattr[pidx];
+  const uint32_t seed = hash3((uint32_t)u >> 3, (uint32_t)v >> 3, frame * 2u);
+  const float angle_shift = (float)((seed & 0x007FFFFFu) | 0x3F800000u) / 4294967295.0f * VRT_PI;
+  const float radius_shift = rnd(key, 65);
+  RReservoir out;
+  rinit(out);
+  const f3 center_x1{gp.x, gp.y, gp.z};
+  const float center_dist = length(center_x1 - P.cam_pos);
+  const f3 center_n1 = decode_unit_vector_3x16(h16val(ga.x), h16val(ga.x >> 16));
+  int center_mat_id;
+  const Mat center_mat = decode_material(G, ga.y, center_mat_id);
+  int valid_samples = 0;
+  float canonical_mis_weight = 1.0f;
+  f3 chosen_F_d = mk3(0.0f), chosen_F_s = mk3(0.0f);
+  const float center_F_lum = luminance(center.z.F);
+  const RcPre center_rc = prep_rc(G, center.z, RB.rc_skyT + pidx);
+  const DstPre center_dst = prep_dst(G, center_x1, center_n1);
+  // The tap loop is split in two so that each loop body inlines ONE copy of shift() (~17 KB of
+  // BSDF code): with both shifts in one body the loop was 40 KB, beyond the SM's instruction
+  // cache, and the kernel was instruction-fetch bound (ncu: 3.0 no-instruction stalls per issue).
+  // Pass A shifts the centre sample to every accepted neighbour (needs the neighbour's G-buffer
+  // record only) and keeps p_hat(centre -> tap) and the tap's pixel index in local memory;
+  // pass B shifts each neighbour's sample to the centre and merges, in the reference's tap order.
+  // Each body sits in a do { } while (0) so that `continue` leaves the tap, not the iteration: with
+  // VRT_GRIS_SYNC every thread of the CTA reaches the barrier that closes the iteration.
+#if VRT_GRIS_SYNC
+#define GRIS_TAP_SYNC(i)                                \
+  do {                                                  \
+    if (((i) + 1) % VRT_GRIS_SYNC == 0) __syncthreads(); \
+  } while (0)
+#else
+#define GRIS_TAP_SYNC(i) \
+  do {                   \
+  } while (0)
+#endif
+  float tap_center_p_hat[32];
+  int tap_index[32];
 #pragma unroll 1
-    for (int i = 0; i < max_taps; i++) {
+  for (int i = 0; i < max_taps; i++) {
+    do {
       tap_index[i] = -1;
+      if (!live) continue;
       const float golden_angle = 2.399963229728f;
       const float angle = ((float)i + angle_shift) * golden_angle;
       const float offset_radius = sqrtf(((float)i + radius_shift) / (float)max_taps) * max_radius;
@@ -246,9 +278,12 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
       shift_sample(G, neighbour_x1, neighbour_n1, neighbour_mat, prep_dst(G, neighbour_x1, neighbour_n1), center, center_rc, c_d, c_s, c_jacobian);
       tap_center_p_hat[i] = luminance(c_d + c_s) * c_jacobian;
       tap_index[i] = (int)ti;
-    }
+    } while (0);
+    GRIS_TAP_SYNC(i);
+  }
 #pragma unroll 1
-    for (int i = 0; i < max_taps; i++) {
+  for (int i = 0; i < max_taps; i++) {
+    do {
       const int ti = tap_index[i];
       if (ti < 0) continue;
       RReservoir nb;
@@ -280,7 +315,14 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
         }
       }
       valid_samples += 1;
-    }
+    } while (0);
+    GRIS_TAP_SYNC(i);
+  }
+#undef GRIS_TAP_SYNC
+#if VRT_GRIS_SYNC
+  if (!in_range) return;
+#endif
+  if (live) {
     // visibility of the resampled reconnection (pathtracer.py:957-965)
     bool force_add_canonical = false;
     if (out.weight > 0.0f) {
@@ -335,7 +377,10 @@ __global__ void __launch_bounds__(128, VRT_GRIS_MIN_BLOCKS) k_gris(const __grid_
 // One thread per pixel, no neighbour reads: the pixel's reservoir, canonical integrands and sun transmittance are
 // rewritten in place, the history slot and the previous G-buffer record are updated for the next frame.
 #define VRT_TEMPORAL_M_CAP 20.0f
-__global__ void __launch_bounds__(128, 4) k_temporal(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int hist_valid, int upper_in_smem,
+#ifndef VRT_TEMPORAL_THREADS
+#define VRT_TEMPORAL_THREADS 128
+#endif
+__global__ void __launch_bounds__(VRT_TEMPORAL_THREADS, 512 / VRT_TEMPORAL_THREADS) k_temporal(const __grid_constant__ Params P, RestirBuffers RB, uint32_t frame, int hist_valid, int upper_in_smem,
                                                      int fixed_words) {
   extern __shared__ uint32_t smem[];
   float4* s_mats = reinterpret_cast<float4*>(smem);
@@ -473,9 +518,9 @@ cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t f
   int uis;
   size_t sm = vrt_render_smem_bytes(P, &uis);
   const int fixed_words = 128 * MAT_ROW_F4 * 4 + 256;
-  int blocks = (P.n_tiles * 32 + 127) / 128;
+  int blocks = (P.n_tiles * 32 + VRT_GRIS_THREADS - 1) / VRT_GRIS_THREADS;
   if (!RB.temporal) k_rc_sky<<<(P.W * P.H + 127) / 128, 128, 0, st>>>(P, RB);  // with temporal reuse on, vrt_launch_temporal ran it already
-  k_gris<<<blocks, 128, sm, st>>>(P, RB, frame, uis, fixed_words);
+  k_gris<<<blocks, VRT_GRIS_THREADS, sm, st>>>(P, RB, frame, uis, fixed_words);
   return cudaGetLastError();
 }
 
@@ -483,8 +528,8 @@ cudaError_t vrt_launch_temporal(const Params& P, const RestirBuffers& RB, uint32
   int uis;
   size_t sm = vrt_render_smem_bytes(P, &uis);
   const int fixed_words = 128 * MAT_ROW_F4 * 4 + 256;
-  int blocks = (P.n_tiles * 32 + 127) / 128;
+  int blocks = (P.n_tiles * 32 + VRT_TEMPORAL_THREADS - 1) / VRT_TEMPORAL_THREADS;
   k_rc_sky<<<(P.W * P.H + 127) / 128, 128, 0, st>>>(P, RB);
-  k_temporal<<<blocks, 128, sm, st>>>(P, RB, frame, hist_valid, uis, fixed_words);
+  k_temporal<<<blocks, VRT_TEMPORAL_THREADS, sm, st>>>(P, RB, frame, hist_valid, uis, fixed_words);
   return cudaGetLastError();
 }
