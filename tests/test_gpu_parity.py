@@ -1023,3 +1023,52 @@ def test_restir_temporal_reuse_lowers_the_error_on_example3(vrt):
     # both estimators lose a few per cent of energy to upstream's W <= 50 / radiance <= 300 clamps on this scene (oracle,
     # 3 seeds x 40 frames: spatial 0.966, temporal + spatial 0.944 of the path-traced mean)
     assert abs(out[True][1] - 1.0) < 0.10 and abs(out[True][1] / out[False][1] - 1.0) < 0.05
+
+
+def test_scene_finish_modes_restir_and_hits(vrt, oracle, tmp_path, monkeypatch):
+    """VRT_MODE through the reference-facing entry point (Scene.finish, /root/reference/scene.py:171): `hits` dumps the
+    BASELINE config-1 buffer of the example1 fixture scene bit-exactly (committed oracle fixture), `restir` renders
+    reservoir frames with temporal + spatial resampling and agrees with the Renderer driven directly."""
+    import hashlib
+    import os
+
+    from voxel_rt2_b200.scene import Scene
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gold, "example1_seed0.npz"))
+    monkeypatch.delenv("VRT_SKY_CACHE", raising=False)
+    monkeypatch.setenv("VRT_RES", "640x640")
+    monkeypatch.setenv("VRT_MODE", "hits")
+    s = Scene(voxel_edges=float(z["voxel_edges"]), exposure=float(z["exposure"]))   # example1.py:5
+    s.voxel_material[:] = z["material"]
+    s.voxel_color[:] = z["color"]
+    s.set_floor(float(z["floor_height"]), z["floor_color"], int(z["floor_material"]))
+    s.set_directional_light(z["light_dir"], float(z["light_noise"]), z["light_color"])
+    s.set_background_color(z["background"])
+    out = tmp_path / "hits.npz"
+    hits = s.finish(out=str(out))
+    assert hashlib.sha256(hits.tobytes()).hexdigest() == str(np.load(os.path.join(gold, "hits_example1_640.npz"))["sha256"])
+    saved = np.load(out)
+    assert np.array_equal(saved["t"].view(np.uint32), hits["t"].view(np.uint32)) and np.array_equal(saved["flags"], hits["flags"])
+    # ReSTIR mode on the example3 fixture scene
+    z3 = np.load(os.path.join(gold, "example3_seed0.npz"))
+    monkeypatch.setenv("VRT_RES", "160x120")
+    monkeypatch.setenv("VRT_MODE", "restir")
+    monkeypatch.setenv("VRT_SEED", "4")
+    s = Scene(voxel_edges=0, exposure=30)                               # example3.py:5
+    s.voxel_material[:] = z3["material"]
+    s.voxel_color[:] = z3["color"]
+    s.set_floor(0, (1.0, 1.0, 1.0))                                    # example3.py:7
+    img = s.finish(spp=6, out=str(tmp_path / "restir.png"))
+    assert (tmp_path / "restir.png").exists() and img.shape == (120, 160, 4) and s.last_stats["mode"] == "restir"
+    g = vrt.Renderer(dx=1.0 / 64, image_res=(160, 120), grid_res=128, sky_res=0, seed=4, voxel_edges=0.0, exposure=30.0)
+    g.set_voxels(z3["material"], z3["color"])
+    g.set_floor(0.0, (1.0, 1.0, 1.0))
+    g.set_directional_light((1, 1, 1), 0.1, (0.0, 0.0, 0.0))
+    g.prepare_data()
+    g.set_restir_temporal(True)
+    g.accumulate_restir(6)
+    assert np.array_equal(g.fetch_image(), img)
+    with pytest.raises(ValueError):
+        monkeypatch.setenv("VRT_MODE", "bogus")
+        s.finish(spp=1)

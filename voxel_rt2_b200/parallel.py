@@ -169,9 +169,13 @@ class FusedMerge:
             self.r.wait_image()
 
     def close(self):
+        """Unmap the peers' buffers; collective: nobody frees a buffer a peer still has mapped."""
+        import torch.distributed as dist
+
         for s in (0, 1):
             for p in self.peer_accum[s]:
                 self.r.close_peer_accum(p)
             if self.peer_out[s]:
                 self.r.close_peer_accum(self.peer_out[s])
         self.peer_accum, self.peer_out = [[], []], [None, None]
+        dist.barrier(group=self.group)

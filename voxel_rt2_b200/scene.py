@@ -10,6 +10,15 @@ returns. Everything the reference hard-codes is an environment override so examp
 unchanged:
     VRT_RES=1920x1080  VRT_GRID=128  VRT_SPP=64  VRT_SKY_RES=3840  VRT_OUT=path.png
     VRT_DEVICE=0  VRT_SEED=0  VRT_BATCH=8 (samples per launch)
+    VRT_MODE=pt|restir|hits   pt: path tracing (default); restir: the USE_RESTIR_PT mode (pathtracer.py:15), one
+                              reservoir frame per sample, with temporal reuse unless VRT_RESTIR_TEMPORAL=0;
+                              hits: BASELINE config 1, the primary-hit buffer (+ sun shadow bit) written as .npz
+    VRT_GPUS=N                run the script on N GPUs of this box: it is re-launched under torch.distributed.run
+                              (one process per GPU); a script already started by torchrun is recognised by RANK /
+                              WORLD_SIZE. VRT_SHARD=tiles (default: interleaved 8x4 tiles of one frame) | samples
+                              (rank r renders sample indices r, r+N, ...; ReSTIR mode always shards samples, one
+                              reservoir chain per GPU). The partial buffers are merged by the fused peer-memory
+                              reduce-scatter + tonemap kernel (parallel.FusedMerge); rank 0 writes the image.
 Voxels live in host NumPy arrays (material int8[R,R,R], colour uint8[R,R,R,3], index + R/2)
 until finish() uploads them once (voxel_world.py:6-25 semantics: colour clamp + u8 truncation,
 material cast to int8)."""
@@ -68,8 +77,33 @@ class Camera:
         return self._lookat_pos
 
 
+def _relaunch_on_gpus():
+    """VRT_GPUS=N outside torchrun: replace this process by `python -m torch.distributed.run ... <script>` so that
+    the unchanged example script runs once per GPU (scene authoring is deterministic, every rank builds the same
+    scene). Done when the Scene is constructed, before any authoring work."""
+    n = int(os.environ.get("VRT_GPUS", "1") or "1")
+    if n <= 1 or "RANK" in os.environ or "WORLD_SIZE" in os.environ:
+        return
+    import socket
+    import sys
+
+    import __main__
+
+    script = getattr(__main__, "__file__", None)
+    if not script:
+        raise RuntimeError("VRT_GPUS needs a script to re-launch (interactive sessions: start it under torchrun yourself)")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    argv = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+            "--master-port", str(port), script] + sys.argv[1:]
+    os.execv(sys.executable, argv)
+
+
 class Scene:
     def __init__(self, voxel_edges=0.06, exposure=3, *, renderer_factory=None):
+        if renderer_factory is None:
+            _relaunch_on_gpus()
         self.grid_res = int(os.environ.get("VRT_GRID", "128"))
         self.voxel_dx = 2.0 / self.grid_res  # VOXEL_DX = 1/64 at 128^3 (scene.py:11): world box [-1,1)^3
         self.image_res = _env_res()
@@ -155,7 +189,7 @@ class Scene:
             self._renderer = factory(
                 dx=self.voxel_dx, image_res=self.image_res, up=(0, 1, 0), voxel_edges=self.voxel_edges, exposure=self.exposure,
                 grid_res=self.grid_res, sky_res=int(os.environ.get("VRT_SKY_RES", "3840")) if self._physical_sky else 0,
-                device=int(os.environ.get("VRT_DEVICE", "0")), seed=int(os.environ.get("VRT_SEED", "0")))
+                device=int(os.environ.get("LOCAL_RANK", os.environ.get("VRT_DEVICE", "0"))), seed=int(os.environ.get("VRT_SEED", "0")))
         return self._renderer
 
     def _configure(self, r):
@@ -168,38 +202,110 @@ class Scene:
         r.set_look_at(*self.camera.look_at)
 
     def finish(self, spp=None, out=None):
-        """Headless replacement of the frame loop (scene.py:171-297)."""
-        print(HELP_MSG)
+        """Headless replacement of the frame loop (scene.py:171-297). Returns the tonemapped image (float32 [H, W, 4]),
+        or the primary-hit records in VRT_MODE=hits; ranks other than 0 of a multi-GPU run return None."""
+        mode = os.environ.get("VRT_MODE", "pt").lower()
+        if mode not in ("pt", "restir", "hits"):
+            raise ValueError("VRT_MODE must be pt, restir or hits")
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        if rank == 0:
+            print(HELP_MSG)
         spp = int(spp if spp is not None else os.environ.get("VRT_SPP", "64"))
         batch = max(1, int(os.environ.get("VRT_BATCH", "8")))
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
         r = self.renderer
         self._configure(r)
-        t0 = time.time()
-        r.prepare_data()
-        t_prep = time.time() - t0
-        t0 = time.time()
-        done = 0
-        while done < spp:
-            n = min(batch, spp - done)
-            r.accumulate(n)
-            done += n
-        img = r.fetch_image()
-        dt = time.time() - t0
-        W, H = self.image_res
-        print("%d samples took %.3f s (%.3f ms/frame, %.1f Mpaths/s); prepare %.2f s" % (spp, dt, 1e3 * dt / spp, W * H * spp / dt / 1e6, t_prep))
-        self.last_image = img
-        self.last_stats = {"spp": spp, "seconds": dt, "prepare_seconds": t_prep}
         out = out or os.environ.get("VRT_OUT")
         if out is None:
             import __main__
 
             os.makedirs("screenshot", exist_ok=True)
             main_filename = os.path.split(getattr(__main__, "__file__", "scene"))[1]
-            out = os.path.join("screenshot", "%s-%s.png" % (main_filename, datetime.today().strftime("%Y-%m-%d-%H%M%S")))
+            out = os.path.join("screenshot", "%s-%s.%s" % (main_filename, datetime.today().strftime("%Y-%m-%d-%H%M%S"), "npz" if mode == "hits" else "png"))
+        if mode == "hits":  # BASELINE config 1: primary hit + sun shadow ray on the cone axis, no TAA jitter (vrt_trace_primary)
+            t0 = time.time()
+            r.prepare_data()
+            hits = r.trace_primary() if rank == 0 else None
+            if rank == 0:
+                print("hit buffer %dx%d took %.3f s including the scene build" % (self.image_res[0], self.image_res[1], time.time() - t0))
+                if out:
+                    np.savez_compressed(out, t=hits["t"], cell=hits["cell"], normal=hits["normal"], flags=hits["flags"])
+                    print("Hit buffer has been saved to %s" % out)
+            self.last_image = hits
+            return hits
+        fm = stream_ctx = None
+        if world > 1:
+            import contextlib
+
+            from . import parallel
+
+            shard = "samples" if mode == "restir" else os.environ.get("VRT_SHARD", "tiles").lower()
+            if shard == "tiles":
+                parallel.shard_tiles(r, rank, world)
+                n_local = spp
+            else:
+                parallel.shard_samples(r, rank, world)
+                n_local = (spp - rank + world - 1) // world  # sample indices rank, rank + world, ... below spp
+            stream = torch.cuda.Stream()
+            r.set_stream(stream.cuda_stream)
+            stream_ctx = torch.cuda.stream(stream)
+        else:
+            n_local = spp
+        t0 = time.time()
+        r.prepare_data()
+        t_prep = time.time() - t0
+        if mode == "restir":
+            r.set_restir_temporal(os.environ.get("VRT_RESTIR_TEMPORAL", "1") != "0")
+        t0 = time.time()
+        with (stream_ctx if stream_ctx is not None else _null_context()):
+            if world > 1:
+                fm = parallel.FusedMerge(r)
+                fm.begin(0)
+            done = 0
+            while done < n_local:
+                n = min(batch, n_local - done)
+                if mode == "restir":
+                    r.accumulate_restir(n)
+                else:
+                    r.accumulate(n)
+                done += n
+            if fm is not None:
+                import torch
+
+                fm.merge()
+                host = torch.empty((self.image_res[1], self.image_res[0], 4), dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
+                fm.finish(host)
+                img = host
+            else:
+                img = r.fetch_image()
+        dt = time.time() - t0
+        if fm is not None:
+            fm.close()
+        W, H = self.image_res
+        self.last_stats = {"spp": spp, "seconds": dt, "prepare_seconds": t_prep, "mode": mode, "gpus": world}
+        if rank != 0:
+            return None
+        print("%d samples took %.3f s (%.3f ms/frame, %.1f Mpaths/s)%s; prepare %.2f s" % (
+            spp, dt, 1e3 * dt / spp, W * H * spp / dt / 1e6, " on %d GPUs" % world if world > 1 else "", t_prep))
+        self.last_image = img
         if out:
             save_image(img, out)
             print("Screenshot has been saved to %s" % out)
         return img
+
+
+class _null_context:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 def save_image(img, path):
