@@ -510,6 +510,8 @@ def main():
     if wl.restir:
         r.set_restir_temporal(True)  # config 4: temporal + spatial resampling per frame
     r.set_sample_shard(rank, world)
+    if world > 1:
+        r.set_sky_shard(rank, world)  # every rank computes 1/N of the sky-table rows, one all-gather per table
     t_prep = time.time()
     r.prepare_data()
     t_prep = time.time() - t_prep

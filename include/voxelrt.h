@@ -113,6 +113,17 @@ int vrt_set_cloud_texture(vrt_ctx* ctx, const uint8_t* tex256x256x3);
  * transmittance LUT, cloud passes and the two sky tables. */
 int vrt_prepare(vrt_ctx* ctx);
 
+/* Sharded sky precompute (one process per GPU): after vrt_set_sky_shard(rank, n) vrt_prepare computes
+ * only rows [rank, rank + 1) * sky_res / n of the two tables (compute_skybox is already sliced by rows upstream,
+ * atmos.py:159-189) and leaves them incomplete; the caller gathers the other ranks' slices into the device buffers
+ * returned by vrt_sky_tables_device_ptr (float4 texels [x][y], one all-gather per table) and then calls
+ * vrt_sky_tables_complete. Rendering calls fail with VRT_ERR_NOT_PREPARED in between. sky_res must be a multiple of n. */
+int vrt_set_sky_shard(vrt_ctx* ctx, int32_t rank, int32_t n);
+int vrt_sky_tables_device_ptr(vrt_ctx* ctx, void** scattering, void** transmittance, uint64_t* bytes_each);
+int vrt_sky_tables_complete(vrt_ctx* ctx);
+/* 1 while a sharded precompute awaits its gather (between vrt_prepare and vrt_sky_tables_complete), else 0. */
+int vrt_sky_tables_pending(vrt_ctx* ctx);
+
 /* Sky tables as float3 [sky_res][sky_res] (atmos.py:68-69). get: copy out after vrt_prepare;
  * set: install externally computed tables (skips the precompute in vrt_prepare). */
 int vrt_get_sky_tables(vrt_ctx* ctx, float* scattering, float* transmittance);

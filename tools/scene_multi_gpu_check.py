@@ -55,6 +55,25 @@ def main():
             out[key + "_max_abs_diff"] = float(np.abs(img - one).max())
             out[key + "_mean_ratio"] = float(img[..., :3].mean() / one[..., :3].mean())
         dist.barrier()
+    # ---- sharded sky precompute (rows of the tables split over the ranks + all-gather) vs the whole precompute on one GPU
+    def sky(shard):
+        g = vrt.Renderer(dx=2.0 / 32, image_res=(64, 32), grid_res=32, sky_res=256, cloud_passes=2, seed=2, device=local)
+        g.set_voxels(*scenes.random_grid(32, 0.2, 3))
+        g.set_directional_light((1, 1, -1), 0.025, (1.3, 1.2, 1.2))
+        g.set_use_physical_sky(True, True)
+        if shard:
+            g.set_sky_shard(rank, world)
+        g.prepare_data()
+        return g.get_sky_tables(), g.stats()["sky_precompute_ms"]
+
+    (sa, ta), ms_shard = sky(True)
+    (sb, tb), ms_full = sky(False)
+    same_sky = bool(np.array_equal(sa, sb) and np.array_equal(ta, tb))
+    flags = [None] * world
+    dist.all_gather_object(flags, same_sky)
+    if rank == 0:
+        out["sharded_sky_identical_on_every_rank"] = bool(all(flags))
+        out["sky_precompute_ms_sharded_vs_full"] = [ms_shard, ms_full]
     # ---- FusedMerge over a sequence of double-buffered batches vs all-reduce + tonemap
     R, W, H = 64, 512, 256
     r = vrt.Renderer(dx=2.0 / R, image_res=(W, H), grid_res=R, sky_res=0, seed=7, device=local)
@@ -98,7 +117,7 @@ def main():
         out["fused_vs_allreduce_max_abs_diff_per_batch"] = ok
         out["world"] = world
         print(json.dumps(out))
-        assert out["pt_tiles_identical"], out
+        assert out["pt_tiles_identical"] and out["sharded_sky_identical_on_every_rank"], out
         assert out["pt_samples_max_abs_diff"] < 1e-5, out
         assert abs(out["restir_samples_mean_ratio"] - 1.0) < 0.05, out
         assert max(ok) < 1e-6, out

@@ -48,6 +48,8 @@ struct vrt_ctx {
   uint8_t* d_cloud_tex = nullptr;
   float* d_cloud_ambient = nullptr;
   bool sky_valid = false, cloud_tex_set = false, lut_valid = false;
+  int sky_shard_rank = 0, sky_shard_n = 1;  // vrt_set_sky_shard: vrt_prepare computes rows [rank, rank + 1) * sky_res / n only
+  bool sky_partial = false;                  // ... and the tables are complete only after vrt_sky_tables_complete
 
   // frame buffers. Two accumulation slots (the second allocated on first use, vrt_set_accum_slot): while the
   // partial sums of batch k are being merged across GPUs, batch k+1 renders into the other slot.
@@ -519,18 +521,64 @@ int vrt_prepare(vrt_ctx* ctx) {
     B.use_clouds = ctx->use_clouds;
     B.cloud_passes = ctx->cfg.cloud_passes > 0 ? ctx->cfg.cloud_passes : 1;
     B.seed = ctx->cfg.seed;
+    const int rows = ctx->cfg.sky_res / ctx->sky_shard_n;
+    B.first_texel = ctx->sky_shard_rank * rows * ctx->cfg.sky_res;
+    B.n_texels = rows * ctx->cfg.sky_res;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(vrt_launch_sky_precompute(B, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->stats.sky_precompute_ms, ctx->ev0, ctx->ev1));
-    ctx->sky_valid = true;
     ctx->lut_valid = true;
     ctx->sky_packed_valid = false;
+    if (ctx->sky_shard_n > 1) {
+      // only this rank's rows are filled: the caller gathers the other ranks' slices into the buffers
+      // (vrt_sky_tables_device_ptr) and then calls vrt_sky_tables_complete
+      ctx->sky_partial = true;
+      ctx->prepared = true;
+      return VRT_OK;
+    }
+    ctx->sky_valid = true;
   }
   if (int rc = sync_packed_sky(ctx)) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->prepared = true;
+  return VRT_OK;
+}
+
+int vrt_set_sky_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(n >= 1 && rank >= 0 && rank < n, "vrt_set_sky_shard: need 0 <= rank < n");
+  REQUIRE(n == 1 || (ctx->cfg.sky_res > 0 && ctx->cfg.sky_res % n == 0), "vrt_set_sky_shard: sky_res must be a multiple of n");
+  ctx->sky_shard_rank = rank, ctx->sky_shard_n = n;
+  return VRT_OK;
+}
+
+int vrt_sky_tables_device_ptr(vrt_ctx* ctx, void** scattering, void** transmittance, uint64_t* bytes_each) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(scattering && transmittance, "vrt_sky_tables_device_ptr: null pointer");
+  REQUIRE(ctx->cfg.sky_res > 0, "vrt_sky_tables_device_ptr: context was created with sky_res = 0");
+  *scattering = ctx->d_sky_scatter, *transmittance = ctx->d_sky_trans;
+  if (bytes_each) *bytes_each = (uint64_t)ctx->cfg.sky_res * ctx->cfg.sky_res * sizeof(float4);
+  return VRT_OK;
+}
+
+int vrt_sky_tables_pending(vrt_ctx* ctx) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  return ctx->sky_partial ? 1 : 0;
+}
+
+int vrt_sky_tables_complete(vrt_ctx* ctx) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  if (!ctx->sky_partial) {
+    ctx->err = "vrt_sky_tables_complete: no sharded sky precompute is pending";
+    return VRT_ERR_NOT_PREPARED;
+  }
+  ctx->sky_partial = false;
+  ctx->sky_valid = true;
+  ctx->sky_packed_valid = false;
+  if (int rc = sync_packed_sky(ctx)) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
   return VRT_OK;
 }
 
@@ -567,6 +615,7 @@ int vrt_set_sky_tables(vrt_ctx* ctx, const float* scattering, const float* trans
     CK(cudaStreamSynchronize(ctx->stream));
   }
   ctx->sky_valid = true;
+  ctx->sky_partial = false;
   ctx->sky_packed_valid = false;
   return sync_packed_sky(ctx);
 }

@@ -45,5 +45,6 @@ struct SkyBuild {
   int use_clouds;
   int cloud_passes;
   uint32_t seed;
+  int first_texel, n_texels;  // the slice of the S x S tables this call computes (texel = x * S + y)
 };
 cudaError_t vrt_launch_sky_precompute(const SkyBuild& B, cudaStream_t st);

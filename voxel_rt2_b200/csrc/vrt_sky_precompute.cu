@@ -280,8 +280,8 @@ __device__ void clouds_scattering(const SkyBuild& B, f3 sbx, f3 sby, f3 ray_orig
 // accumulate_clouds, all passes of one texel: scatter.xyz += 1.2*in_scatter/n, trans.x += sat(T)/n,
 // trans.y += mean distance / n  (atmos.py:140-157)
 __global__ void __launch_bounds__(128) k_clouds(SkyBuild B) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B.S * B.S) return;
+  const int idx = B.first_texel + blockIdx.x * blockDim.x + threadIdx.x;  // this rank's slice of the table (vrt_set_sky_shard)
+  if (idx >= B.first_texel + B.n_texels) return;
   const float fres = 1.0f / (float)B.S;
   const int u = idx / B.S, v = idx % B.S;
   f3 sbx, sby;
@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(128) k_clouds(SkyBuild B) {
 
 // compute_skybox (atmos.py:159-189)
 __global__ void __launch_bounds__(128) k_skybox(SkyBuild B) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B.S * B.S) return;
+  const int idx = B.first_texel + blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B.first_texel + B.n_texels) return;
   const float fres = 1.0f / (float)B.S;
   const int u = idx / B.S, v = idx % B.S;
   f3 sbx, sby;
@@ -354,7 +354,8 @@ cudaError_t vrt_launch_sky_precompute(const SkyBuild& B, cudaStream_t st) {
   if (e != cudaSuccess) return e;
   k_trans_lut<<<(256 * 128 + 127) / 128, 128, 0, st>>>(B.trans_lut);
   k_cloud_ambient<<<1, 1, 0, st>>>(B);
-  const int n = B.S * B.S;
+  const int n = B.n_texels;
+  if (n <= 0) return cudaGetLastError();
   k_clouds<<<(n + 127) / 128, 128, 0, st>>>(B);
   k_skybox<<<(n + 127) / 128, 128, 0, st>>>(B);
   return cudaGetLastError();

@@ -52,6 +52,8 @@ class Renderer:
         self.device = int(device)
         self.current_spp = 0
         self.current_frame = 0
+        self._sky_tables_installed = False
+        self._sky_shard = None
         self.sample_stride = 1   # sample sharding: this renderer draws indices offset, offset+stride, ...
         self.sample_offset = 0
         cfg = _cabi.vrt_config(
@@ -205,9 +207,17 @@ class Renderer:
             tabs = np.load(path, mmap_mode="r")
             if tabs.shape == (2, self.sky_res, self.sky_res, 3):
                 self.set_sky_tables(np.ascontiguousarray(tabs[0]), np.ascontiguousarray(tabs[1]))
-                path = None  # tables installed: vrt_prepare skips the precompute
+                path = False  # tables installed: vrt_prepare skips the precompute
+        shard = getattr(self, "_sky_shard", None)
+        sharded = bool(shard and shard[1] > 1 and self.use_physical_atmosphere and path is not False and not self._sky_tables_installed)
+        if sharded:
+            self._check(self._lib.vrt_set_sky_shard(self._h, shard[0], shard[1]))
         self._check(self._lib.vrt_prepare(self._h))
-        if path:
+        if sharded and self._lib.vrt_sky_tables_pending(self._h) == 1:
+            self._gather_sky_slices(shard[2])
+        else:
+            sharded = False
+        if path and (not sharded or shard[0] == 0):
             os.makedirs(os.path.dirname(path), exist_ok=True)
             a, b = self.get_sky_tables()
             # one temp file per writer (several ranks may fill the same cache at once); the rename is atomic
@@ -222,6 +232,33 @@ class Renderer:
                 if os.path.exists(tmp):
                     os.remove(tmp)
                 raise
+
+    def set_sky_shard(self, rank, n, group=None):
+        """One process per GPU: prepare_data() computes rows [rank, rank+1) * sky_res / n of the sky tables on this GPU
+        and all-gathers the rest from the other ranks (torch.distributed, one all-gather per table) instead of
+        repeating the whole precompute on every rank. Needs sky_res % n == 0 (3840 = 2^8 * 15: n = 2, 4, 8 are fine)."""
+        if self.sky_res and self.sky_res % int(n) == 0:
+            self._sky_shard = (int(rank), int(n), group)
+
+    def _gather_sky_slices(self, group):
+        import torch
+        import torch.distributed as dist
+
+        a, b, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self._lib.vrt_sky_tables_device_ptr(self._h, C.byref(a), C.byref(b), C.byref(nbytes)))
+        rank, n = self._sky_shard[0], self._sky_shard[1]
+        self.synchronize()
+        for ptr in (a.value, b.value):
+            class _Wrap:
+                pass
+
+            w = _Wrap()
+            w.__cuda_array_interface__ = {"shape": (n, self.sky_res // n * self.sky_res * 4), "typestr": "<f4", "data": (ptr, False), "version": 3}
+            t = torch.as_tensor(w, device=torch.device("cuda", self.device))
+            assert t.data_ptr() == ptr
+            dist.all_gather_into_tensor(t, t[rank].clone(), group=group)
+        torch.cuda.synchronize(self.device)
+        self._check(self._lib.vrt_sky_tables_complete(self._h))
 
     def set_tile_shard(self, rank, n):
         self._check(self._lib.vrt_set_tile_shard(self._h, int(rank), int(n)))
@@ -412,6 +449,7 @@ class Renderer:
 
     def set_sky_tables(self, scattering, transmittance):
         S = self.sky_res
+        self._sky_tables_installed = True
         self._check(self._lib.vrt_set_sky_tables(self._h, _fp(_f32(scattering, S * S * 3)), _fp(_f32(transmittance, S * S * 3))))
 
     def get_trans_lut(self):

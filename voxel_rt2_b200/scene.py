@@ -252,6 +252,7 @@ class Scene:
             else:
                 parallel.shard_samples(r, rank, world)
                 n_local = (spp - rank + world - 1) // world  # sample indices rank, rank + world, ... below spp
+            r.set_sky_shard(rank, world)  # 1/N of the sky-table rows per GPU + one all-gather per table
             stream = torch.cuda.Stream()
             r.set_stream(stream.cuda_stream)
             stream_ctx = torch.cuda.stream(stream)
