@@ -195,6 +195,12 @@ int vrt_reset(vrt_ctx* ctx);
  * one slot while the partial sums of batch k in the other are still being merged by the peers. */
 int vrt_set_accum_slot(vrt_ctx* ctx, int32_t slot);
 
+/* Accumulation checkpoint (upstream keeps its history buffers on the device only, pathtracer.py:39-44):
+ * copy the float4 sums (rgb sums, w = samples) of the current slot to / from host memory, so a long render can be
+ * saved and resumed (Scene.finish: VRT_CHECKPOINT=file.npz). */
+int vrt_get_accum(vrt_ctx* ctx, float* rgba_sums);
+int vrt_set_accum(vrt_ctx* ctx, const float* rgba_sums);
+
 /* Device pointer of the float4 [height][width] accumulation buffer (rgb sums, w = samples),
  * for device-side collectives (NCCL all-reduce through torch.distributed). */
 int vrt_accum_device_ptr(vrt_ctx* ctx, void** ptr, uint64_t* bytes);

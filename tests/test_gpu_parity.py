@@ -1072,3 +1072,32 @@ def test_scene_finish_modes_restir_and_hits(vrt, oracle, tmp_path, monkeypatch):
     with pytest.raises(ValueError):
         monkeypatch.setenv("VRT_MODE", "bogus")
         s.finish(spp=1)
+
+
+def test_accumulation_checkpoint_round_trip(vrt):
+    """vrt_get_accum / vrt_set_accum: 4 + 4 samples with a checkpoint in between and a fresh context in
+    the middle equal 8 samples in one go, bit for bit."""
+    R = 32
+
+    def mk():
+        g = vrt.Renderer(dx=2.0 / R, image_res=(64, 32), grid_res=R, sky_res=0, seed=4)
+        g.set_voxels(*scenes.random_grid(R, 0.3, 9))
+        g.set_directional_light((1, 1, 0.5), 0.05, (1.2, 1.1, 1.0))
+        g.set_background_color((0.3, 0.4, 0.6))
+        g.prepare_data()
+        return g
+
+    a = mk()
+    a.accumulate(4)
+    a.accumulate(4)
+    want = a.fetch_hdr()
+    b = mk()
+    b.accumulate(4)
+    sums, spp = b.get_accumulation()
+    assert spp == 4 and (sums[..., 3] == 4).all()
+    c = mk()
+    c.set_accumulation(sums, spp)
+    c.accumulate(4)
+    assert np.array_equal(c.fetch_hdr(), want)
+    with pytest.raises(ValueError):
+        c.set_accumulation(sums[:8], 4)

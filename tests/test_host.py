@@ -183,3 +183,62 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
     assert j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_finish_modes_dispatch_through_the_renderer_surface(tmp_path, monkeypatch):
+    """VRT_MODE / VRT_CHECKPOINT of Scene.finish with a recording stub renderer (no GPU): `hits` calls trace_primary and
+    writes an .npz, `restir` switches temporal reuse on and calls accumulate_restir, a checkpoint is written and a second
+    run resumes from it instead of starting over."""
+    from voxel_rt2_b200.renderer import HIT_DTYPE
+    from voxel_rt2_b200.scene import Scene
+
+    calls = []
+
+    class Rec:
+        def __init__(self, **kw):
+            self.spp = 0
+
+        def get_accumulation(self):
+            return np.full((8, 8, 4), float(self.spp), np.float32), self.spp
+
+        def set_accumulation(self, sums, spp):
+            calls.append(("set_accumulation", int(spp)))
+            self.spp = int(spp)
+
+        def accumulate(self, n):
+            calls.append(("accumulate", n))
+            self.spp += n
+
+        def __getattr__(self, n):
+            def f(*a, **k):
+                calls.append((n,) + tuple(x for x in a if not isinstance(x, np.ndarray)))
+                if n == "fetch_image":
+                    return np.zeros((8, 8, 4), np.float32)
+                if n == "trace_primary":
+                    return np.zeros((8, 8), HIT_DTYPE)
+
+            return f
+
+    monkeypatch.setenv("VRT_RES", "8x8")
+    monkeypatch.setenv("VRT_MODE", "hits")
+    s = Scene(renderer_factory=Rec)
+    h = s.finish(out=str(tmp_path / "h.npz"))
+    assert h.dtype == HIT_DTYPE and "trace_primary" in [c[0] for c in calls] and "accumulate" not in [c[0] for c in calls]
+    assert set(np.load(tmp_path / "h.npz").files) == {"t", "cell", "normal", "flags"}
+    calls.clear()
+    monkeypatch.setenv("VRT_MODE", "restir")
+    Scene(renderer_factory=Rec).finish(spp=5, out=str(tmp_path / "r.png"))
+    assert ("set_restir_temporal", True) in calls and sum(c[1] for c in calls if c[0] == "accumulate_restir") == 5
+    calls.clear()
+    monkeypatch.setenv("VRT_MODE", "pt")
+    monkeypatch.setenv("VRT_CHECKPOINT", str(tmp_path / "ck.npz"))
+    monkeypatch.setenv("VRT_CHECKPOINT_EVERY", "8")
+    Scene(renderer_factory=Rec).finish(spp=16, out=str(tmp_path / "a.png"))
+    z = np.load(tmp_path / "ck.npz")
+    assert int(z["spp"]) == 16 and float(z["sums"][0, 0, 0]) == 16.0
+    calls.clear()
+    Scene(renderer_factory=Rec).finish(spp=24, out=str(tmp_path / "b.png"))   # resumes at 16, renders 8 more
+    assert ("set_accumulation", 16) in calls and sum(c[1] for c in calls if c[0] == "accumulate") == 8
+    with pytest.raises(ValueError):
+        monkeypatch.setenv("VRT_MODE", "nope")
+        Scene(renderer_factory=Rec).finish(spp=1)

@@ -940,6 +940,27 @@ int vrt_get_reservoirs(vrt_ctx* ctx, void* out) {
   return VRT_OK;
 }
 
+// Accumulation checkpoint: the float4 sums + sample counts of the current slot, to / from host memory.
+int vrt_get_accum(vrt_ctx* ctx, float* rgba_sums) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(rgba_sums, "vrt_get_accum: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = flush_pending_zero(ctx)) return rc;
+  CK(cudaMemcpyAsync(rgba_sums, ctx->d_accum, (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRT_OK;
+}
+int vrt_set_accum(vrt_ctx* ctx, const float* rgba_sums) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  REQUIRE(rgba_sums, "vrt_set_accum: null pointer");
+  CK(cudaSetDevice(ctx->device));
+  ctx->zero_pending[ctx->cur_slot] = false;
+  ctx->mv.active = false;
+  CK(cudaMemcpyAsync(ctx->d_accum, rgba_sums, (size_t)ctx->cfg.width * ctx->cfg.height * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRT_OK;
+}
+
 int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(n >= 1 && rank >= 0 && rank < n, "vrt_set_tile_shard: need 0 <= rank < n");

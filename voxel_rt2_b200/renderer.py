@@ -325,6 +325,20 @@ class Renderer:
         self._check(self._lib.vrt_spatial_gris(self._h, int(frame), *[b.ctypes.data_as(C.c_void_p) for b in bufs]))
         self.current_spp += 1
 
+    def get_accumulation(self):
+        """Checkpoint: float32 [H, W, 4] sums (rgb sums, w = samples accumulated) and the sample counter."""
+        out = np.empty((self.image_res[1], self.image_res[0], 4), np.float32)
+        self._check(self._lib.vrt_get_accum(self._h, _fp(out)))
+        return out, self.current_spp
+
+    def set_accumulation(self, sums, spp):
+        """Resume from a checkpoint: the next accumulate() continues with sample index `spp`."""
+        sums = np.ascontiguousarray(sums, np.float32)
+        if sums.shape != (self.image_res[1], self.image_res[0], 4):
+            raise ValueError("accumulation checkpoint has the wrong shape")
+        self._check(self._lib.vrt_set_accum(self._h, _fp(sums)))
+        self.current_spp = int(spp)
+
     def reset_framebuffer(self):  # pathtracer.py:664-668
         self.current_spp = 0
         self._check(self._lib.vrt_reset(self._h))

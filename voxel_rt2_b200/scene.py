@@ -13,6 +13,8 @@ unchanged:
     VRT_MODE=pt|restir|hits   pt: path tracing (default); restir: the USE_RESTIR_PT mode (pathtracer.py:15), one
                               reservoir frame per sample, with temporal reuse unless VRT_RESTIR_TEMPORAL=0;
                               hits: BASELINE config 1, the primary-hit buffer (+ sun shadow bit) written as .npz
+    VRT_CHECKPOINT=file.npz   (pt mode, one GPU) save the accumulation sums + sample counter every VRT_CHECKPOINT_EVERY
+                              (256) samples and resume from the file if it exists
     VRT_GPUS=N                run the script on N GPUs of this box: it is re-launched under torch.distributed.run
                               (one process per GPU); a script already started by torchrun is recognised by RANK /
                               WORLD_SIZE. VRT_SHARD=tiles (default: interleaved 8x4 tiles of one frame) | samples
@@ -269,6 +271,15 @@ class Scene:
                 fm = parallel.FusedMerge(r)
                 fm.begin(0)
             done = 0
+            ckpt = os.environ.get("VRT_CHECKPOINT") if (world == 1 and mode == "pt") else None
+            every = max(1, int(os.environ.get("VRT_CHECKPOINT_EVERY", "256")))
+            if ckpt and os.path.exists(ckpt):  # resume: the accumulation sums and the sample counter of an earlier run
+                z = np.load(ckpt)
+                if tuple(z["sums"].shape) == (self.image_res[1], self.image_res[0], 4) and int(z["spp"]) <= n_local:
+                    r.set_accumulation(z["sums"], int(z["spp"]))
+                    done = int(z["spp"])
+                    print("resumed from %s at %d samples" % (ckpt, done))
+            last_saved = done
             while done < n_local:
                 n = min(batch, n_local - done)
                 if mode == "restir":
@@ -276,6 +287,11 @@ class Scene:
                 else:
                     r.accumulate(n)
                 done += n
+                if ckpt and (done - last_saved >= every or done == n_local):
+                    sums, _ = r.get_accumulation()
+                    np.savez(ckpt + ".tmp.npz", sums=sums, spp=np.int64(done))
+                    os.replace(ckpt + ".tmp.npz", ckpt)
+                    last_saved = done
             if fm is not None:
                 import torch
 
