@@ -718,8 +718,19 @@ def main():
                                 "sample": "ReSTIR workloads: run `bench.py --impl reference --workload %s` for the CPU arm" % args.workload}
     r.close()
 
-    # ---- the other BASELINE configurations, outside the timed region, each with its own clock record
+    # ---- the other BASELINE configurations, outside the timed region, each with its own clock record.
+    # A watchdog guards the main line: if a leg hangs (a rank lost in a collective, say), every rank gives up after
+    # 240 s, rank 0 prints the line measured so far with the failure noted, and the processes exit.
     if args.workload == "config3" and not args.no_other_configs:
+        def give_up():
+            if rank == 0:
+                line["other_configs"] = {"failed": "a leg did not finish within 240 s; the main measurement above is unaffected"}
+                emit(line)
+            os._exit(0)
+
+        watchdog = threading.Timer(240.0, give_up)
+        watchdog.daemon = True
+        watchdog.start()
         others = {}
         if world == 1:
             others["config1"] = _leg(lambda: leg_config1(vrt, torch, local_rank))
@@ -730,6 +741,7 @@ def main():
             c5 = _leg(lambda: leg_config5(vrt, torch, dist, rank, world, local_rank))
             if rank == 0:
                 others["config5"] = c5
+        watchdog.cancel()
         if rank == 0 and others:
             line["other_configs"] = others
     if rank == 0:
