@@ -66,12 +66,14 @@ enum { PIX_IDLE = -1, PIX_DONE = -2 };
 #define VRT_PASS1_MIN_LANES 14 // lanes with a fresh shadow ray that justify a second trace pass in the same iteration
 #endif
 #ifndef VRT_PATH_THREADS
-#define VRT_PATH_THREADS 640   // threads per CTA of the static-camera path kernel: ONE CTA of 20 warps per SM instead of five of 4
-                               // (same occupancy; +1.2 % dense, +2.1 % example6, +4.3 % city: the staged tables are loaded once per SM
-                               // and co-scheduled warps share instruction-cache lines, profiles/r02h_ab_path.log)
+#define VRT_PATH_THREADS 768   // threads per CTA of the static-camera path kernel: ONE CTA per SM (the staged tables are loaded once per
+                               // SM, co-scheduled warps share instruction-cache lines). Measured, config 3 / example6 / city in G paths/s
+                               // (profiles/r02h_ab_path.log, r02r_ab_threads.log): 5 x 128 threads 3.36 / 1.86 / 3.48; 1 x 640 (96 regs)
+                               // 3.40 / 1.90 / 3.64; 1 x 768 (24 warps, 80 regs, 48 B of spills) 3.44 / 1.92 / 3.67; 1 x 896 (72 regs)
+                               // 3.30 / 1.94 / 3.66; 1 x 1024 (64 regs) 3.14 / 1.94 / 3.65
 #endif
 #ifndef VRT_PATH_MIN_BLOCKS
-#define VRT_PATH_MIN_BLOCKS (640 / VRT_PATH_THREADS)  // 20 resident warps per SM: the register allocation (96) is tuned for it
+#define VRT_PATH_MIN_BLOCKS 1
 #endif
 #ifndef VRT_RESTIR_THREADS
 #define VRT_RESTIR_THREADS 128  // ... of the ReSTIR / moving-camera variants (12 resident warps per SM)
