@@ -526,7 +526,13 @@ def main():
     r.current_spp = 0
 
     fused = world > 1 and args.merge == "fused" and not wl.restir
-    fm = parallel.FusedMerge(r) if fused else None
+    fm, merge_note = None, None
+    if fused:
+        try:
+            fm = parallel.FusedMerge(r)  # raises on every rank or on none
+        except RuntimeError as e:       # no CUDA-IPC peer access on this box: the NCCL all-reduce path still works
+            fused, merge_note = False, "fused merge unavailable (%s): NCCL all-reduce used" % e
+            r.set_accum_slot(0)
     accum = r.accum_tensor() if (world > 1 and not fused) else None
     counter = [0]
 
@@ -655,7 +661,7 @@ def main():
         elif fused:
             par = "sample-shard x%d + fused peer-memory reduce-scatter/tonemap per step (4-byte NCCL barrier)" % world
         else:
-            par = "sample-shard x%d + 1 NCCL all-reduce/step" % world
+            par = "sample-shard x%d + 1 NCCL all-reduce/step" % world + ("; " + merge_note if merge_note else "")
         line = {
             "metric": "paths_per_sec_depth4_1080p", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_frame": ms_total / args.steps / spp,

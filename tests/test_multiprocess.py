@@ -83,3 +83,73 @@ def test_world_size_2_gloo_merge_equals_unsharded(oracle, mode):
     else:
         # same sample set, summed in a different order (running means vs sums)
         assert np.allclose(merged[..., :3], full[..., :3], rtol=2e-5, atol=1e-6)
+
+
+def _fm_worker(rank, world, port, q):
+    """FusedMerge set-up with a stand-in renderer: rank 1 cannot export its buffers. Both ranks must raise
+    (a rank that failed alone before the handle exchange would leave the other waiting in the collective), and the
+    pixel slices of a healthy set-up must tile the frame."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    from voxel_rt2_b200 import parallel
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Fake:
+        image_res, device = (30, 7), 0
+
+        def __init__(self, broken):
+            self.broken = broken
+
+        def set_accum_slot(self, s):
+            pass
+
+        def accum_ipc_handle(self):
+            if self.broken:
+                raise RuntimeError("no IPC here")
+            return b"a" * 64
+
+        def out_ipc_handle(self):
+            return b"o" * 64
+
+        def open_peer_accum(self, h):
+            raise RuntimeError("no peer access")
+
+        def close_peer_accum(self, p):
+            pass
+
+    results = []
+    for broken_rank in (1, None):  # export fails on rank 1; then: export fine, peer mapping fails everywhere
+        try:
+            parallel.FusedMerge(Fake(rank == broken_rank))
+            results.append("constructed")
+        except RuntimeError as e:
+            results.append(str(e)[:40])
+    q.put((rank, results))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_merge_setup_fails_on_every_rank_or_none():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7
+    procs = [ctx.Process(target=_fm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        assert got[rank][0].startswith("FusedMerge: a rank could not export")
+        assert got[rank][1].startswith("FusedMerge: peer mapping failed")
+    # pixel slices tile the frame for any world size
+    for world in (1, 2, 3, 8):
+        npx = 1920 * 1080
+        cuts = [r * npx // world for r in range(world + 1)]
+        assert cuts[0] == 0 and cuts[-1] == npx and all(b > a for a, b in zip(cuts, cuts[1:]))

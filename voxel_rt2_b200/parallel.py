@@ -119,21 +119,40 @@ class FusedMerge:
         npx = W * H
         self.first = self.rank * npx // self.world
         self.count = (self.rank + 1) * npx // self.world - self.first
-        mine = []
-        for s in (0, 1):
-            renderer.set_accum_slot(s)
-            mine.append((renderer.accum_ipc_handle(), renderer.out_ipc_handle()))
-        renderer.set_accum_slot(0)
+        # Set-up is collective and must fail on EVERY rank or on none (a rank that raised before a collective would
+        # leave the others waiting in it): local failures are gathered first, then raised everywhere.
+        mine, err = [], None
+        try:
+            for s in (0, 1):
+                renderer.set_accum_slot(s)
+                mine.append((renderer.accum_ipc_handle(), renderer.out_ipc_handle()))
+            renderer.set_accum_slot(0)
+        except Exception as e:  # noqa: BLE001
+            mine, err = None, repr(e)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
+        if any(h is None for h in everyone):
+            raise RuntimeError("FusedMerge: a rank could not export its buffers (%s)" % (err or "see the other ranks"))
         self.peer_accum = [[], []]   # per slot: the other ranks' accumulation buffers, in rank order
         self.peer_out = [None, None]  # per slot: the displaying rank's image buffer (None on that rank itself)
-        for s in (0, 1):
-            for k, h in enumerate(everyone):
-                if k != self.rank:
-                    self.peer_accum[s].append(renderer.open_peer_accum(h[s][0]))
-            if self.rank != display_rank:
-                self.peer_out[s] = renderer.open_peer_accum(everyone[display_rank][s][1])
+        try:
+            for s in (0, 1):
+                for k, h in enumerate(everyone):
+                    if k != self.rank:
+                        self.peer_accum[s].append(renderer.open_peer_accum(h[s][0]))
+                if self.rank != display_rank:
+                    self.peer_out[s] = renderer.open_peer_accum(everyone[display_rank][s][1])
+        except Exception as e:  # noqa: BLE001  (no peer access between two GPUs, for one)
+            err = repr(e)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, err, group=group)
+        if any(x is not None for x in oks):
+            for s in (0, 1):
+                for p in self.peer_accum[s]:
+                    renderer.close_peer_accum(p)
+                if self.peer_out[s]:
+                    renderer.close_peer_accum(self.peer_out[s])
+            raise RuntimeError("FusedMerge: peer mapping failed on a rank (%s)" % next(x for x in oks if x is not None))
         self._token = torch.zeros(1, device=torch.device("cuda", renderer.device))
         self.slot, self.k = 0, -1
 
