@@ -1,7 +1,9 @@
 """BASELINE.json config 5: 3840x2160, 1024 spp converged render of the largest example scene
 (example4's sphere, 319 489 voxels; rebuilt here procedurally: x.x < n*n/2, example4.py:13-17),
-tile-sharded over the GPUs of one box (interleaved 8x4 tiles, tile_id % N == rank) with ONE NCCL
-all-reduce of the accumulation buffer at the end (disjoint support => exact gather).
+tile-sharded over the GPUs of one box (interleaved 8x4 tiles, tile_id % N == rank), merged at the end by
+the fused peer-memory gather + tonemap (parallel.FusedMerge: every rank moves W*H/N float4; the partial
+buffers have disjoint support, so the sum IS the gather). bench.py runs the same thing as its
+`other_configs.config5` leg at N = 8; this script also writes the image.
 
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/render_4k_tiles.py
 """
@@ -48,18 +50,26 @@ def main():
     r.set_background_color((0.3, 0.4, 0.6))                  # example4.py:7
     parallel.shard_tiles(r, rank, world)
     r.prepare_data()
-    accum = r.accum_tensor()
+    fm = parallel.FusedMerge(r) if world > 1 else None
+    host = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     with torch.cuda.stream(stream):
+        if fm:
+            fm.begin(0)
         done = 0
         while done < spp:
             n = min(64, spp - done)
             r.accumulate(n)
             done += n
-        parallel.merge_accumulation(accum)
+        if fm:
+            fm.merge()
+            fm.finish(host)
+        elif rank == 0:
+            r.fetch_image_async(host)
+            r.wait_image()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -67,11 +77,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     if rank == 0:
-        img = r.fetch_image()
-        w = accum[..., 3]
-        out = {"config": "config5: 3840x2160, %d spp, example4 sphere (%d voxels), tile-sharded x%d + 1 all-reduce" % (spp, int((mat > 0).sum()), world),
-               "seconds": dt, "paths_per_s": W * H * spp / dt, "samples_min": float(w.min()), "samples_max": float(w.max()),
-               "mean_ldr": float(img[..., :3].mean())}
+        img = host
+        out = {"config": "config5: 3840x2160, %d spp, example4 sphere (%d voxels), tile-sharded x%d + fused peer-memory gather" % (spp, int((mat > 0).sum()), world),
+               "seconds": dt, "paths_per_s": W * H * spp / dt, "alpha_min": float(img[..., 3].min()), "mean_ldr": float(img[..., :3].mean())}
         print(json.dumps(out))
         os.makedirs("gpurun_out", exist_ok=True)
         try:
@@ -80,6 +88,8 @@ def main():
             save_image(img, "gpurun_out/config5_4k.jpg")
         except Exception as e:
             print("no image:", e)
+    if fm:
+        fm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
