@@ -186,6 +186,13 @@ int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs56, cons
 /* Only pixels in 8x4 tiles with tile_id % n == rank are rendered (tile sharding). Default 0,1. */
 int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n);
 
+/* Contiguous strips instead of interleaved tiles: this context owns the tile rows
+ * [rank, rank + 1) * (height / 4) / n. vrt_accumulate renders the own rows only; vrt_accumulate_restir renders the
+ * reservoirs / G-buffer (and runs the per-pixel temporal pass) for the own rows plus a halo of 24 pixels on either side
+ * — spatial_GRIS's max_radius (pathtracer.py:1313) — and resamples the own rows, so ONE reservoir chain is spread over
+ * the GPUs and the merged frame equals the unsharded one. n = 1 switches the mode off. */
+int vrt_set_row_shard(vrt_ctx* ctx, int32_t rank, int32_t n);
+
 /* Renderer.reset_framebuffer (pathtracer.py:664-668). Deferred: if a full-frame vrt_accumulate follows, its
  * kernel overwrites the buffer (no memset, no read-modify-write); any other use clears it first. */
 int vrt_reset(vrt_ctx* ctx);

@@ -1127,3 +1127,40 @@ def test_accumulation_checkpoint_round_trip(vrt):
     assert np.array_equal(c.fetch_hdr(), want)
     with pytest.raises(ValueError):
         c.set_accumulation(sums[:8], 4)
+
+
+def test_restir_row_shards_merge_to_the_unsharded_frame(vrt):
+    """vrt_set_row_shard at N = 1: the ReSTIR frames (temporal + spatial resampling) rendered strip by strip — each
+    strip with its 24-pixel halo of reservoirs — and summed equal the unsharded frames bit for bit; the same for plain
+    path tracing. (On several GPUs the strips run concurrently and FusedMerge adds them: tools/scene_multi_gpu_check.py.)"""
+    R, res, frames = 64, (128, 96), 3
+
+    def run(mode, shard=None):
+        g = vrt.Renderer(dx=2.0 / R, image_res=res, grid_res=R, sky_res=0, seed=9)
+        g.set_voxels(*scenes.material_zoo(R))
+        g.set_floor(-1e5, (0.9, 0.9, 0.9))
+        g.set_directional_light((1, 1, 0.3), 0.05, (1.0, 0.95, 0.9))
+        g.set_background_color((0.3, 0.4, 0.6))
+        if shard:
+            g.set_row_shard(*shard)
+        g.prepare_data()
+        if mode == "restir":
+            g.set_restir_temporal(True)
+            g.accumulate_restir(frames)
+        else:
+            g.accumulate(frames)
+        sums, _ = g.get_accumulation()
+        return sums
+
+    for mode in ("restir", "pt"):
+        full = run(mode)
+        assert (full[..., 3] == frames).all()
+        for n in (2, 5):   # 24 tile rows: 5 does not divide them
+            parts = [run(mode, (r, n)) for r in range(n)]
+            owned = sum((p[..., 3] > 0).astype(int) for p in parts)
+            assert (owned == 1).all()                      # every pixel belongs to exactly one strip
+            assert np.array_equal(sum(parts), full), (mode, n)
+    g = vrt.Renderer(dx=2.0 / R, image_res=res, grid_res=R, sky_res=0)
+    with pytest.raises(RuntimeError, match="row"):
+        g.set_tile_shard(0, 2)
+        g.set_row_shard(0, 2)

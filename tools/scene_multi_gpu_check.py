@@ -2,10 +2,10 @@
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/scene_multi_gpu_check.py
 
-Scene.finish() sharded over the ranks (tiles, then samples, then ReSTIR with one reservoir chain per GPU) against
-the same Scene rendered on one GPU by rank 0: the tile-sharded image must be IDENTICAL (disjoint support, same sample
-indices), the sample-sharded one equal up to float re-association of the per-pixel sums, the ReSTIR one a valid image
-with the same mean within noise. Also checks parallel.FusedMerge against all-reduce + tonemap on a double-buffered
+Scene.finish() sharded over the ranks (tiles, samples, ReSTIR in row strips with a 24-pixel halo = ONE reservoir chain
+over all GPUs, ReSTIR with one chain per GPU) against the same Scene rendered on one GPU by rank 0: the tile-sharded
+and the row-sharded ReSTIR images must be IDENTICAL, the sample-sharded one equal up to float re-association of the
+per-pixel sums, the per-GPU-chain ReSTIR one a valid image with the same mean within noise. Also checks parallel.FusedMerge against all-reduce + tonemap on a double-buffered
 sequence of batches (the protocol bench.py uses)."""
 import json
 import os
@@ -44,7 +44,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     out = {}
     # ---- Scene.finish on N GPUs vs one GPU
-    for mode, shard, spp in (("pt", "tiles", 16), ("pt", "samples", 16), ("restir", "samples", 8)):
+    for mode, shard, spp in (("pt", "tiles", 16), ("pt", "samples", 16), ("restir", "rows", 8), ("restir", "samples", 8)):
         img = make_scene(mode, shard).finish(spp=spp, out="")
         if rank == 0:
             save = {k: os.environ.pop(k) for k in ("RANK", "WORLD_SIZE")}
@@ -117,7 +117,7 @@ def main():
         out["fused_vs_allreduce_max_abs_diff_per_batch"] = ok
         out["world"] = world
         print(json.dumps(out))
-        assert out["pt_tiles_identical"] and out["sharded_sky_identical_on_every_rank"], out
+        assert out["pt_tiles_identical"] and out["restir_rows_identical"] and out["sharded_sky_identical_on_every_rank"], out
         assert out["pt_samples_max_abs_diff"] < 1e-5, out
         assert abs(out["restir_samples_mean_ratio"] - 1.0) < 0.05, out
         assert max(ok) < 1e-6, out

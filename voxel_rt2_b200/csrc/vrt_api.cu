@@ -79,6 +79,9 @@ struct vrt_ctx {
   float view[16], proj[16];
 
   int tile_rank = 0, tile_n = 1;
+  // vrt_set_row_shard: this context owns the tile rows [strip_row0, strip_row1) of the frame (contiguous strips, the
+  // partition that lets the ReSTIR passes run on a shard: their 24-pixel neighbourhood becomes a 6-tile-row halo)
+  int strip_n = 1, strip_row0 = 0, strip_row1 = 0;
   vrt_stats stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // vrt_accumulate is asynchronous: the device time of each launch is bracketed by an event pair from this ring
@@ -177,7 +180,10 @@ static void default_materials(float* rows) {  // materials.py:50-63
   for (int i = 0; i < 128; i++) pack_material(d, rows + i * 20);
 }
 
+static bool is_sharded(const vrt_ctx* ctx) { return ctx->tile_n != 1 || ctx->strip_n > 1; }
+
 static int n_local_tiles(const vrt_ctx* ctx) {
+  if (ctx->strip_n > 1) return (ctx->strip_row1 - ctx->strip_row0) * (ctx->cfg.width / 8);
   int total = (ctx->cfg.width / 8) * (ctx->cfg.height / 4);
   if (ctx->tile_rank >= total) return 0;
   return (total - ctx->tile_rank + ctx->tile_n - 1) / ctx->tile_n;
@@ -218,6 +224,7 @@ static void fill_params(const vrt_ctx* ctx, Params& P) {
   P.tile_rank = ctx->tile_rank, P.tile_n = ctx->tile_n;
   P.tiles_x = c.width / 8;
   P.n_tiles = n_local_tiles(ctx);
+  if (ctx->strip_n > 1) P.tile_rank = ctx->strip_row0 * P.tiles_x, P.tile_n = 1;  // a contiguous tile range
   P.work_counter = ctx->d_work;
   P.stats = nullptr;
   P.jitter = ctx->d_jitter;
@@ -703,7 +710,7 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
   P.stats = stats ? ctx->d_stats : nullptr;
   if (P.n_tiles <= 0) return VRT_OK;
   // reset_framebuffer + full-frame batch: the kernel writes every texel, so the memset (and the read) is skipped
-  if (ctx->zero_pending[ctx->cur_slot] && ctx->tile_n == 1) {
+  if (ctx->zero_pending[ctx->cur_slot] && !is_sharded(ctx)) {
     P.accum_overwrite = 1;
     ctx->zero_pending[ctx->cur_slot] = false;
   } else if (int rcz = flush_pending_zero(ctx)) {
@@ -757,7 +764,7 @@ static int ensure_restir_buffers(vrt_ctx* ctx) {
 int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, int32_t stride) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(n_frames > 0 && stride > 0 && first_sample >= 0, "vrt_accumulate_restir: bad sample range");
-  REQUIRE(ctx->tile_n == 1, "vrt_accumulate_restir: tile sharding needs a 24-pixel halo (not implemented); use sample sharding");
+  REQUIRE(ctx->tile_n == 1, "vrt_accumulate_restir: interleaved tile sharding cannot carry the 24-pixel neighbourhood; use vrt_set_row_shard or sample sharding");
   int rc = check_ready(ctx, "vrt_accumulate_restir");
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
@@ -776,13 +783,25 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
     Params P;
     fill_params(ctx, P);
     P.first_sample = (int)s, P.n_samples = 1, P.stride = 1;
+    // Row shard: the reservoirs / G-buffer (and the per-pixel temporal chain) are produced for the own rows plus a halo of
+    // 6 tile rows = 24 pixels on either side (spatial_GRIS max_radius, pathtracer.py:1313), the spatial pass runs on the
+    // own rows only. Every halo pixel is computed exactly as its owner computes it, so the merged frame equals the
+    // unsharded one.
+    Params PX = P;
+    if (ctx->strip_n > 1) {
+      const int rows = ctx->cfg.height / 4;
+      const int r0 = ctx->strip_row0 - 6 > 0 ? ctx->strip_row0 - 6 : 0, r1 = ctx->strip_row1 + 6 < rows ? ctx->strip_row1 + 6 : rows;
+      PX.tile_rank = r0 * P.tiles_x, PX.n_tiles = (r1 - r0) * P.tiles_x;
+    }
     cudaEvent_t* ev = &ctx->frame_events[4 * (size_t)k];
     CK(cudaEventRecord(ev[0], ctx->stream));
-    CK(vrt_launch_path_restir(P, ctx->rb, ctx->sm_count, ctx->stream));
+    CK(vrt_launch_path_restir(PX, ctx->rb, ctx->sm_count, ctx->stream));
     CK(cudaEventRecord(ev[1], ctx->stream));
     if (ctx->restir_temporal) {  // temporal reuse of the previous frame's reservoirs (k_rc_sky + k_temporal), in place
-      CK(vrt_launch_temporal(P, ctx->rb, s, ctx->hist_valid ? 1 : 0, ctx->stream));
+      CK(vrt_launch_temporal(PX, ctx->rb, s, ctx->hist_valid ? 1 : 0, ctx->stream));
       ctx->hist_valid = true;
+    } else {
+      CK(vrt_launch_rc_sky(PX, ctx->rb, ctx->stream));
     }
     CK(cudaEventRecord(ev[2], ctx->stream));
     CK(vrt_launch_gris(P, ctx->rb, s, ctx->stream));
@@ -817,7 +836,7 @@ int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs, const 
                      const float* col_s) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(frame >= 0 && reservoirs && gpos && gattr && col_d && col_s, "vrt_spatial_gris: bad arguments");
-  REQUIRE(ctx->tile_n == 1, "vrt_spatial_gris: tile sharding is not supported (taps cross tiles)");
+  REQUIRE(!is_sharded(ctx), "vrt_spatial_gris: sharding is not supported here (taps cross tiles)");
   int rc = check_ready(ctx, "vrt_spatial_gris");
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
@@ -835,6 +854,7 @@ int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs, const 
   fill_params(ctx, P);
   P.first_sample = frame, P.n_samples = 1, P.stride = 1;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(vrt_launch_rc_sky(P, ctx->rb, ctx->stream));
   CK(vrt_launch_gris(P, ctx->rb, (uint32_t)frame, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));  // the host buffers may be freed on return
@@ -850,7 +870,7 @@ int vrt_spatial_gris(vrt_ctx* ctx, int32_t frame, const void* reservoirs, const 
 int vrt_accumulate_moving(vrt_ctx* ctx, int32_t sample, float render_scale, float max_accum) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(sample >= 0 && render_scale > 0.0f && render_scale <= 1.0f && max_accum >= 1.0f, "vrt_accumulate_moving: bad arguments");
-  REQUIRE(ctx->tile_n == 1, "vrt_accumulate_moving: tile sharding is not supported (history taps cross tiles)");
+  REQUIRE(!is_sharded(ctx), "vrt_accumulate_moving: sharding is not supported (history taps cross tiles)");
   int rc = check_ready(ctx, "vrt_accumulate_moving");
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
@@ -961,9 +981,35 @@ int vrt_set_accum(vrt_ctx* ctx, const float* rgba_sums) {
   return VRT_OK;
 }
 
+static int flush_all_pending_zero(vrt_ctx* ctx) {
+  CK(cudaSetDevice(ctx->device));
+  const int keep = ctx->cur_slot;
+  for (int k = 0; k < 2; k++)
+    if (ctx->accum_slot[k]) {
+      ctx->cur_slot = k, ctx->d_accum = ctx->accum_slot[k];
+      if (int rcz = flush_pending_zero(ctx)) return rcz;
+    }
+  ctx->cur_slot = keep, ctx->d_accum = ctx->accum_slot[keep];
+  return VRT_OK;
+}
+
+int vrt_set_row_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  const int rows = ctx->cfg.height / 4;
+  REQUIRE(n >= 1 && rank >= 0 && rank < n && n <= rows, "vrt_set_row_shard: need 0 <= rank < n <= height / 4");
+  REQUIRE(n == 1 || ctx->tile_n == 1, "vrt_set_row_shard: interleaved tile sharding is already active");
+  if (n != 1)
+    if (int rc = flush_all_pending_zero(ctx)) return rc;  // a strip covers only its rows: pending resets must really clear
+  ctx->strip_n = n;
+  ctx->strip_row0 = (int)((long long)rank * rows / n), ctx->strip_row1 = (int)((long long)(rank + 1) * rows / n);
+  ctx->hist_valid = false;
+  return VRT_OK;
+}
+
 int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(n >= 1 && rank >= 0 && rank < n, "vrt_set_tile_shard: need 0 <= rank < n");
+  REQUIRE(n == 1 || ctx->strip_n <= 1, "vrt_set_tile_shard: row sharding is already active");
   if (n != 1) {  // a sharded batch covers only its own tiles: pending resets must really clear the buffers
     CK(cudaSetDevice(ctx->device));
     const int keep = ctx->cur_slot;
@@ -984,7 +1030,7 @@ int vrt_reset(vrt_ctx* ctx) {
   // deferred: a full-frame path-tracing batch that follows overwrites the buffer (no memset, no read-modify-write);
   // every other consumer turns the flag into the memset first (flush_pending_zero)
   ctx->zero_pending[ctx->cur_slot] = true;
-  if (ctx->tile_n != 1)
+  if (is_sharded(ctx))
     if (int rcz = flush_pending_zero(ctx)) return rcz;
   ctx->mv.has_prev = false;
   ctx->mv.active = false;

@@ -22,6 +22,9 @@ size_t vrt_render_smem_bytes(const Params& P, int* upper_in_smem);
 cudaError_t vrt_launch_pack_sky(const float4* scatter, const float4* trans, uint4* out, size_t n, cudaStream_t st);
 // vrt_restir.cu — spatial_GRIS (pathtracer.py:815-989); adds the frame's colour into P.accum
 cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t frame, cudaStream_t st);
+// sun transmittance at every reservoir's reconnection vertex, once per frame before the resampling passes (vrt_launch_temporal
+// includes it; without temporal reuse the frame loop calls it before vrt_launch_gris)
+cudaError_t vrt_launch_rc_sky(const Params& P, const RestirBuffers& RB, cudaStream_t st);
 // temporal reservoir reuse between the path kernel and k_gris (k_rc_sky + k_temporal)
 cudaError_t vrt_launch_temporal(const Params& P, const RestirBuffers& RB, uint32_t frame, int hist_valid, cudaStream_t st);
 cudaError_t vrt_launch_resolve_merged(const float4* accum, const float4* const* peers, int n_peers, float4* ldr, int W, int H, float exposure,

@@ -140,12 +140,13 @@ HD void load_reservoir(const uint2* __restrict__ base, size_t pidx, const float*
 // value depends on the reservoir alone, so it is looked up once per pixel here, between the path
 // kernel and k_gris, which then reads 16 bytes per surviving tap instead of projecting the
 // direction and fetching four texels of the 236 MB table.
-__global__ void __launch_bounds__(128) k_rc_sky(const __grid_constant__ Params P, RestirBuffers RB) {
+__global__ void __launch_bounds__(128) k_rc_sky(const __grid_constant__ Params P, RestirBuffers RB, size_t first_px, size_t n_px) {
   __shared__ float s_unorm[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm[i] = xdiv((float)i, 255.0f);
   __syncthreads();
-  const size_t pidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pidx >= (size_t)P.W * P.H) return;
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_px) return;
+  const size_t pidx = first_px + k;  // the rows this context renders (the whole frame unless row-sharded)
   RReservoir r;
   load_reservoir(RB.reservoirs, pidx, s_unorm, r);
   f3 T = mk3(1.0f);
@@ -514,13 +515,25 @@ __global__ void __launch_bounds__(VRT_TEMPORAL_THREADS, 512 / VRT_TEMPORAL_THREA
 
 }  // namespace
 
+// The tiles of P form whole tile rows when tile_n == 1 (the whole frame, or the contiguous range of a row shard): the pixel
+// range k_rc_sky covers.
+static void rc_sky_range(const Params& P, size_t* first_px, size_t* n_px) {
+  *first_px = (size_t)(P.tile_rank / P.tiles_x) * 4 * P.W;
+  *n_px = (size_t)(P.n_tiles / P.tiles_x) * 4 * P.W;
+}
+cudaError_t vrt_launch_rc_sky(const Params& P, const RestirBuffers& RB, cudaStream_t st) {
+  size_t f, n;
+  rc_sky_range(P, &f, &n);
+  if (n) k_rc_sky<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, RB, f, n);
+  return cudaGetLastError();
+}
+
 cudaError_t vrt_launch_gris(const Params& P, const RestirBuffers& RB, uint32_t frame, cudaStream_t st) {
   int uis;
   size_t sm = vrt_render_smem_bytes(P, &uis);
   const int fixed_words = 128 * MAT_ROW_F4 * 4 + 256;
   int blocks = (P.n_tiles * 32 + VRT_GRIS_THREADS - 1) / VRT_GRIS_THREADS;
-  if (!RB.temporal) k_rc_sky<<<(P.W * P.H + 127) / 128, 128, 0, st>>>(P, RB);  // with temporal reuse on, vrt_launch_temporal ran it already
-  k_gris<<<blocks, VRT_GRIS_THREADS, sm, st>>>(P, RB, frame, uis, fixed_words);
+  if (blocks > 0) k_gris<<<blocks, VRT_GRIS_THREADS, sm, st>>>(P, RB, frame, uis, fixed_words);  // k_rc_sky has run (vrt_launch_rc_sky / vrt_launch_temporal)
   return cudaGetLastError();
 }
 
@@ -529,7 +542,7 @@ cudaError_t vrt_launch_temporal(const Params& P, const RestirBuffers& RB, uint32
   size_t sm = vrt_render_smem_bytes(P, &uis);
   const int fixed_words = 128 * MAT_ROW_F4 * 4 + 256;
   int blocks = (P.n_tiles * 32 + VRT_TEMPORAL_THREADS - 1) / VRT_TEMPORAL_THREADS;
-  k_rc_sky<<<(P.W * P.H + 127) / 128, 128, 0, st>>>(P, RB);
-  k_temporal<<<blocks, VRT_TEMPORAL_THREADS, sm, st>>>(P, RB, frame, hist_valid, uis, fixed_words);
+  if (cudaError_t e = vrt_launch_rc_sky(P, RB, st)) return e;
+  if (blocks > 0) k_temporal<<<blocks, VRT_TEMPORAL_THREADS, sm, st>>>(P, RB, frame, hist_valid, uis, fixed_words);
   return cudaGetLastError();
 }

@@ -25,6 +25,12 @@ def shard_tiles(renderer, rank, world):
     renderer.set_tile_shard(rank, world)
 
 
+def shard_rows(renderer, rank, world):
+    """Contiguous strips of tile rows: the partition for the ReSTIR mode (one reservoir chain over all GPUs; each rank
+    renders a 24-pixel halo around its rows for the spatial pass)."""
+    renderer.set_row_shard(rank, world)
+
+
 def merge_accumulation(accum, group=None):
     """One collective per frame batch: sum the [H, W, 4] accumulation buffers (rgb sums and the
     per-pixel sample count in w) of all ranks, in place."""

@@ -263,6 +263,11 @@ class Renderer:
     def set_tile_shard(self, rank, n):
         self._check(self._lib.vrt_set_tile_shard(self._h, int(rank), int(n)))
 
+    def set_row_shard(self, rank, n):
+        """Contiguous strips of tile rows (vrt_set_row_shard): the partition under which the ReSTIR passes run on a
+        shard (24-pixel halo), so one reservoir chain is spread over the GPUs."""
+        self._check(self._lib.vrt_set_row_shard(self._h, int(rank), int(n)))
+
     def set_sample_shard(self, rank, n):
         """Sample sharding: this renderer renders sample indices rank, rank+n, rank+2n, ..."""
         self.sample_offset, self.sample_stride = int(rank), int(n)

@@ -17,10 +17,12 @@ unchanged:
                               (256) samples and resume from the file if it exists
     VRT_GPUS=N                run the script on N GPUs of this box: it is re-launched under torch.distributed.run
                               (one process per GPU); a script already started by torchrun is recognised by RANK /
-                              WORLD_SIZE. VRT_SHARD=tiles (default: interleaved 8x4 tiles of one frame) | samples
-                              (rank r renders sample indices r, r+N, ...; ReSTIR mode always shards samples, one
-                              reservoir chain per GPU). The partial buffers are merged by the fused peer-memory
-                              reduce-scatter + tonemap kernel (parallel.FusedMerge); rank 0 writes the image.
+                              WORLD_SIZE. VRT_SHARD=tiles (default: interleaved 8x4 tiles of one frame) | rows
+                              (contiguous strips; the default in ReSTIR mode: ONE reservoir chain over all GPUs, each
+                              rank renders a 24-pixel halo for the spatial pass) | samples (rank r renders sample
+                              indices r, r+N, ...; in ReSTIR mode one independent chain per GPU). The partial buffers
+                              are merged by the fused peer-memory reduce-scatter + tonemap kernel
+                              (parallel.FusedMerge); rank 0 writes the image.
 Voxels live in host NumPy arrays (material int8[R,R,R], colour uint8[R,R,R,3], index + R/2)
 until finish() uploads them once (voxel_world.py:6-25 semantics: colour clamp + u8 truncation,
 material cast to int8)."""
@@ -279,9 +281,14 @@ class Scene:
 
             from . import parallel
 
-            shard = "samples" if mode == "restir" else os.environ.get("VRT_SHARD", "tiles").lower()
+            shard = os.environ.get("VRT_SHARD", "rows" if mode == "restir" else "tiles").lower()
+            if mode == "restir" and shard == "tiles":
+                shard = "rows"  # interleaved tiles cannot carry the 24-pixel neighbourhood of the resampling passes
             if shard == "tiles":
                 parallel.shard_tiles(r, rank, world)
+                n_local = spp
+            elif shard == "rows":
+                parallel.shard_rows(r, rank, world)
                 n_local = spp
             else:
                 parallel.shard_samples(r, rank, world)
