@@ -475,6 +475,51 @@ def leg_config5(vrt, torch, dist, rank, world, device, spp=1024):
     return out
 
 
+def leg_config4_rows(vrt, torch, dist, rank, world, device, W, H, sky_res, frames=24):
+    """config 4 on N GPUs as ONE reservoir chain: row strips with a 24-pixel halo (vrt_set_row_shard), temporal + spatial
+    resampling per frame, the strips merged per frame by the fused peer-memory kernel. Strong scaling of the ReSTIR frame."""
+    from voxel_rt2_b200 import parallel
+
+    wl = Workload("config4", 128)
+    r = vrt.Renderer(dx=2.0 / wl.R, image_res=(W, H), grid_res=wl.R, sky_res=sky_res, exposure=wl.exposure, seed=1, voxel_edges=wl.voxel_edges,
+                     device=device)
+    stream = torch.cuda.Stream()
+    r.set_stream(stream.cuda_stream)
+    wl.configure(r)
+    r.set_sky_shard(rank, world)
+    parallel.shard_rows(r, rank, world)
+    r.prepare_data()
+    r.set_restir_temporal(True)
+    fm = parallel.FusedMerge(r)
+    with torch.cuda.stream(stream):
+        for k in range(4):  # warm-up: the chain reaches its steady state
+            r.accumulate_restir(1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = ClockSampler(device).start() if rank == 0 else None
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for k in range(frames):
+            fm.begin(k, reset=False)  # progressive accumulation: a reset would also drop the reservoir history
+            r.accumulate_restir(1)
+            fm.merge()
+        fm.barrier()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    out = None
+    if rank == 0:
+        out = {"workload": wl.desc.format(W=W, H=H) + "; ONE chain over %d GPUs (row strips + 24-pixel halo, fused merge per frame)" % world,
+               "frames": frames, "ms_per_frame": 1e3 * dt / frames, "paths_per_s": W * H * frames / dt,
+               "timing": "wall clock around the frame loop, max over ranks", "clocks": clocks.stop()}
+    fm.close()
+    r.close()
+    return out
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     args = parse()
@@ -745,8 +790,10 @@ def main():
             others["config4_example3"] = _leg(lambda: leg_path_or_restir(vrt, torch, "config4_example3", W, H, local_rank, args.sky_res, 1, 24))
         if world == 8:
             c5 = _leg(lambda: leg_config5(vrt, torch, dist, rank, world, local_rank))
+            c4 = _leg(lambda: leg_config4_rows(vrt, torch, dist, rank, world, local_rank, W, H, args.sky_res))
             if rank == 0:
                 others["config5"] = c5
+                others["config4_example6_one_chain_over_8_gpus"] = c4
         watchdog.cancel()
         if rank == 0 and others:
             line["other_configs"] = others

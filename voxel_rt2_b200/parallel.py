@@ -162,10 +162,13 @@ class FusedMerge:
         self._token = torch.zeros(1, device=torch.device("cuda", renderer.device))
         self.slot, self.k = 0, -1
 
-    def begin(self, k):
+    def begin(self, k, reset=True):
+        """Batch k goes to slot k & 1. reset=False keeps what the slot has accumulated (and the ReSTIR reservoir history,
+        which reset_framebuffer drops): the slot then holds the running sum of every second batch."""
         self.k, self.slot = k, k & 1
         self.r.set_accum_slot(self.slot)
-        self.r.reset_framebuffer()
+        if reset:
+            self.r.reset_framebuffer()
 
     def barrier(self):
         """Stream-ordered barrier: a 4-byte NCCL all-reduce on the current torch stream."""
