@@ -487,8 +487,8 @@ def leg_config4_rows(vrt, torch, dist, rank, world, device, W, H, sky_res, frame
     r.set_stream(stream.cuda_stream)
     wl.configure(r)
     r.set_sky_shard(rank, world)
-    parallel.shard_rows(r, rank, world)
     r.prepare_data()
+    cuts = parallel.shard_rows(r, rank, world)  # strips balanced by geometry pixels (sky rows are nearly free)
     r.set_restir_temporal(True)
     fm = parallel.FusedMerge(r)
     with torch.cuda.stream(stream):
@@ -513,7 +513,7 @@ def leg_config4_rows(vrt, torch, dist, rank, world, device, W, H, sky_res, frame
     out = None
     if rank == 0:
         out = {"workload": wl.desc.format(W=W, H=H) + "; ONE chain over %d GPUs (row strips + 24-pixel halo, fused merge per frame)" % world,
-               "frames": frames, "ms_per_frame": 1e3 * dt / frames, "paths_per_s": W * H * frames / dt,
+               "frames": frames, "ms_per_frame": 1e3 * dt / frames, "paths_per_s": W * H * frames / dt, "tile_row_cuts": cuts,
                "timing": "wall clock around the frame loop, max over ranks", "clocks": clocks.stop()}
     fm.close()
     r.close()

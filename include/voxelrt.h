@@ -192,6 +192,9 @@ int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n);
  * — spatial_GRIS's max_radius (pathtracer.py:1313) — and resamples the own rows, so ONE reservoir chain is spread over
  * the GPUs and the merged frame equals the unsharded one. n = 1 switches the mode off. */
 int vrt_set_row_shard(vrt_ctx* ctx, int32_t rank, int32_t n);
+/* The same with an explicit strip: tile rows [first_row, first_row + n_rows) (a tile row = 4 pixel rows). Lets the host
+ * balance the strips by cost — sky rows are nearly free, geometry rows are not (parallel.shard_rows). */
+int vrt_set_row_range(vrt_ctx* ctx, int32_t first_row, int32_t n_rows);
 
 /* Renderer.reset_framebuffer (pathtracer.py:664-668). Deferred: if a full-frame vrt_accumulate follows, its
  * kernel overwrites the buffer (no memset, no read-modify-write); any other use clears it first. */

@@ -153,3 +153,18 @@ def test_fused_merge_setup_fails_on_every_rank_or_none():
         npx = 1920 * 1080
         cuts = [r * npx // world for r in range(world + 1)]
         assert cuts[0] == 0 and cuts[-1] == npx and all(b > a for a, b in zip(cuts, cuts[1:]))
+
+
+def test_balanced_row_cuts():
+    """parallel.balanced_row_cuts: contiguous strips of nearly equal cost, every strip non-empty, deterministic."""
+    from voxel_rt2_b200.parallel import balanced_row_cuts
+
+    cost = np.r_[np.ones(100), np.full(100, 50.0), np.ones(70)]
+    cuts = balanced_row_cuts(cost, 8)
+    assert cuts[0] == 0 and cuts[-1] == 270 and all(b > a for a, b in zip(cuts, cuts[1:]))
+    per = [cost[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+    assert max(per) <= 1.15 * sum(per) / 8
+    assert balanced_row_cuts(np.ones(24), 5) == [0, 5, 10, 15, 20, 24]
+    z = balanced_row_cuts(np.zeros(10), 4)
+    assert z[0] == 0 and z[-1] == 10 and all(b > a for a, b in zip(z, z[1:]))
+    assert balanced_row_cuts(cost, 1) == [0, 270]

@@ -10,7 +10,7 @@ EXPORTS = [
     "vrt_create", "vrt_destroy", "vrt_last_error", "vrt_set_stream", "vrt_upload_voxels", "vrt_set_camera",
     "vrt_set_light", "vrt_set_floor", "vrt_set_background", "vrt_set_sky", "vrt_set_materials",
     "vrt_set_cloud_texture", "vrt_prepare", "vrt_set_sky_shard", "vrt_sky_tables_device_ptr", "vrt_sky_tables_complete", "vrt_sky_tables_pending", "vrt_get_sky_tables", "vrt_set_sky_tables", "vrt_set_sky_format", "vrt_get_trans_lut",
-    "vrt_trace_primary", "vrt_accumulate", "vrt_accumulate_restir", "vrt_set_restir_temporal", "vrt_accumulate_moving", "vrt_get_reservoirs", "vrt_spatial_gris", "vrt_set_tile_shard", "vrt_set_row_shard", "vrt_reset", "vrt_get_accum", "vrt_set_accum", "vrt_accum_device_ptr",
+    "vrt_trace_primary", "vrt_accumulate", "vrt_accumulate_restir", "vrt_set_restir_temporal", "vrt_accumulate_moving", "vrt_get_reservoirs", "vrt_spatial_gris", "vrt_set_tile_shard", "vrt_set_row_shard", "vrt_set_row_range", "vrt_reset", "vrt_get_accum", "vrt_set_accum", "vrt_accum_device_ptr",
     "vrt_fetch_hdr", "vrt_fetch_ldr", "vrt_fetch_ldr_async", "vrt_fetch_wait", "vrt_accum_ipc_handle", "vrt_open_peer_accum", "vrt_close_peer_accum", "vrt_fetch_ldr_merged", "vrt_set_accum_slot", "vrt_out_ipc_handle", "vrt_merge_slice", "vrt_copy_ldr_async", "vrt_stream_wait_copy", "vrt_resolve_ldr_device", "vrt_get_stats", "vrt_synchronize",
 ]
 
@@ -87,6 +87,7 @@ def load():
     lib.vrt_spatial_gris.argtypes = [P, C.c_int32, P, P, P, P, P]
     lib.vrt_set_tile_shard.argtypes = [P, C.c_int32, C.c_int32]
     lib.vrt_set_row_shard.argtypes = [P, C.c_int32, C.c_int32]
+    lib.vrt_set_row_range.argtypes = [P, C.c_int32, C.c_int32]
     lib.vrt_reset.argtypes = [P]
     lib.vrt_get_accum.argtypes = [P, fp]
     lib.vrt_set_accum.argtypes = [P, fp]

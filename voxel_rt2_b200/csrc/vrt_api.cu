@@ -1006,6 +1006,18 @@ int vrt_set_row_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
   return VRT_OK;
 }
 
+int vrt_set_row_range(vrt_ctx* ctx, int32_t first_row, int32_t n_rows) {
+  if (!ctx) return VRT_ERR_BAD_ARG;
+  const int rows = ctx->cfg.height / 4;
+  REQUIRE(first_row >= 0 && n_rows >= 0 && first_row + n_rows <= rows, "vrt_set_row_range: tile rows outside the frame");
+  REQUIRE(ctx->tile_n == 1, "vrt_set_row_range: interleaved tile sharding is already active");
+  if (int rc = flush_all_pending_zero(ctx)) return rc;
+  ctx->strip_n = 2;  // any value > 1: "a strip is active"
+  ctx->strip_row0 = first_row, ctx->strip_row1 = first_row + n_rows;
+  ctx->hist_valid = false;
+  return VRT_OK;
+}
+
 int vrt_set_tile_shard(vrt_ctx* ctx, int32_t rank, int32_t n) {
   if (!ctx) return VRT_ERR_BAD_ARG;
   REQUIRE(n >= 1 && rank >= 0 && rank < n, "vrt_set_tile_shard: need 0 <= rank < n");

@@ -25,10 +25,40 @@ def shard_tiles(renderer, rank, world):
     renderer.set_tile_shard(rank, world)
 
 
-def shard_rows(renderer, rank, world):
+def balanced_row_cuts(row_cost, world):
+    """Cut positions (world + 1 tile-row indices) that split the per-tile-row costs into `world` contiguous strips of
+    nearly equal total cost. Deterministic: every rank computes the same cuts from the same costs."""
+    import numpy as np
+
+    c = np.concatenate([[0.0], np.cumsum(np.asarray(row_cost, np.float64))])
+    rows = len(row_cost)
+    cuts = [0]
+    for k in range(1, world):
+        target = c[-1] * k / world
+        r = int(np.searchsorted(c, target))
+        r = min(max(r, cuts[-1] + 1), rows - (world - k))  # every strip keeps at least one row
+        cuts.append(r)
+    cuts.append(rows)
+    return cuts
+
+
+def shard_rows(renderer, rank, world, balance=True):
     """Contiguous strips of tile rows: the partition for the ReSTIR mode (one reservoir chain over all GPUs; each rank
-    renders a 24-pixel halo around its rows for the spatial pass)."""
-    renderer.set_row_shard(rank, world)
+    renders a 24-pixel halo around its rows for the spatial pass). With balance=True (call after prepare_data) the
+    strips are cut by cost instead of by height: a primary-hit pass counts the geometry pixels of every tile row (sky
+    pixels cost the resampling passes next to nothing), and the halo rows a strip has to render are charged to it."""
+    if not balance or world == 1:
+        renderer.set_row_shard(rank, world)
+        return None
+    import numpy as np
+
+    hits = renderer.trace_primary()
+    H = hits.shape[0]
+    geo = ((hits["flags"] & 255) > 0).reshape(H // 4, 4, -1).sum(axis=(1, 2)).astype(np.float64)
+    cost = geo + 0.05 * hits.shape[1] * 4          # a sky pixel still costs a primary ray and a pass-through
+    cuts = balanced_row_cuts(cost, world)
+    renderer.set_row_range(cuts[rank], cuts[rank + 1] - cuts[rank])
+    return cuts
 
 
 def merge_accumulation(accum, group=None):

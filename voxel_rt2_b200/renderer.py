@@ -268,6 +268,10 @@ class Renderer:
         shard (24-pixel halo), so one reservoir chain is spread over the GPUs."""
         self._check(self._lib.vrt_set_row_shard(self._h, int(rank), int(n)))
 
+    def set_row_range(self, first_row, n_rows):
+        """Explicit strip of tile rows (vrt_set_row_range); a tile row is 4 pixel rows."""
+        self._check(self._lib.vrt_set_row_range(self._h, int(first_row), int(n_rows)))
+
     def set_sample_shard(self, rank, n):
         """Sample sharding: this renderer renders sample indices rank, rank+n, rank+2n, ..."""
         self.sample_offset, self.sample_stride = int(rank), int(n)

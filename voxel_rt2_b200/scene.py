@@ -288,8 +288,7 @@ class Scene:
                 parallel.shard_tiles(r, rank, world)
                 n_local = spp
             elif shard == "rows":
-                parallel.shard_rows(r, rank, world)
-                n_local = spp
+                n_local = spp  # the strips are cut after prepare_data (they are balanced by a primary-hit pass)
             else:
                 parallel.shard_samples(r, rank, world)
                 n_local = (spp - rank + world - 1) // world  # sample indices rank, rank + world, ... below spp
@@ -301,6 +300,8 @@ class Scene:
             n_local = spp
         t0 = time.time()
         r.prepare_data()
+        if world > 1 and shard == "rows":
+            parallel.shard_rows(r, rank, world)
         t_prep = time.time() - t0
         if mode == "restir":
             r.set_restir_temporal(os.environ.get("VRT_RESTIR_TEMPORAL", "1") != "0")
