@@ -151,7 +151,9 @@ int vrt_accumulate(vrt_ctx* ctx, int32_t first_sample, int32_t n_samples, int32_
 /* Renderer.accumulate with USE_RESTIR_PT = True (pathtracer.py:15,1310-1319): per frame, render
  * writes one packed reservoir + G-buffer record per pixel (pathtracer.py:535-607) and
  * spatial_GRIS(0, 24.0, 32, 1) (pathtracer.py:815-989) resamples 32 neighbours; the frame is then
- * accumulated like a path-traced one. n_frames frames with sample indices first, first+stride... */
+ * accumulated like a path-traced one. n_frames frames with sample indices first, first+stride...
+ * Asynchronous like vrt_accumulate: the frames are enqueued on the context's stream; vrt_get_stats reads the
+ * per-phase device times back (and waits for them). */
 int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, int32_t stride);
 /* Temporal reservoir reuse for vrt_accumulate_restir (BASELINE.json configs[3]: "temporal+spatial resampling per
  * frame"). No upstream counterpart: the reference allocates two reservoir slots per pixel (pathtracer.py:108-109) and

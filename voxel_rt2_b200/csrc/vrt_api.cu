@@ -90,7 +90,8 @@ struct vrt_ctx {
   cudaEvent_t ring_a[EV_RING] = {nullptr}, ring_b[EV_RING] = {nullptr};
   bool ring_pending[EV_RING] = {false};
   int ring_head = 0;
-  std::vector<cudaEvent_t> frame_events;  // ReSTIR mode: 3 events per frame of a call
+  std::vector<cudaEvent_t> frame_events;  // ReSTIR mode: 4 events per frame of a call
+  int restir_pending_frames = 0;           // ... whose times have not been read back yet (vrt_accumulate_restir is asynchronous)
   // pipelined image fetch (vrt_fetch_ldr_async): copy engine stream + events, created on first use
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_resolved = nullptr, ev_copied = nullptr;
@@ -807,7 +808,18 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
     CK(vrt_launch_gris(P, ctx->rb, s, ctx->stream));
     CK(cudaEventRecord(ev[3], ctx->stream));
   }
-  CK(cudaStreamSynchronize(ctx->stream));
+  // asynchronous like vrt_accumulate: the per-phase device times are read back by vrt_get_stats
+  ctx->restir_pending_frames = n_frames;
+  ctx->stats.kernel_launches = (ctx->restir_temporal ? 5u : 4u) * (uint32_t)n_frames;  // k_jitter, k_path, k_rc_sky, [k_temporal,] k_gris
+  ctx->stats.launches_total += ctx->stats.kernel_launches;
+  return VRT_OK;
+}
+
+static int drain_restir_events(vrt_ctx* ctx) {
+  if (ctx->restir_pending_frames <= 0) return VRT_OK;
+  const int n_frames = ctx->restir_pending_frames;
+  ctx->restir_pending_frames = 0;
+  CK(cudaEventSynchronize(ctx->frame_events[4 * (size_t)(n_frames - 1) + 3]));
   float render_ms = 0.0f, gris_ms = 0.0f, temporal_ms = 0.0f;
   for (int k = 0; k < n_frames; k++) {
     float a = 0.0f, b = 0.0f, c = 0.0f;
@@ -820,8 +832,6 @@ int vrt_accumulate_restir(vrt_ctx* ctx, int32_t first_sample, int32_t n_frames, 
   ctx->stats.last_render_ms = render_ms;
   ctx->stats.last_gris_ms = gris_ms;
   ctx->stats.last_temporal_ms = ctx->restir_temporal ? temporal_ms : 0.0f;
-  ctx->stats.kernel_launches = (ctx->restir_temporal ? 5u : 4u) * (uint32_t)n_frames;  // k_jitter, k_path, k_rc_sky, [k_temporal,] k_gris
-  ctx->stats.launches_total += ctx->stats.kernel_launches;
   return VRT_OK;
 }
 
@@ -1263,6 +1273,7 @@ int vrt_get_stats(vrt_ctx* ctx, vrt_stats* out) {
   REQUIRE(out, "vrt_get_stats: null pointer");
   CK(cudaSetDevice(ctx->device));
   if (int rc = drain_ring(ctx)) return rc;  // waits for the asynchronous launches still in flight
+  if (int rc = drain_restir_events(ctx)) return rc;
   *out = ctx->stats;
   ctx->stats.render_ms_sum = 0.0f, ctx->stats.render_launches = 0, ctx->stats.launches_total = 0;  // "since the last query"
   return VRT_OK;
