@@ -435,7 +435,12 @@ def leg_config5(vrt, torch, dist, rank, world, device, spp=1024):
     fm = parallel.FusedMerge(r) if world > 1 else None
     host = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
     with torch.cuda.stream(stream):
-        r.accumulate(8)  # warm-up
+        if fm:
+            fm.begin(1)
+        r.accumulate(8)  # warm-up, incl. one merge: the first collective on a stream pays NCCL's set-up
+        if fm:
+            fm.merge()
+            fm.barrier()
         r.reset_framebuffer()
     torch.cuda.synchronize()
     if world > 1:
@@ -492,8 +497,11 @@ def leg_config4_rows(vrt, torch, dist, rank, world, device, W, H, sky_res, frame
     r.set_restir_temporal(True)
     fm = parallel.FusedMerge(r)
     with torch.cuda.stream(stream):
-        for k in range(4):  # warm-up: the chain reaches its steady state
+        for k in range(4):  # warm-up: the chain reaches its steady state; the first collective on a stream pays NCCL's set-up
+            fm.begin(k, reset=False)
             r.accumulate_restir(1)
+            fm.merge()
+        fm.barrier()
     torch.cuda.synchronize()
     dist.barrier()
     clocks = ClockSampler(device).start() if rank == 0 else None
