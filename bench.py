@@ -115,53 +115,59 @@ class Workload:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled during a timed region. In-process NVML (two cheap queries every 50 ms from a
+    thread); an `nvidia-smi -lms 50` child — the obvious way — is NOT used: its periodic multi-field query stalls kernel
+    launches on the GPU it watches and cost the launch-heavy ReSTIR legs a factor 2-3 (2.14 -> 3.85-6.35 ms/frame at
+    N = 4, profiles/r03h_clock_sampler_perturbation.log) and the 5 ms path-kernel steps ~0.8 %."""
 
     def __init__(self, index):
-        self.index, self.lines, self.p = index, [], None
+        self.index, self.samples, self.stop_flag, self.t, self.err = index, [], threading.Event(), None, None
 
     def start(self):
+        if os.environ.get("VRT_BENCH_NO_CLOCKS"):  # diagnostic: is the sampler itself perturbing a leg?
+            self.err = "disabled by VRT_BENCH_NO_CLOCKS"
+            return self
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                    except Exception as e:  # noqa: BLE001
+                        self.err = repr(e)
+                        return
+                    self.stop_flag.wait(0.05)
+
+            self.pynvml = pynvml
+            self.t = threading.Thread(target=loop, daemon=True)
             self.t.start()
-            # the first sample takes nvidia-smi ~0.1-0.3 s: do not start the clock before the sampler runs
             t0 = time.time()
-            while not self.lines and time.time() - t0 < 3.0:
-                time.sleep(0.01)
-        except Exception:
-            self.p = None
+            while not self.samples and self.err is None and time.time() - t0 < 2.0:
+                time.sleep(0.005)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
         return self
 
-    def _read(self):
-        for ln in self.p.stdout:
-            self.lines.append(ln.strip())
-
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        time.sleep(0.12)
-        self.p.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable: %s" % self.err], "samples": 0}
+        self.stop_flag.set()
+        self.t.join(timeout=1.0)
+        nv = self.pynvml
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(nm for nm, bit in names.items() if any(r & bit for _, r in self.samples))
+        sm = [c for c, _ in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "how": "in-process NVML, 50 ms period"}
 
 
 def measured_peak():
@@ -480,7 +486,7 @@ def leg_config5(vrt, torch, dist, rank, world, device, spp=1024):
     return out
 
 
-def leg_config4_rows(vrt, torch, dist, rank, world, device, W, H, sky_res, frames=24):
+def leg_config4_rows(vrt, torch, dist, rank, world, device, W, H, sky_res, frames=120):
     """config 4 on N GPUs as ONE reservoir chain: row strips with a 24-pixel halo (vrt_set_row_shard), temporal + spatial
     resampling per frame, the strips merged per frame by the fused peer-memory kernel. Strong scaling of the ReSTIR frame."""
     from voxel_rt2_b200 import parallel
