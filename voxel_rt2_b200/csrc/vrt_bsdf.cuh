@@ -227,6 +227,46 @@ HD f3 GGX_VNDF_aniso(f3 v, f3 n, f3 tang, f3 bitang, float ax, float ay, float u
   return h;
 }
 
+// The specular-lobe sampler of sample_disney, out of line by default (VRT_COLD_SPEC): on the dense benchmark scene
+// 2-3 lanes of a warp take it per shading stage (200 SASS instructions in the middle of the main loop otherwise), and
+// with 24 warps per SM the loop is instruction-fetch sensitive: +2.0 % on config 3 (profiles/r03m_ab_coldspec.log).
+// Results move in the last ulp (no FMA contraction across the call), inside every radiance tolerance.
+struct SpecParams {
+  f3 base_col;
+  float metallic, specular, specular_tint, ax, ay, inv_pi_axay, sw;
+};
+struct SpecSample {
+  f3 dir, brdf;
+  float pdf;
+};
+HD Mat spec_mat(const SpecParams& p) {
+  Mat m{};
+  m.base_col = p.base_col, m.metallic = p.metallic, m.specular = p.specular, m.specular_tint = p.specular_tint;
+  m.ax = p.ax, m.ay = p.ay, m.inv_pi_axay = p.inv_pi_axay, m.sw = p.sw;
+  return m;
+}
+HD SpecSample spec_sample_body(const Mat& m, f3 v, f3 n, f3 tang, f3 bitang, float ux, float uy) {
+  SpecSample r;
+  f3 h = GGX_VNDF_aniso(v, n, tang, bitang, m.ax, m.ay, ux, uy);
+  r.dir = reflect(-v, h);
+  // pdf with the sampled micro-normal (bsdf.py:290-302)
+  float D = GTR2_anisotropic(m, dot(n, h), dot(h, tang), dot(h, bitang));
+  float Gv = smithG_GGX_aniso(dot(n, v), dot(v, tang), dot(v, bitang), m.ax, m.ay);
+  r.pdf = fdiv(Gv * fabsf(dot(r.dir, h)) * D, fabsf(dot(n, r.dir))) * m.sw;
+  // brdf with the half vector recomputed from (dir, v) as the reference does (:430-450)
+  Geo g = make_geo(v, n, r.dir, tang, bitang);
+  r.brdf = disney_specular(m, g);
+  return r;
+}
+#ifndef VRT_COLD_SPEC
+#define VRT_COLD_SPEC 1
+#endif
+#if VRT_COLD_SPEC
+VRT_COLD SpecSample cold_spec_sample(SpecParams p, f3 v, f3 n, f3 tang, f3 bitang, float ux, float uy) {
+  return spec_sample_body(spec_mat(p), v, n, tang, bitang, ux, uy);
+}
+#endif
+
 // bsdf.py:395-458 sample_disney: returns direction, brdf of the chosen lobe, pdf (lobe pdf x
 // lobe probability; inf/NaN -> 1) and the lobe id.
 HD f3 sample_disney(const Mat& m, f3 v, f3 n, f3 tang, f3 bitang, float u_lobe, float ux, float uy, f3& brdf, float& pdf, int& lobe) {
@@ -239,16 +279,14 @@ HD f3 sample_disney(const Mat& m, f3 v, f3 n, f3 tang, f3 bitang, float u_lobe, 
     f3 h = normalize(dir + v);
     brdf = disney_diffuse(m, n_dot_l, dot(n, v), dot(dir, h)) * (1.0f - m.metallic);
   } else if (u_lobe <= m.dw + m.sw) {
-    f3 h = GGX_VNDF_aniso(v, n, tang, bitang, m.ax, m.ay, ux, uy);
-    dir = reflect(-v, h);
-    // pdf with the sampled micro-normal (bsdf.py:290-302)
-    float D = GTR2_anisotropic(m, dot(n, h), dot(h, tang), dot(h, bitang));
-    float Gv = smithG_GGX_aniso(dot(n, v), dot(v, tang), dot(v, bitang), m.ax, m.ay);
-    pdf = fdiv(Gv * fabsf(dot(dir, h)) * D, fabsf(dot(n, dir))) * m.sw;
+#if VRT_COLD_SPEC
+    const SpecSample r = cold_spec_sample(SpecParams{m.base_col, m.metallic, m.specular, m.specular_tint, m.ax, m.ay, m.inv_pi_axay, m.sw}, v, n, tang,
+                                          bitang, ux, uy);
+#else
+    const SpecSample r = spec_sample_body(m, v, n, tang, bitang, ux, uy);
+#endif
+    dir = r.dir, pdf = r.pdf, brdf = r.brdf;
     lobe = LOBE_SPEC_REFL;
-    // brdf with the half vector recomputed from (dir, v) as the reference does (:430-450)
-    Geo g = make_geo(v, n, dir, tang, bitang);
-    brdf = disney_specular(m, g);
   } else {
     const float4 r = cold_clearcoat_sample(coat_of(m), v, n, tang, bitang, ux, uy);
     dir = f3{r.x, r.y, r.z};
