@@ -76,7 +76,13 @@ enum { PIX_IDLE = -1, PIX_DONE = -2 };
 #define VRT_PATH_MIN_BLOCKS 1
 #endif
 #ifndef VRT_RESTIR_THREADS
-#define VRT_RESTIR_THREADS 128  // ... of the ReSTIR / moving-camera variants (12 resident warps per SM)
+#define VRT_RESTIR_THREADS 512  // ... of the ReSTIR variant: ONE CTA of 16 warps per SM at 123 registers, no spills. Measured at 1080p
+                                // (profiles/r04c_ab_restir_threads.log), path + reservoir pass of example6 / example3 in ms: 3 x 128 threads
+                                // (145 regs, 12 warps) 1.861 / 2.119; 1 x 384 1.840 / 2.091; 1 x 512 1.711 / 1.908; 1 x 640 (96 regs, 178 B
+                                // of spills) 1.712 / 1.888; 768 threads would spill 422 B
+#endif
+#ifndef VRT_MOVING_THREADS
+#define VRT_MOVING_THREADS 128  // ... of the moving-camera variant (12 resident warps per SM)
 #endif
 
 // RESTIR = true is the USE_RESTIR_PT variant of render (pathtracer.py:15): besides the pixel
@@ -89,7 +95,8 @@ enum { PIX_IDLE = -1, PIX_DONE = -2 };
 // the G-buffer the reprojecting temporal filters need (NDC depth, octahedral normal, material,
 // virtual reflection depth; pathtracer.py:535-546) is written next to the two colour buffers.
 template <bool STATS, int MODE, bool SKY16 = false>
-__global__ void __launch_bounds__(MODE != 0 ? VRT_RESTIR_THREADS : VRT_PATH_THREADS, MODE != 0 ? 384 / VRT_RESTIR_THREADS : VRT_PATH_MIN_BLOCKS) k_path(const __grid_constant__ Params P, int upper_in_smem, RestirBuffers RB, MovingOut MO) {
+__global__ void __launch_bounds__(MODE == 1 ? VRT_RESTIR_THREADS : (MODE == 2 ? VRT_MOVING_THREADS : VRT_PATH_THREADS),
+                                  MODE == 1 ? 1 : (MODE == 2 ? 384 / VRT_MOVING_THREADS : VRT_PATH_MIN_BLOCKS)) k_path(const __grid_constant__ Params P, int upper_in_smem, RestirBuffers RB, MovingOut MO) {
   constexpr bool RESTIR = MODE == 1;
   constexpr bool MOVING = MODE == 2;
   extern __shared__ uint32_t smem[];
@@ -651,7 +658,7 @@ static cudaError_t launch_path_t(const Params& P, int sm_count, cudaStream_t st,
   int uis;
   size_t sm = smem_bytes(P, &uis);
   int per_sm = 0;
-  constexpr int threads = MODE != 0 ? VRT_RESTIR_THREADS : VRT_PATH_THREADS;
+  constexpr int threads = MODE == 1 ? VRT_RESTIR_THREADS : (MODE == 2 ? VRT_MOVING_THREADS : VRT_PATH_THREADS);
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_path<STATS, MODE, SKY16>, threads, sm);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
