@@ -127,38 +127,222 @@ def test_taichi_shim_vector_semantics():
     assert list(w) == [-1.0, 9, 3.0] and list(w.zx) == [3.0, -1.0]
 
 
-@pytest.mark.parametrize("example,occupied", [("main", 1), ("example1", 3539), ("example3", 13168)])
-def test_reference_examples_run_unchanged_through_the_shim(example, occupied):
-    """The scene scripts of the reference execute unmodified (authoring only: the renderer is a
-    stub because this container has no GPU). Needs the mounted reference tree."""
-    path = "/root/reference/%s.py" % example
-    if not os.path.exists(path):
-        pytest.skip("reference tree not mounted")
+class _StubRenderer:
+    def __init__(self, **kw):
+        pass
+
+    def __getattr__(self, n):
+        return lambda *a, **k: np.zeros((4, 4, 4), np.float32) if n == "fetch_image" else None
+
+
+def _run_script(path, *, vectorise=True, legacy=False, seed=0):
+    """Execute a scene script unchanged through the shim with a stub renderer (authoring only: this container has no
+    GPU) and return its Scene. `vectorise` / `legacy` select the shim's execution mode for this run."""
     import voxel_rt2_b200.scene as S
-
-    class Stub:
-        def __init__(self, **kw):
-            pass
-
-        def __getattr__(self, n):
-            return lambda *a, **k: np.zeros((4, 4, 4), np.float32) if n == "fetch_image" else None
+    import taichi
+    from taichi import _simd
 
     orig, save = S.Scene.__init__, S.save_image
 
     def patched(self, *a, **k):
-        k["renderer_factory"] = Stub
+        k["renderer_factory"] = _StubRenderer
         orig(self, *a, **k)
 
     S.Scene.__init__ = patched
     S.save_image = lambda img, p: None
+    saved = (_simd.ENABLED, taichi._LEGACY_RNG)
+    _simd.ENABLED, taichi._LEGACY_RNG = vectorise and not legacy, legacy
     try:
-        import taichi
-
-        taichi.seed(0)
+        taichi.seed(seed)
         g = runpy.run_path(path, run_name="__main__")
     finally:
         S.Scene.__init__, S.save_image = orig, save
-    assert int((g["scene"].voxel_material > 0).sum()) == occupied
+        _simd.ENABLED, taichi._LEGACY_RNG = saved
+    return g["scene"]
+
+
+def _digest(scene):
+    import hashlib
+
+    return hashlib.sha256(scene.voxel_material.tobytes() + scene.voxel_color.tobytes()).hexdigest()[:16]
+
+
+# occupied voxels and sha256 of (material, colour) of every script of the reference, shim seed 0. The digests were
+# taken from the PLAIN execution (VRT_SHIM_VECTORIZE=0: one loop iteration at a time, 63 s for the eleven scripts);
+# the default, vectorised execution has to land on the same bytes (8 s).
+_EXAMPLE_SCENES = [
+    ("main", 1, "3caf0fff8cdc3d51"),
+    ("example1", 3580, "3b98603cb73a22f3"),
+    ("example2", 2356, "704493698d73d16b"),
+    ("example3", 13168, "d52f94ba2ae36bb2"),
+    ("example4", 319489, "6ce6fa5311fd1c57"),
+    ("example5", 87350, "c288dcf5808c3e91"),
+    ("example6", 265546, "9d8e9df4dbe45793"),
+    ("example7", 93623, "bc7212bf47fb13bc"),
+    ("example8", 272309, "8d4ec87c2cca7638"),
+    ("example9", 85710, "d9044ca15eb9d8bd"),
+    ("example10", 95488, "193f472b5f3445c8"),
+]
+
+
+@pytest.mark.parametrize("example,occupied,digest", _EXAMPLE_SCENES)
+def test_reference_examples_run_unchanged_through_the_shim(example, occupied, digest):
+    """The scene scripts of the reference execute unmodified, vectorised (compat/taichi/_simd.py), and build exactly the
+    scene the one-iteration-at-a-time execution builds. Needs the mounted reference tree."""
+    path = "/root/reference/%s.py" % example
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    scene = _run_script(path)
+    assert int((scene.voxel_material > 0).sum()) == occupied
+    assert _digest(scene) == digest
+
+
+@pytest.mark.parametrize("example", ["example1", "example2", "example7", "example10"])
+def test_vectorised_and_plain_execution_of_the_examples_agree(example):
+    """The same script run both ways in this process (the cheap ones; the digests above cover the rest): while loops with
+    per-lane trip counts, swizzles, get_voxel of an earlier kernel's voxels and random draws under masks (example7), grouped
+    loops with random colours (example10)."""
+    path = "/root/reference/%s.py" % example
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    a, b = _run_script(path, vectorise=True), _run_script(path, vectorise=False)
+    assert np.array_equal(a.voxel_material, b.voxel_material) and np.array_equal(a.voxel_color, b.voxel_color)
+
+
+@pytest.mark.parametrize("example", ["example1", "example3", "example6"])
+def test_legacy_rng_reproduces_the_committed_fixture_scenes(example):
+    """tests/golden/<example>_seed0.npz were generated with the shim's first, sequential RNG (VRT_SHIM_RNG=legacy): that
+    mode still rebuilds them byte for byte, so every golden derived from them stays reproducible."""
+    path = "/root/reference/%s.py" % example
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    scene = _run_script(path, legacy=True)
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", example + "_seed0.npz"))
+    assert np.array_equal(scene.voxel_material, z["material"]) and np.array_equal(scene.voxel_color, z["color"])
+
+
+_SYNTHETIC_SCRIPT = """
+from scene import Scene
+import taichi as ti
+from taichi.math import *
+
+scene = Scene(voxel_edges=0, exposure=1)
+
+@ti.func
+def shade(p, k):
+    c = vec3(0.2, 0.4, 0.6) * (0.5 + 0.5 * ti.random())
+    if k % 3 == 0:
+        c = vec3(c.z, c.x, c.y)
+    elif p.norm() < 20 and ti.random() < 0.5:
+        c = c * 0.25 + vec3(ti.sin(p.x * 0.3), ti.cos(p.y * 0.2), fract(p.z * 0.37)) * 0.1
+    return c
+
+@ti.func
+def column(x, z, base):
+    h = int(6 + 10 * ti.random() * max(0, 1 - vec2(x, z).norm() / 40))   # per-lane trip count
+    for y in range(base, base + h):
+        scene.set_voxel(vec3(x, y, z), 1 if y % 4 else 2, shade(vec3(x, y, z), y))
+    t = 0
+    n = x * x + z * z
+    while n % 7 != 0 and t < 5:   # per-lane while
+        n += 3
+        t += 1
+    scene.set_voxel(ivec3(x, base - 1, z), 10 + t, vec3(0.1 * t, 1 - 0.1 * t, 0.5 if t > 2 else 0.25))
+
+@ti.func
+def first_gap(x, z):   # not vectorisable (break): runs one call per lane
+    r = -1
+    for y in range(-40, 0):
+        if scene.get_voxel(ivec3(x, y, z))[0] == 0:
+            r = y
+            break
+    return r
+
+@ti.kernel
+def build():
+    for i, j in ti.ndrange((-30, 30), (-30, 30)):
+        if (i + j) % 2 == 0 or ti.random() < 0.3:
+            column(i, j, -20)
+    for I in ti.grouped(ti.ndrange((-8, 8), (20, 28), (-8, 8))):
+        w = 1.0 if I.norm() < 24 else 0.0
+        if ti.random() < 0.5 * w and not (I.x == 0 and I.z == 0):
+            scene.set_voxel(I + ivec3(0, 1, 0), 3, vec3(0.9, 0.8, 0.7) * ti.random())
+            scene.set_voxel(I, 4, vec3(0.3))    # overlaps the previous statement of the lane below: order matters
+
+@ti.kernel
+def annotate():
+    for i, j in ti.ndrange((-10, 10), (-10, 10)):
+        m, c = scene.get_voxel(ivec3(i, -20, j))   # written by build(): read-only here
+        g = first_gap(i, j)
+        if m > 0:
+            scene.set_voxel(ivec3(i, 40, j), m, c * 0.5 + vec3(0.01 * (g + 40)))
+    for k in ti.ndrange(12):
+        mat, col = scene.get_voxel(ivec3(k, 41, 0))
+        scene.set_voxel(ivec3(k + 1, 41, 0), mat + 1, col + 0.05)   # reads what the previous iteration wrote: sequential
+
+@ti.func
+def cell(k):
+    return ivec3(k % 50 - 25, 50, k // 50 - 30)
+
+@ti.kernel
+def chain():
+    for k in ti.ndrange(3000):
+        if k >= 2500:   # reads the voxel the previous iteration wrote: with 1000-lane chunks the conflict shows up in the third chunk
+            m, c = scene.get_voxel(cell(k - 1))
+            scene.set_voxel(cell(k), 5, c * 0.9 + 0.05)
+        else:
+            scene.set_voxel(cell(k), 5, vec3(ti.random()))
+
+build()
+annotate()
+chain()
+"""
+
+
+@pytest.mark.parametrize("max_lanes", [1 << 22, 1000])
+def test_vectorised_shim_equals_plain_execution_on_a_synthetic_script(tmp_path, monkeypatch, max_lanes):
+    """Self-contained version of the agreement test (no reference tree): masks from if / elif / and / or / conditional
+    expressions with random draws inside them, inner loops and while loops with per-lane trip counts, two writes to one
+    voxel from neighbouring lanes, a function the pass leaves alone (break) called per lane, get_voxel of an earlier
+    kernel's voxels, loops that read their own writes (one falls back to sequential execution on its own; the other finds out
+    in its third chunk, after two chunks have been applied, and the whole kernel is rolled back and re-run sequentially)."""
+    import voxel_rt2_b200.scene  # noqa: F401  (registers the shim as `taichi`)
+    from taichi import _simd
+
+    monkeypatch.setattr(_simd, "MAX_LANES", max_lanes)
+    monkeypatch.syspath_prepend(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    path = tmp_path / "synthetic_scene.py"
+    path.write_text(_SYNTHETIC_SCRIPT)
+    a, b = _run_script(str(path), vectorise=True, seed=5), _run_script(str(path), vectorise=False, seed=5)
+    assert int((a.voxel_material != 0).sum()) > 20000
+    assert np.array_equal(a.voxel_material, b.voxel_material) and np.array_equal(a.voxel_color, b.voxel_color)
+    c = _run_script(str(path), vectorise=True, seed=6)
+    assert not np.array_equal(a.voxel_color, c.voxel_color)  # the seed reaches ti.random()
+
+
+def test_shim_math_is_bit_identical_on_lane_arrays():
+    """Every taichi.math function gives, on an array, exactly the values it gives element by element (NumPy's own exp /
+    log / pow / tan / atan2 / acos differ from libm in the last ulp and are therefore not used)."""
+    import voxel_rt2_b200.scene  # noqa: F401  (registers the shim as `taichi`)
+    import taichi as ti
+    from taichi import math as tm
+
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-50, 50, 4000)
+    pos = np.abs(x) + 1e-3
+    unit = np.clip(x / 50, -1, 1)
+    for f, arg in ((tm.sin, x), (tm.cos, x), (tm.tan, x), (tm.exp, x / 10), (tm.log, pos), (tm.sqrt, pos), (tm.acos, unit), (tm.asin, unit),
+                   (tm.floor, x), (tm.ceil, x), (tm.fract, x), (tm.sign, x), (ti.round, x), (ti.abs, x), (tm.int, x), (tm.float, x)):
+        assert np.array_equal(np.asarray(f(arg), np.float64), np.array([float(f(float(v))) for v in arg])), f
+    y = rng.uniform(-3, 3, 4000)
+    for f in (tm.atan2, tm.pow, tm.mod, tm.min, tm.max, tm.step):
+        a = pos if f is tm.pow else x
+        assert np.array_equal(np.asarray(f(a, y), np.float64), np.array([float(f(float(u), float(v))) for u, v in zip(a, y)])), f
+    k = rng.integers(-9, 9, 4000)
+    assert np.array_equal(tm.pow(k, 3), np.array([int(v) ** 3 for v in k]))
+    v = tm.vec3(x, 2.0, y)
+    n = v.norm()
+    assert np.array_equal(n, np.array([tm.vec3(float(a), 2.0, float(b)).norm() for a, b in zip(x, y)]))
 
 
 def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():

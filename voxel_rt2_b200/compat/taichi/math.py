@@ -5,6 +5,10 @@ that is how `int(vec2(...))` (legal inside a Taichi kernel) keeps working in pla
 import builtins as _b
 import math as _m
 
+import operator as _operator
+
+import numpy as _np
+
 pi = _m.pi
 e = _m.e
 inf = float("inf")
@@ -16,12 +20,73 @@ def _is_vec(x):
 
 _set = object.__setattr__
 _SCALARS = (_b.int, _b.float, _b.bool)
+_ND = _np.ndarray
+
+# --- lane arrays. Inside a vectorised loop (compat/taichi/_simd.py) the loop indices, and everything computed
+# from them, are NumPy arrays with one element per iteration ("lane"); a Vec then holds arrays as components.
+# Every function below therefore accepts arrays next to Python numbers. Functions whose NumPy implementation is
+# not bit-identical to libm's (exp, log, pow, tan, atan, acos, ... differ in the last ulp) go through the math
+# module element by element, so that a vectorised loop computes exactly what the plain Python loop computes.
+
+
+def _exact1(f):
+    def g(x):
+        if type(x) is _ND:
+            return _np.fromiter(map(f, x.ravel().tolist()), _np.float64, x.size).reshape(x.shape)
+        return f(x)
+
+    return g
+
+
+def _exact2(f):
+    def g(a, b):
+        if type(a) is _ND or type(b) is _ND:
+            a, b = _np.broadcast_arrays(a, b)
+            return _np.fromiter(map(f, a.ravel().tolist(), b.ravel().tolist()), _np.float64, a.size).reshape(a.shape)
+        return f(a, b)
+
+    return g
+
+
+def _pow_any(a, b):
+    """a ** b with Python's semantics (libm pow for floats, exact integers for int ** non-negative int)."""
+    if type(a) is _ND or type(b) is _ND:
+        ka = a.dtype.kind if type(a) is _ND else ("i" if type(a) is _b.int else "f")
+        kb = b.dtype.kind if type(b) is _ND else ("i" if type(b) is _b.int else "f")
+        if ka in "iub" and kb in "iub" and _np.all(_np.asarray(b) >= 0):
+            return _np.power(_np.asarray(a, _np.int64), _np.asarray(b, _np.int64))
+        return _pow_f(a, b)
+    return a ** b
+
+
+def _np1(f, nf):
+    def g(x):
+        if type(x) is _ND:
+            return nf(x)
+        return f(x)
+
+    return g
+
+
+def _bi(x):
+    """int(bool) of a comparison result (Taichi comparisons yield integers)."""
+    return x.astype(_np.int64) if type(x) is _ND else _b.int(x)
+
+
+def _ii(x):
+    return x.astype(_np.int64) if type(x) is _ND else _b.int(x)
+
+
+_sqrt = _np1(_m.sqrt, _np.sqrt)
+_pow_f = _exact2(_operator.pow)
+_pow = _pow_any
 
 
 class Vec:
     """Small fixed-size numeric vector with GLSL-style swizzles and element-wise operators."""
 
     __slots__ = ("v",)
+    __array_ufunc__ = None  # lane_array * Vec must reach Vec.__rmul__ instead of NumPy treating the Vec as a sequence
     _SW = {"x": 0, "y": 1, "z": 2, "w": 3, "r": 0, "g": 1, "b": 2, "a": 3}
 
     def __init__(self, vals):
@@ -114,24 +179,24 @@ class Vec:
     def __rfloordiv__(self, o): return self._rbin(o, lambda a, b: a // b)
     def __mod__(self, o): return self._bin(o, lambda a, b: a % b)
     def __rmod__(self, o): return self._rbin(o, lambda a, b: a % b)
-    def __pow__(self, o): return self._bin(o, lambda a, b: a ** b)
-    def __rpow__(self, o): return self._rbin(o, lambda a, b: a ** b)
-    def __and__(self, o): return self._bin(o, lambda a, b: _b.int(a) & _b.int(b))
-    def __rand__(self, o): return self._rbin(o, lambda a, b: _b.int(a) & _b.int(b))
-    def __or__(self, o): return self._bin(o, lambda a, b: _b.int(a) | _b.int(b))
-    def __ror__(self, o): return self._rbin(o, lambda a, b: _b.int(a) | _b.int(b))
-    def __xor__(self, o): return self._bin(o, lambda a, b: _b.int(a) ^ _b.int(b))
-    def __rxor__(self, o): return self._rbin(o, lambda a, b: _b.int(a) ^ _b.int(b))
+    def __pow__(self, o): return self._bin(o, _pow)
+    def __rpow__(self, o): return self._rbin(o, _pow)
+    def __and__(self, o): return self._bin(o, lambda a, b: _ii(a) & _ii(b))
+    def __rand__(self, o): return self._rbin(o, lambda a, b: _ii(a) & _ii(b))
+    def __or__(self, o): return self._bin(o, lambda a, b: _ii(a) | _ii(b))
+    def __ror__(self, o): return self._rbin(o, lambda a, b: _ii(a) | _ii(b))
+    def __xor__(self, o): return self._bin(o, lambda a, b: _ii(a) ^ _ii(b))
+    def __rxor__(self, o): return self._rbin(o, lambda a, b: _ii(a) ^ _ii(b))
     def __neg__(self): return Vec([-a for a in self.v])
     def __pos__(self): return Vec(self.v)
-    def __abs__(self): return Vec([_b.abs(a) for a in self.v])
+    def __abs__(self): return Vec([_b.abs(a) for a in self.v])  # abs() of an array is element-wise
     # comparisons are element-wise and return integer vectors, as in Taichi
-    def __eq__(self, o): return self._bin(o, lambda a, b: _b.int(a == b))
-    def __ne__(self, o): return self._bin(o, lambda a, b: _b.int(a != b))
-    def __lt__(self, o): return self._bin(o, lambda a, b: _b.int(a < b))
-    def __le__(self, o): return self._bin(o, lambda a, b: _b.int(a <= b))
-    def __gt__(self, o): return self._bin(o, lambda a, b: _b.int(a > b))
-    def __ge__(self, o): return self._bin(o, lambda a, b: _b.int(a >= b))
+    def __eq__(self, o): return self._bin(o, lambda a, b: _bi(a == b))
+    def __ne__(self, o): return self._bin(o, lambda a, b: _bi(a != b))
+    def __lt__(self, o): return self._bin(o, lambda a, b: _bi(a < b))
+    def __le__(self, o): return self._bin(o, lambda a, b: _bi(a <= b))
+    def __gt__(self, o): return self._bin(o, lambda a, b: _bi(a > b))
+    def __ge__(self, o): return self._bin(o, lambda a, b: _bi(a >= b))
     __hash__ = None
 
     # --- methods used by the examples
@@ -144,8 +209,8 @@ class Vec:
     def norm(self, eps=0.0):
         a = self.v
         if len(a) == 3:
-            return _m.sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + eps)
-        return _m.sqrt(_b.sum(x * x for x in a) + eps)
+            return _sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + eps)
+        return _sqrt(_b.sum(x * x for x in a) + eps)
 
     def norm_sqr(self):
         return _b.sum(a * a for a in self.v)
@@ -158,10 +223,10 @@ class Vec:
         return _b.sum(self.v)
 
     def max(self):
-        return _b.max(self.v)
+        return _minmax(_b.max, self.v)
 
     def min(self):
-        return _b.min(self.v)
+        return _minmax(_b.min, self.v)
 
     def cross(self, o):
         a, b = self.v, list(o)
@@ -204,11 +269,11 @@ def _make_ctor(n, conv):
 
 
 def _to_f(x):
-    return _b.float(x)
+    return x.astype(_np.float64) if type(x) is _ND else _b.float(x)
 
 
 def _to_i(x):
-    return _b.int(x)  # truncation toward zero, like a Taichi i32 cast
+    return x.astype(_np.int64) if type(x) is _ND else _b.int(x)  # truncation toward zero, like a Taichi i32 cast
 
 
 _vec2g, _vec3g, _vec4g = _make_ctor(2, _to_f), _make_ctor(3, _to_f), _make_ctor(4, _to_f)
@@ -253,13 +318,17 @@ uvec2, uvec3, uvec4 = ivec2, ivec3, ivec4
 
 def int(x=0, *a):  # noqa: A001 - deliberate shadow, see module docstring
     if isinstance(x, Vec):
-        return Vec([_b.int(c) for c in x.v])
+        return Vec([_to_i(c) for c in x.v])
+    if type(x) is _ND:
+        return x.astype(_np.int64)
     return _b.int(x, *a)
 
 
 def float(x=0.0):  # noqa: A001
     if isinstance(x, Vec):
-        return Vec([_b.float(c) for c in x.v])
+        return Vec([_to_f(c) for c in x.v])
+    if type(x) is _ND:
+        return x.astype(_np.float64)
     return _b.float(x)
 
 
@@ -287,37 +356,56 @@ def mix(x, y, a):
     return x * (1 - a) + y * a
 
 
-fract = _lift1(lambda x: x - _m.floor(x))
-floor = _lift1(lambda x: _b.float(_m.floor(x)))
-ceil = _lift1(lambda x: _b.float(_m.ceil(x)))
-sign = _lift1(lambda x: (x > 0) - (x < 0))
-sqrt = _lift1(_m.sqrt)
-sin = _lift1(_m.sin)
-cos = _lift1(_m.cos)
-tan = _lift1(_m.tan)
-exp = _lift1(_m.exp)
-log = _lift1(_m.log)
-acos = _lift1(_m.acos)
-asin = _lift1(_m.asin)
-atan2 = _lift2(_m.atan2)
-pow = _lift2(lambda a, b: a ** b)
-mod = _lift2(lambda a, b: a - b * _m.floor(a / b))
-step = _lift2(lambda edge, x: 0.0 if x < edge else 1.0)
+_floor = _np1(lambda x: _b.float(_m.floor(x)), _np.floor)
+_ceil = _np1(lambda x: _b.float(_m.ceil(x)), _np.ceil)
+fract = _lift1(lambda x: x - _floor(x))  # int - float for an integer argument, as before
+floor = _lift1(_floor)
+ceil = _lift1(_ceil)
+sign = _lift1(lambda x: _bi(x > 0) - _bi(x < 0))
+sqrt = _lift1(_sqrt)
+sin = _lift1(_np1(_m.sin, _np.sin))  # NumPy's sin / cos agree with libm bit for bit (checked by the tests), the rest does not
+cos = _lift1(_np1(_m.cos, _np.cos))
+tan = _lift1(_exact1(_m.tan))
+exp = _lift1(_exact1(_m.exp))
+log = _lift1(_exact1(_m.log))
+acos = _lift1(_exact1(_m.acos))
+asin = _lift1(_exact1(_m.asin))
+atan2 = _lift2(_exact2(_m.atan2))
+pow = _lift2(_pow)
+mod = _lift2(lambda a, b: a - b * _floor(a / b))
+step = _lift2(lambda edge, x: _np.where(x < edge, 0.0, 1.0) if (type(x) is _ND or type(edge) is _ND) else (0.0 if x < edge else 1.0))
 
 
 def abs(x):  # noqa: A001
     return x.__abs__() if isinstance(x, Vec) else _b.abs(x)
 
 
+def _mm2(f):
+    nf = _np.minimum if f is _b.min else _np.maximum
+
+    def g(a, b):
+        if type(a) is _ND or type(b) is _ND:
+            return nf(a, b)
+        return f(a, b)
+
+    return g
+
+
+_MM = {_b.min: _mm2(_b.min), _b.max: _mm2(_b.max)}
+
+
 def _minmax(f, args):
     if len(args) == 1 and isinstance(args[0], Vec):
-        return f(args[0].v)
+        args = args[0].v
+    elif len(args) == 1 and isinstance(args[0], (list, tuple)):
+        args = args[0]
+    g = _MM[f]
     r = args[0]
     for o in args[1:]:
         if isinstance(r, Vec) or isinstance(o, Vec):
-            r = _lift2(lambda a, b: f(a, b))(r, o)
+            r = _lift2(g)(r, o)
         else:
-            r = f(r, o)
+            r = g(r, o)
     return r
 
 
@@ -358,16 +446,26 @@ def normalize(a):
     return Vec(a).normalized()
 
 
+def _truthy(c):
+    return (c != 0) if type(c) is _ND else bool(c)
+
+
 def any(x):  # noqa: A001
     if isinstance(x, Vec):
-        return _b.int(_b.any(x.v))
-    return _b.int(bool(x))
+        r = _truthy(x.v[0])
+        for c in x.v[1:]:
+            r = r | _truthy(c)
+        return _bi(r)
+    return _bi(_truthy(x))
 
 
 def all(x):  # noqa: A001
     if isinstance(x, Vec):
-        return _b.int(_b.all(x.v))
-    return _b.int(bool(x))
+        r = _truthy(x.v[0])
+        for c in x.v[1:]:
+            r = r & _truthy(c)
+        return _bi(r)
+    return _bi(_truthy(x))
 
 
 def reflect(i, n):

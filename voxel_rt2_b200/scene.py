@@ -37,6 +37,10 @@ import numpy as np
 from . import compat
 
 compat.install()
+try:  # the shim's vectorised kernels (compat/taichi/_simd.py); absent when a real Taichi is installed
+    from taichi import _simd as _vz
+except ImportError:
+    _vz = None
 
 from .renderer import Renderer  # noqa: E402
 
@@ -150,6 +154,10 @@ class Scene:
         self._clouds = False
         self.last_image = None
         self.last_stats = None
+        if _vz is not None:
+            import weakref
+
+            _vz.SCENES[:] = [r for r in _vz.SCENES if r() is not None] + [weakref.ref(self)]
 
     # ------------------------------------------------------------------ voxel authoring
     @staticmethod
@@ -175,14 +183,45 @@ class Scene:
         if not (0 <= i < R and 0 <= j < R and 0 <= k < R):
             return  # the reference writes out of bounds silently; ignored here
         o = (i * R + j) * R + k
+        r, g, b = color
+        if _vz is not None and _vz.PLAIN_LOG is not None:
+            # a plain-Python function running lane by lane inside a vectorised loop: the write joins the loop's ordered log
+            _vz.PLAIN_LOG.add(self, o, ((int(mat) + 128) & 255) - 128, (_u8(r), _u8(g), _u8(b)))
+            return
         self._mat_mv[o] = ((int(mat) + 128) & 255) - 128  # ti.cast(mat, ti.i8) wraps
         # rgb32f_to_rgb8: clamp, u8(c * 255) truncation in float32 (math_utils.py:86-92)
-        r, g, b = color
         o *= 3
         cm = self._col_mv
         cm[o] = _u8(r)
         cm[o + 1] = _u8(g)
         cm[o + 2] = _u8(b)
+
+    def _set_voxel_lanes(self, m, idx, mat, color):
+        """set_voxel for every lane of mask m of a vectorised loop (compat/taichi/_simd.py): the same rounding, clamping
+        and truncation as above on arrays; the writes are logged and applied in iteration order when the loop ends."""
+        if m is True:
+            return self.set_voxel(idx, mat, color)
+        L = _vz.LANES
+        sel, o = self._lane_index(m, idx)
+        if len(sel) == 0:
+            return
+        take = lambda x: x[sel] if type(x) is np.ndarray else x  # noqa: E731
+        mi = take(mat)
+        mi = mi.astype(np.int64) if type(mi) is np.ndarray else int(mi)
+        m8 = np.broadcast_to(((mi + 128) & 255) - 128, sel.shape).astype(np.int8)
+        rgb = np.empty((len(sel), 3), np.uint8)
+        comps = list(color)
+        if len(comps) != 3:
+            raise ValueError("set_voxel: colour must have 3 components")
+        for ch, c in enumerate(comps):
+            if type(c) is np.ndarray:
+                x = np.clip(c[sel].astype(np.float32), np.float32(0.0), np.float32(1.0))
+                rgb[:, ch] = (x * np.float32(255.0)).astype(np.uint8)
+            else:
+                rgb[:, ch] = _u8(c)
+        L.writes.append((self, sel, o, m8, rgb))
+
+    set_voxel.__simd__ = _set_voxel_lanes
 
     def get_voxel(self, idx):  # scene.py:143-146 -> pathtracer.py:1330-1334
         from taichi.math import vec3
@@ -198,8 +237,53 @@ class Scene:
         if not (0 <= i < R and 0 <= j < R and 0 <= k < R):
             return 0, vec3(0.0)
         o = (i * R + j) * R + k
+        if _vz is not None and _vz.PLAIN_LOG is not None:
+            _vz.PLAIN_LOG.read(self, o)  # checked against the loop's logged writes when it ends
         cm = self._col_mv
         return self._mat_mv[o], vec3(cm[3 * o] / 255.0, cm[3 * o + 1] / 255.0, cm[3 * o + 2] / 255.0)
+
+    def _lane_index(self, m, idx):
+        """round_idx for the lanes of mask m: (lane numbers, flat voxel indices) of those that address the grid."""
+        R = self.grid_res
+        h = R >> 1
+        sel = np.flatnonzero(m)
+        inb = np.ones(len(sel), bool)
+        ijk = []
+        for c in idx:
+            if type(c) is np.ndarray:
+                c = c[sel]
+                if c.dtype.kind == "f":
+                    f = c.astype(np.float32).astype(np.float64)
+                    c = np.where(f >= 0, np.floor(f + 0.5), np.ceil(f - 0.5)).astype(np.int64)
+                else:
+                    c = c.astype(np.int64)
+            else:
+                c = c if type(c) is int else self.round_idx((c,))[0]
+            c = c + h
+            inb &= (c >= 0) & (c < R)
+            ijk.append(c)
+        if len(ijk) != 3:
+            raise ValueError("voxel index must have 3 components")
+        o = np.broadcast_to((ijk[0] * R + ijk[1]) * R + ijk[2], sel.shape)
+        return sel[inb], o[inb].astype(np.int64)
+
+    def _get_voxel_lanes(self, m, idx):
+        """get_voxel for the lanes of mask m. The voxels are read now, while the loop's own writes are still in its
+        log: the read indices are recorded and the loop is re-run sequentially if it also wrote one of them."""
+        if m is True:
+            return self.get_voxel(idx)
+        from taichi.math import Vec
+
+        L = _vz.LANES
+        sel, o = self._lane_index(m, idx)
+        L.reads.append((self, o))
+        mat = np.zeros(L.n, np.int64)
+        mat[sel] = self.voxel_material.reshape(-1)[o]
+        col = np.zeros((L.n, 3), np.float64)
+        col[sel] = self.voxel_color.reshape(-1, 3)[o] / 255.0
+        return mat, Vec([col[:, 0].copy(), col[:, 1].copy(), col[:, 2].copy()])
+
+    get_voxel.__simd__ = _get_voxel_lanes
 
     # ------------------------------------------------------------------ scene settings
     def set_floor(self, height, color, material=1):
