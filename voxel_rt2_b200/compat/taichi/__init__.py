@@ -102,6 +102,12 @@ class _NDRange:
     def product(self):
         return itertools.product(*self.ranges)
 
+    def total(self):
+        n = 1
+        for r in self.ranges:
+            n *= len(r)
+        return n
+
     def __iter__(self):
         if self.varying:
             raise TypeError("ndrange with per-lane bounds iterated outside a vectorised loop")

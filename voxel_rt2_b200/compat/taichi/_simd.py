@@ -33,6 +33,7 @@ from .math import Vec
 
 ENABLED = os.environ.get("VRT_SHIM_VECTORIZE", "1") != "0" and os.environ.get("VRT_SHIM_RNG", "") != "legacy"
 MAX_LANES = 1 << 22  # lanes per chunk of a vectorised loop (bounds the size of the temporaries)
+MIN_LANES = 16       # a loop with fewer iterations runs one index at a time (its inner loops would otherwise walk arrays of a few lanes)
 _ND = np.ndarray
 _M64 = (1 << 64) - 1
 _C0, _C1, _C2, _C3 = 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB, 0xD6E8FEB86659FD93
@@ -467,7 +468,7 @@ def loop(m, it, st):
                 raise Unsupported("per-lane ndrange outside a vectorised loop")
             yield from _iter_ndrange_varying(m, nd, grouped)
             return
-        if m is True and LANES is None and ENABLED and RNG.depth == 0 and st[0] != 2:
+        if m is True and LANES is None and ENABLED and RNG.depth == 0 and st[0] != 2 and nd.total() >= MIN_LANES:
             st[0] = 1
             yield from _launch(nd, grouped, st)
             st[0] = 0
