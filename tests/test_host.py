@@ -250,13 +250,42 @@ def column(x, z, base):
     scene.set_voxel(ivec3(x, base - 1, z), 10 + t, vec3(0.1 * t, 1 - 0.1 * t, 0.5 if t > 2 else 0.25))
 
 @ti.func
-def first_gap(x, z):   # not vectorisable (break): runs one call per lane
+def first_gap(x, z):   # break out of an inner loop, lane by lane
     r = -1
     for y in range(-40, 0):
         if scene.get_voxel(ivec3(x, y, z))[0] == 0:
             r = y
             break
     return r
+
+@ti.func
+def dots(x, z):   # continue / break in for and while loops, random draws after the jumps
+    n = 0
+    for y in range(60, 70):
+        if (x + y + z) % 3 == 0:
+            continue
+        if ti.random() < 0.1:
+            break
+        scene.set_voxel(ivec3(x, y, z), 6, vec3(ti.random(), 0.5, 0.1 * n))
+        n += 1
+    t = 0
+    while True:
+        t += 1
+        if t > 6 or ti.random() < 0.2:
+            break
+        if t % 2 == 0:
+            continue
+        scene.set_voxel(ivec3(x, 70 + t, z), 7, vec3(0.1 * t))
+
+@ti.func
+def odd_one(x, z):   # a function the pass leaves alone (it stores to a global): runs one call per active lane
+    global _calls
+    _calls = _calls + 1
+    if x % 5 == 0:
+        scene.set_voxel(ivec3(x, 80, z), 8, vec3(ti.random()))
+    return x + z
+
+_calls = 0
 
 @ti.kernel
 def build():
@@ -276,6 +305,10 @@ def annotate():
         g = first_gap(i, j)
         if m > 0:
             scene.set_voxel(ivec3(i, 40, j), m, c * 0.5 + vec3(0.01 * (g + 40)))
+        dots(i, j)
+        if (i * j) % 4 == 1:
+            w = odd_one(i, j)
+            scene.set_voxel(ivec3(i, 81, j), 9, vec3(0.01 * (w + 30)))
     for k in ti.ndrange(12):
         mat, col = scene.get_voxel(ivec3(k, 41, 0))
         scene.set_voxel(ivec3(k + 1, 41, 0), mat + 1, col + 0.05)   # reads what the previous iteration wrote: sequential
@@ -303,7 +336,8 @@ chain()
 def test_vectorised_shim_equals_plain_execution_on_a_synthetic_script(tmp_path, monkeypatch, max_lanes):
     """Self-contained version of the agreement test (no reference tree): masks from if / elif / and / or / conditional
     expressions with random draws inside them, inner loops and while loops with per-lane trip counts, two writes to one
-    voxel from neighbouring lanes, a function the pass leaves alone (break) called per lane, get_voxel of an earlier
+    voxel from neighbouring lanes, break / continue in inner for and while loops, a function the pass leaves alone (global
+    statement) called per lane, get_voxel of an earlier
     kernel's voxels, loops that read their own writes (one falls back to sequential execution on its own; the other finds out
     in its third chunk, after two chunks have been applied, and the whole kernel is rolled back and re-run sequentially)."""
     import voxel_rt2_b200.scene  # noqa: F401  (registers the shim as `taichi`)

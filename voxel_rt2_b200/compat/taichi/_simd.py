@@ -14,9 +14,12 @@ The contract is that the vectorised loop leaves EXACTLY the scene the plain loop
  * arithmetic is the same IEEE double arithmetic; functions whose NumPy version differs from libm in the last ulp
    are evaluated through the math module (taichi/math.py);
  * voxel writes are replayed sorted by (lane, time), i.e. in the order the sequential loop issues them.
-Anything the pass does not understand (while, break, get_voxel inside a loop, closures, ...) leaves the function as
-it was — it then runs as plain Python, also when called from a vectorised loop (one call per active lane). A
-failure inside a vectorised kernel rolls the scene back and re-runs the kernel in plain Python.
+`while`, `break` and `continue` are masked like `if`; `scene.get_voxel` reads the grid as it is when the loop starts and
+the loop is re-run sequentially if it also WROTE one of the voxels it read. Anything the pass does not understand
+(closures, global statements, early returns, ...) leaves the function as it was — it then runs as plain Python, also
+when called from a vectorised loop (one call per active lane, its writes joining the loop's log). A failure inside a
+vectorised loop re-runs that loop sequentially; if part of it has already been applied, the scene is rolled back and
+the whole kernel re-runs in plain Python.
 VRT_SHIM_VECTORIZE=0 switches the pass off.
 """
 import ast
@@ -191,6 +194,31 @@ def m_and(m, c):
     if m is True:
         return c
     return m & c
+
+
+def m_or(a, b):
+    if a is True or b is True:
+        return True
+    if a is False:
+        return b
+    if b is False:
+        return a
+    return a | b
+
+
+def m_test(m, th):
+    """Loop test of a while: evaluated for the lanes still in the loop (not at all when none is left)."""
+    if not live(m):
+        return False
+    return m_and(m, truth(th(m)))
+
+
+def brk(st, b, m):
+    """`break` under mask m. Leaving an outermost loop that runs as a vectorised launch would cancel every later
+    iteration, draws and writes included: that loop is re-run one index at a time instead."""
+    if st is not None and st[0] == 1:
+        raise Unsupported("break in a loop that runs as a vectorised launch")
+    return m_or(b, m)
 
 
 def m_andnot(m, c):
@@ -619,9 +647,19 @@ def pow_(a, b):
     return tm._pow(a, b)
 
 
+def _has_jump(node):
+    """Does the statement contain a break / continue of the loop it sits in (not of a loop nested inside it)?"""
+    if isinstance(node, (ast.Break, ast.Continue)):
+        return True
+    if isinstance(node, (ast.For, ast.While, ast.FunctionDef, ast.Lambda)):
+        return False
+    return _b.any(_has_jump(c) for c in ast.iter_child_nodes(node))
+
+
 class _Stmts:
     def __init__(self):
         self.n = 0
+        self.loops = []  # (break-mask name, continue-mask name, retry-token name or None) of the enclosing loops
 
     def fresh(self, stem):
         self.n += 1
@@ -668,6 +706,14 @@ class _Stmts:
         out = []
         for k, s in enumerate(stmts):
             out += self.stmt(s, mask, last=top and k == len(stmts) - 1)
+            if self.loops and k + 1 < len(stmts) and not isinstance(s, (ast.For, ast.While)) and _has_jump(s):
+                # lanes that hit a break / continue inside s skip the rest of the block
+                b, c, _ = self.loops[-1]
+                m2 = self.fresh("m")
+                out.append(ast.Assign([ast.Name(m2, ast.Store())],
+                                      self.vz("m_andnot", ast.Name(mask, ast.Load()), self.vz("m_or", ast.Name(c, ast.Load()), ast.Name(b, ast.Load())))))
+                out.append(ast.If(self.vz("live", ast.Name(m2, ast.Load())), self.block(stmts[k + 1:], m2), []))
+                break
         return out or [ast.Pass()]
 
     def stmt(self, s, mask, last=False):
@@ -676,6 +722,12 @@ class _Stmts:
             return [ast.Expr(self.expr(s.value, mask))]
         if isinstance(s, ast.Pass):
             return [s]
+        if isinstance(s, ast.Break):
+            b, _, st = self.loops[-1]
+            return [ast.Assign([ast.Name(b, ast.Store())], self.vz("brk", ast.Name(st, ast.Load()) if st else ast.Constant(None), ast.Name(b, ast.Load()), m))]
+        if isinstance(s, ast.Continue):
+            _, c, _ = self.loops[-1]
+            return [ast.Assign([ast.Name(c, ast.Store())], self.vz("m_or", ast.Name(c, ast.Load()), m))]
         if isinstance(s, ast.Assign):
             val = self.expr(s.value, mask)
             if len(s.targets) == 1:
@@ -708,9 +760,21 @@ class _Stmts:
             if s.orelse:
                 raise Unsupported("for ... else")
             m1, v = self.fresh("m"), self.fresh("v")
+            st, ex = self.fresh("s"), self.fresh("e")
+            jumps = _b.any(_has_jump(x) for x in s.body)
+            bk, cn = self.fresh("b"), self.fresh("k")
+            self.loops.append((bk, cn, st))
+            inner = self.block(s.body, m1)
+            self.loops.pop()
             # the loop variable is stored unmasked: a lane that does not take part in an iteration never reads it, and
             # the index of a masked inner loop stays a plain number
-            body = [ast.Assign([self._store_target(s.target)], ast.Name(v, ast.Load()))] + self.block(s.body, m1)
+            body = [ast.Assign([self._store_target(s.target)], ast.Name(v, ast.Load()))] + inner
+            if jumps:
+                # per iteration: nobody has continued yet; lanes that broke out earlier stay out (plain code really leaves)
+                body = [ast.Assign([ast.Name(cn, ast.Store())], ast.Constant(False)),
+                        ast.If(ast.Compare(ast.Name(bk, ast.Load()), [ast.Is()], [ast.Constant(True)]), [ast.Break()], []),
+                        ast.Assign([ast.Name(m1, ast.Store())], self.vz("m_andnot", ast.Name(m1, ast.Load()), ast.Name(bk, ast.Load()))),
+                        ast.If(self.vz("live", ast.Name(m1, ast.Load())), body, [])]
             tgt = ast.Tuple([ast.Name(m1, ast.Store()), ast.Name(v, ast.Store())], ast.Store())
             # st = [0]
             # while True:
@@ -719,12 +783,13 @@ class _Stmts:
             #         break
             #     except Exception as e:
             #         if not _vz.retry_plain(st, e): raise
-            st, ex = self.fresh("s"), self.fresh("e")
             loop = ast.For(tgt, self.vz("loop", m, self.expr(s.iter, mask), ast.Name(st, ast.Load())), body, [])
             handler = ast.ExceptHandler(ast.Name("Exception", ast.Load()), ex,
                                         [ast.If(ast.UnaryOp(ast.Not(), self.vz("retry_plain", ast.Name(st, ast.Load()), ast.Name(ex, ast.Load()))), [ast.Raise(None, None)], [])])
+            # (a retry starts from a clean break mask: the assignment sits inside the retry loop)
             return [ast.Assign([ast.Name(st, ast.Store())], ast.List([ast.Constant(0)], ast.Load())),
-                    ast.While(ast.Constant(True), [ast.Try([loop, ast.Break()], [handler], [], [])], [])]
+                    ast.While(ast.Constant(True), [ast.Assign([ast.Name(bk, ast.Store())], ast.Constant(False)),
+                                                   ast.Try([loop, ast.Break()], [handler], [], [])], [])]
         if isinstance(s, ast.While):
             if s.orelse:
                 raise Unsupported("while ... else")
@@ -734,9 +799,16 @@ class _Stmts:
             #     if not live(mw): break
             #     body under mw
             mw = self.fresh("m")
-            head = [ast.Assign([ast.Name(mw, ast.Store())], self.vz("m_and", ast.Name(mw, ast.Load()), self.vz("truth", self.expr(s.test, mw)))),
+            bk, cn = self.fresh("b"), self.fresh("k")
+            self.loops.append((bk, cn, None))
+            inner = self.block(s.body, mw)
+            self.loops.pop()
+            head = [ast.Assign([ast.Name(cn, ast.Store())], ast.Constant(False)),
+                    ast.Assign([ast.Name(mw, ast.Store())], self.vz("m_andnot", ast.Name(mw, ast.Load()), ast.Name(bk, ast.Load()))),
+                    ast.Assign([ast.Name(mw, ast.Store())], self.vz("m_test", ast.Name(mw, ast.Load()), _Expr(mw)._thunk(s.test))),
                     ast.If(ast.UnaryOp(ast.Not(), self.vz("live", ast.Name(mw, ast.Load()))), [ast.Break()], [])]
-            return [ast.Assign([ast.Name(mw, ast.Store())], m), ast.While(ast.Constant(True), head + self.block(s.body, mw), [])]
+            return [ast.Assign([ast.Name(mw, ast.Store())], m), ast.Assign([ast.Name(bk, ast.Store())], ast.Constant(False)),
+                    ast.While(ast.Constant(True), head + inner, [])]
         if isinstance(s, ast.Return):
             if not last:
                 raise Unsupported("return before the end of the function")
