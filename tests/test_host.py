@@ -169,7 +169,7 @@ def _digest(scene):
 
 # occupied voxels and sha256 of (material, colour) of every script of the reference, shim seed 0. The digests were
 # taken from the PLAIN execution (VRT_SHIM_VECTORIZE=0: one loop iteration at a time, 63 s for the eleven scripts);
-# the default, vectorised execution has to land on the same bytes (8 s).
+# the default, vectorised execution has to land on the same bytes (4 s).
 _EXAMPLE_SCENES = [
     ("main", 1, "3caf0fff8cdc3d51"),
     ("example1", 3580, "3b98603cb73a22f3"),
@@ -332,7 +332,7 @@ chain()
 """
 
 
-@pytest.mark.parametrize("max_lanes", [1 << 22, 1000])
+@pytest.mark.parametrize("max_lanes", [1 << 22, 1000])  # one chunk per loop / many
 def test_vectorised_shim_equals_plain_execution_on_a_synthetic_script(tmp_path, monkeypatch, max_lanes):
     """Self-contained version of the agreement test (no reference tree): masks from if / elif / and / or / conditional
     expressions with random draws inside them, inner loops and while loops with per-lane trip counts, two writes to one
