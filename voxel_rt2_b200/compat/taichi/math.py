@@ -363,8 +363,8 @@ floor = _lift1(_floor)
 ceil = _lift1(_ceil)
 sign = _lift1(lambda x: _bi(x > 0) - _bi(x < 0))
 sqrt = _lift1(_sqrt)
-sin = _lift1(_np1(_m.sin, _np.sin))  # NumPy's sin / cos agree with libm bit for bit (checked by the tests), the rest does not
-cos = _lift1(_np1(_m.cos, _np.cos))
+sin = _lift1(_exact1(_m.sin))  # (NumPy's sin / cos agree with libm on this machine, but its SIMD dispatch depends on the CPU)
+cos = _lift1(_exact1(_m.cos))
 tan = _lift1(_exact1(_m.tan))
 exp = _lift1(_exact1(_m.exp))
 log = _lift1(_exact1(_m.log))
