@@ -326,9 +326,18 @@ def chain():
         else:
             scene.set_voxel(cell(k), 5, vec3(ti.random()))
 
+@ti.kernel
+def count():
+    total = 0
+    for i, j in ti.ndrange((-20, 20), (-20, 20)):   # a reduction: every iteration reads what the previous ones left -> sequential
+        if scene.get_voxel(ivec3(i, -20, j))[0] > 0:
+            total += 1
+    scene.set_voxel(ivec3(0, 45, 0), total % 100, vec3(0.001 * total))
+
 build()
 annotate()
 chain()
+count()
 """
 
 

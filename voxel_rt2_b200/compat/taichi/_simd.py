@@ -656,6 +656,81 @@ def _has_jump(node):
     return _b.any(_has_jump(c) for c in ast.iter_child_nodes(node))
 
 
+def _target_names(t):
+    if isinstance(t, ast.Name):
+        return {t.id}
+    if isinstance(t, (ast.Tuple, ast.List)):
+        out = set()
+        for e in t.elts:
+            out |= _target_names(e)
+        return out
+    return set()
+
+
+def _carried(loop):
+    """Does an iteration of this for-loop read what an earlier iteration wrote (`count += 1`, `acc[0] = ...` on something
+    defined outside the loop)? Such a loop is sequential by nature and never runs as a vectorised launch. Conservative:
+    a name counts as defined inside an iteration only after an unconditional assignment (or one on both arms of an if)."""
+    stored = {n.id for n in ast.walk(ast.Module(loop.body, [])) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
+
+    def loads(node):
+        return {n.id for n in ast.walk(node) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+
+    def scan(stmts, defined):
+        """-> (carried?, names definitely assigned after the block)"""
+        defined = set(defined)
+        for st in stmts:
+            if isinstance(st, ast.Assign):
+                if (loads(st.value) & stored) - defined:
+                    return True, defined
+                for t in st.targets:
+                    if isinstance(t, (ast.Subscript, ast.Attribute)):
+                        base = t
+                        while isinstance(base, (ast.Subscript, ast.Attribute)):
+                            base = base.value
+                        if (loads(t) & stored) - defined or not (isinstance(base, ast.Name) and base.id in defined):
+                            return True, defined  # a store into an object that lives across iterations
+                    defined |= _target_names(t)
+            elif isinstance(st, ast.AugAssign):
+                names = loads(st.value) | loads(st.target) | _target_names(st.target)
+                base = st.target
+                while isinstance(base, (ast.Subscript, ast.Attribute)):
+                    base = base.value
+                if isinstance(base, ast.Name):
+                    names.add(base.id)
+                    if base.id not in defined:
+                        return True, defined
+                if (names & stored) - defined:
+                    return True, defined
+            elif isinstance(st, ast.If):
+                if (loads(st.test) & stored) - defined:
+                    return True, defined
+                c1, d1 = scan(st.body, defined)
+                c2, d2 = scan(st.orelse, defined)
+                if c1 or c2:
+                    return True, defined
+                defined |= d1 & d2
+            elif isinstance(st, (ast.For, ast.While)):
+                head = st.iter if isinstance(st, ast.For) else st.test
+                if (loads(head) & stored) - defined:
+                    return True, defined
+                inner = set(defined) | (_target_names(st.target) if isinstance(st, ast.For) else set())
+                # inside an inner loop a name may legitimately carry from one of ITS iterations to the next: only reads of names
+                # that this outer iteration has not defined at all are a dependence on an earlier outer iteration
+                body_stored = {n.id for n in ast.walk(ast.Module(st.body, [])) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
+                if ((loads(ast.Module(st.body, [])) & stored) - inner) - body_stored:
+                    return True, defined
+                c, _ = scan(st.body, inner | body_stored)
+                if c:
+                    return True, defined
+            else:
+                if (loads(st) & stored) - defined:
+                    return True, defined
+        return False, defined
+
+    return scan(loop.body, _target_names(loop.target))[0]
+
+
 class _Stmts:
     def __init__(self):
         self.n = 0
@@ -783,11 +858,13 @@ class _Stmts:
             #         break
             #     except Exception as e:
             #         if not _vz.retry_plain(st, e): raise
+            # a loop whose iterations depend on each other starts with its retry token at 2: never a vectorised launch
+            first = 2 if _carried(s) else 0
             loop = ast.For(tgt, self.vz("loop", m, self.expr(s.iter, mask), ast.Name(st, ast.Load())), body, [])
             handler = ast.ExceptHandler(ast.Name("Exception", ast.Load()), ex,
                                         [ast.If(ast.UnaryOp(ast.Not(), self.vz("retry_plain", ast.Name(st, ast.Load()), ast.Name(ex, ast.Load()))), [ast.Raise(None, None)], [])])
             # (a retry starts from a clean break mask: the assignment sits inside the retry loop)
-            return [ast.Assign([ast.Name(st, ast.Store())], ast.List([ast.Constant(0)], ast.Load())),
+            return [ast.Assign([ast.Name(st, ast.Store())], ast.List([ast.Constant(first)], ast.Load())),
                     ast.While(ast.Constant(True), [ast.Assign([ast.Name(bk, ast.Store())], ast.Constant(False)),
                                                    ast.Try([loop, ast.Break()], [handler], [], [])], [])]
         if isinstance(s, ast.While):
