@@ -334,10 +334,19 @@ def count():
             total += 1
     scene.set_voxel(ivec3(0, 45, 0), total % 100, vec3(0.001 * total))
 
+@ti.kernel
+def last():
+    best = -1
+    for k in ti.ndrange(64):   # leaves a value behind for the code after the loop (the last matching iteration's) -> sequential
+        if k % 7 == 3 and scene.get_voxel(cell(k))[0] == 5:
+            best = k
+    scene.set_voxel(ivec3(1, 45, 0), 20 + best % 10, vec3(0.2))
+
 build()
 annotate()
 chain()
 count()
+last()
 """
 
 

@@ -667,68 +667,63 @@ def _target_names(t):
     return set()
 
 
-def _carried(loop):
-    """Does an iteration of this for-loop read what an earlier iteration wrote (`count += 1`, `acc[0] = ...` on something
-    defined outside the loop)? Such a loop is sequential by nature and never runs as a vectorised launch. Conservative:
-    a name counts as defined inside an iteration only after an unconditional assignment (or one on both arms of an if)."""
-    stored = {n.id for n in ast.walk(ast.Module(loop.body, [])) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
+def _loads(node):
+    return {n.id for n in ast.walk(node) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
 
-    def loads(node):
-        return {n.id for n in ast.walk(node) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
 
-    def scan(stmts, defined):
-        """-> (carried?, names definitely assigned after the block)"""
-        defined = set(defined)
-        for st in stmts:
-            if isinstance(st, ast.Assign):
-                if (loads(st.value) & stored) - defined:
-                    return True, defined
-                for t in st.targets:
-                    if isinstance(t, (ast.Subscript, ast.Attribute)):
-                        base = t
+def _stored(stmts):
+    return {n.id for n in ast.walk(ast.Module(list(stmts), [])) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
+
+
+def _exposed(stmts, defined):
+    """Names a statement list reads before it has definitely assigned them (conservative: an assignment counts only if it is
+    unconditional or sits on both arms of an if) -> (exposed names, names definitely assigned afterwards, stores into objects
+    that were not created by these statements?)."""
+    defined = set(defined)
+    exposed = set()
+    outer_store = False
+    for st in stmts:
+        if isinstance(st, ast.Assign):
+            exposed |= _loads(st.value) - defined
+            for t in st.targets:
+                for sub in ([t] if not isinstance(t, (ast.Tuple, ast.List)) else t.elts):
+                    if isinstance(sub, (ast.Subscript, ast.Attribute)):
+                        exposed |= _loads(sub) - defined
+                        base = sub
                         while isinstance(base, (ast.Subscript, ast.Attribute)):
                             base = base.value
-                        if (loads(t) & stored) - defined or not (isinstance(base, ast.Name) and base.id in defined):
-                            return True, defined  # a store into an object that lives across iterations
-                    defined |= _target_names(t)
-            elif isinstance(st, ast.AugAssign):
-                names = loads(st.value) | loads(st.target) | _target_names(st.target)
-                base = st.target
-                while isinstance(base, (ast.Subscript, ast.Attribute)):
-                    base = base.value
-                if isinstance(base, ast.Name):
-                    names.add(base.id)
-                    if base.id not in defined:
-                        return True, defined
-                if (names & stored) - defined:
-                    return True, defined
-            elif isinstance(st, ast.If):
-                if (loads(st.test) & stored) - defined:
-                    return True, defined
-                c1, d1 = scan(st.body, defined)
-                c2, d2 = scan(st.orelse, defined)
-                if c1 or c2:
-                    return True, defined
-                defined |= d1 & d2
-            elif isinstance(st, (ast.For, ast.While)):
-                head = st.iter if isinstance(st, ast.For) else st.test
-                if (loads(head) & stored) - defined:
-                    return True, defined
-                inner = set(defined) | (_target_names(st.target) if isinstance(st, ast.For) else set())
-                # inside an inner loop a name may legitimately carry from one of ITS iterations to the next: only reads of names
-                # that this outer iteration has not defined at all are a dependence on an earlier outer iteration
-                body_stored = {n.id for n in ast.walk(ast.Module(st.body, [])) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
-                if ((loads(ast.Module(st.body, [])) & stored) - inner) - body_stored:
-                    return True, defined
-                c, _ = scan(st.body, inner | body_stored)
-                if c:
-                    return True, defined
-            else:
-                if (loads(st) & stored) - defined:
-                    return True, defined
-        return False, defined
+                        if not (isinstance(base, ast.Name) and base.id in defined):
+                            outer_store = True
+                defined |= _target_names(t)
+        elif isinstance(st, ast.AugAssign):
+            exposed |= (_loads(st.value) | _loads(st.target) | _target_names(st.target)) - defined
+            base = st.target
+            while isinstance(base, (ast.Subscript, ast.Attribute)):
+                base = base.value
+            if isinstance(st.target, (ast.Subscript, ast.Attribute)) and not (isinstance(base, ast.Name) and base.id in defined):
+                outer_store = True
+        elif isinstance(st, ast.If):
+            exposed |= _loads(st.test) - defined
+            e1, d1, o1 = _exposed(st.body, defined)
+            e2, d2, o2 = _exposed(st.orelse, defined)
+            exposed |= e1 | e2
+            outer_store |= o1 or o2
+            defined |= d1 & d2
+        elif isinstance(st, (ast.For, ast.While)):
+            exposed |= _loads(st.iter if isinstance(st, ast.For) else st.test) - defined
+            e, _, o = _exposed(st.body, defined | (_target_names(st.target) if isinstance(st, ast.For) else set()))
+            exposed |= e
+            outer_store |= o
+        else:
+            exposed |= _loads(st) - defined
+    return exposed, defined, outer_store
 
-    return scan(loop.body, _target_names(loop.target))[0]
+
+def _carried(loop):
+    """Does an iteration of this for-loop read what an earlier iteration wrote (`count += 1`, `acc[0] = ...` on something
+    defined outside the loop)? Such a loop is sequential by nature and never runs as a vectorised launch."""
+    exposed, _, outer_store = _exposed(loop.body, _target_names(loop.target))
+    return outer_store or bool(exposed & _stored(loop.body))
 
 
 class _Stmts:
@@ -777,21 +772,23 @@ class _Stmts:
             return ast.Tuple([ast.Name(e.id, ast.Store()) for e in t.elts], ast.Store())
         raise Unsupported("loop target")
 
-    def block(self, stmts, mask, top=False):
+    def block(self, stmts, mask, top=False, after=frozenset()):
+        """`after`: the names that whatever runs after this block (in the enclosing blocks) reads before assigning them."""
         out = []
         for k, s in enumerate(stmts):
-            out += self.stmt(s, mask, last=top and k == len(stmts) - 1)
+            follow = _exposed(stmts[k + 1:], set())[0] | after
+            out += self.stmt(s, mask, last=top and k == len(stmts) - 1, after=follow)
             if self.loops and k + 1 < len(stmts) and not isinstance(s, (ast.For, ast.While)) and _has_jump(s):
                 # lanes that hit a break / continue inside s skip the rest of the block
                 b, c, _ = self.loops[-1]
                 m2 = self.fresh("m")
                 out.append(ast.Assign([ast.Name(m2, ast.Store())],
                                       self.vz("m_andnot", ast.Name(mask, ast.Load()), self.vz("m_or", ast.Name(c, ast.Load()), ast.Name(b, ast.Load())))))
-                out.append(ast.If(self.vz("live", ast.Name(m2, ast.Load())), self.block(stmts[k + 1:], m2), []))
+                out.append(ast.If(self.vz("live", ast.Name(m2, ast.Load())), self.block(stmts[k + 1:], m2, after=after), []))
                 break
         return out or [ast.Pass()]
 
-    def stmt(self, s, mask, last=False):
+    def stmt(self, s, mask, last=False, after=frozenset()):
         m = ast.Name(mask, ast.Load())
         if isinstance(s, ast.Expr):
             return [ast.Expr(self.expr(s.value, mask))]
@@ -826,10 +823,10 @@ class _Stmts:
             c, m1, m2 = self.fresh("c"), self.fresh("m"), self.fresh("m")
             out = [ast.Assign([ast.Name(c, ast.Store())], self.vz("truth", self.expr(s.test, mask))),
                    ast.Assign([ast.Name(m1, ast.Store())], self.vz("m_and", m, ast.Name(c, ast.Load()))),
-                   ast.If(self.vz("live", ast.Name(m1, ast.Load())), self.block(s.body, m1), [])]
+                   ast.If(self.vz("live", ast.Name(m1, ast.Load())), self.block(s.body, m1, after=after), [])]
             if s.orelse:
                 out += [ast.Assign([ast.Name(m2, ast.Store())], self.vz("m_andnot", m, ast.Name(c, ast.Load()))),
-                        ast.If(self.vz("live", ast.Name(m2, ast.Load())), self.block(s.orelse, m2), [])]
+                        ast.If(self.vz("live", ast.Name(m2, ast.Load())), self.block(s.orelse, m2, after=after), [])]
             return out
         if isinstance(s, ast.For):
             if s.orelse:
@@ -839,7 +836,7 @@ class _Stmts:
             jumps = _b.any(_has_jump(x) for x in s.body)
             bk, cn = self.fresh("b"), self.fresh("k")
             self.loops.append((bk, cn, st))
-            inner = self.block(s.body, m1)
+            inner = self.block(s.body, m1, after=after | _exposed(s.body, set())[0])  # (what follows the body includes its next iteration)
             self.loops.pop()
             # the loop variable is stored unmasked: a lane that does not take part in an iteration never reads it, and
             # the index of a masked inner loop stays a plain number
@@ -859,7 +856,8 @@ class _Stmts:
             #     except Exception as e:
             #         if not _vz.retry_plain(st, e): raise
             # a loop whose iterations depend on each other starts with its retry token at 2: never a vectorised launch
-            first = 2 if _carried(s) else 0
+            # ... and so does a loop that leaves a value behind for the code after it (the last iteration's, sequentially)
+            first = 2 if (_carried(s) or (after & _stored(s.body))) else 0
             loop = ast.For(tgt, self.vz("loop", m, self.expr(s.iter, mask), ast.Name(st, ast.Load())), body, [])
             handler = ast.ExceptHandler(ast.Name("Exception", ast.Load()), ex,
                                         [ast.If(ast.UnaryOp(ast.Not(), self.vz("retry_plain", ast.Name(st, ast.Load()), ast.Name(ex, ast.Load()))), [ast.Raise(None, None)], [])])
@@ -878,7 +876,7 @@ class _Stmts:
             mw = self.fresh("m")
             bk, cn = self.fresh("b"), self.fresh("k")
             self.loops.append((bk, cn, None))
-            inner = self.block(s.body, mw)
+            inner = self.block(s.body, mw, after=after | _exposed(s.body, set())[0] | _loads(s.test))
             self.loops.pop()
             head = [ast.Assign([ast.Name(cn, ast.Store())], ast.Constant(False)),
                     ast.Assign([ast.Name(mw, ast.Store())], self.vz("m_andnot", ast.Name(mw, ast.Load()), ast.Name(bk, ast.Load()))),
