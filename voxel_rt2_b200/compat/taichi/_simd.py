@@ -15,7 +15,9 @@ The contract is that the vectorised loop leaves EXACTLY the scene the plain loop
    are evaluated through the math module (taichi/math.py);
  * voxel writes are replayed sorted by (lane, time), i.e. in the order the sequential loop issues them.
 `while`, `break` and `continue` are masked like `if`; `scene.get_voxel` reads the grid as it is when the loop starts and
-the loop is re-run sequentially if it also WROTE one of the voxels it read. Anything the pass does not understand
+the loop is re-run sequentially if it also WROTE one of the voxels it read. A loop whose iterations depend on each other (a reduction into a name or object defined outside the loop, or a value the
+code after the loop reads) is recognised statically and runs one index at a time; so does a loop with fewer than MIN_LANES
+iterations. Anything the pass does not understand
 (closures, global statements, early returns, ...) leaves the function as it was — it then runs as plain Python, also
 when called from a vectorised loop (one call per active lane, its writes joining the loop's log). A failure inside a
 vectorised loop re-runs that loop sequentially; if part of it has already been applied, the scene is rolled back and
