@@ -8,7 +8,8 @@
 Workload (config.workload = "config3"): BASELINE.json configs[2] — synthetic dense random 256^3
 voxel grid (~50 % occupancy), 1920x1080, depth 4, physical sky + clouds, sun (1,1,1); this is the
 configuration the north-star target (>= 1 Gpaths/s per B200) is quoted on and it fits one GPU.
-A "step" is one accumulate() batch of --spp samples per pixel over the whole frame.
+A "step" is one accumulate() batch of --spp samples per pixel over the whole frame (default 64: config 3 is quoted at ">= 64 spp
+per timing"; until profiles/r04l the default was 8, which measures 3.7 % lower because the per-launch costs weigh more).
 
 N > 1 (launched by torch.distributed.run, one rank per GPU): sample sharding — rank r renders
 sample indices r, r+N, ... of every pixel (weak scaling: per-GPU work fixed). Per step the partial
@@ -53,7 +54,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--spp", type=int, default=8, help="samples per pixel per step (per GPU)")
+    ap.add_argument("--spp", type=int, default=64,
+                    help="samples per pixel per step (per GPU). 64 = the batch BASELINE.json config 3 names (\">= 64 spp per timing\") and the default "
+                         "VRT_SPP of Scene.finish; one k_path launch per step. Measured device rate by batch: 8 spp 3.50, 16 spp 3.56, 32 spp 3.58, "
+                         "64 spp 3.63 G paths/s (profiles/r04l_spp_per_launch.log): per-launch set-up, the tail of the tile queue and the one "
+                         "accumulation read-modify-write per pixel are amortised over more samples")
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--res", default="1920x1080")
     ap.add_argument("--sky-res", type=int, default=3840)
