@@ -443,6 +443,7 @@ def test_scene_script_with_kernels_runs_end_to_end_on_gpu(vrt, oracle, tmp_path,
     path = tmp_path / "synthetic_scene.py"
     path.write_text(_SYNTHETIC_SCRIPT + "\nscene.set_floor(-0.4, (1.0, 1.0, 1.0))\nscene.set_directional_light((1, 1, 1), 0.1, (1, 1, 1))\n"
                     "scene.set_background_color((0.3, 0.4, 0.6))\nscene.finish()\n")
+    import voxel_rt2_b200.scene  # noqa: F401  (registers the shim as `taichi`)
     import taichi
 
     taichi.seed(5)
