@@ -15,7 +15,7 @@ import random as _random
 import numpy as _np
 
 from . import math  # noqa: F401  (ti.math)
-from .math import Vec, _exact1, _exact2, _lift1, _lift2, _np1
+from .math import Vec, _lift1, _np1
 
 f32 = "f32"
 i32 = "i32"
