@@ -145,7 +145,7 @@ class _Lanes:
         self.reads = []   # (scene, flat voxel indices) read through scene.get_voxel while the writes are still in the log
 
 
-SCENES = []  # weak registry of the Scene objects alive (rollback after a failed vectorised kernel)
+UNDO = None  # while a top-level kernel call runs vectorised: (scene, voxel indices, old materials, old colours) of every applied launch
 
 
 def _flush(L):
@@ -170,8 +170,11 @@ def _flush(L):
         rev = idx[::-1]
         _, first = np.unique(rev, return_index=True)
         keep = len(idx) - 1 - first
-        scene.voxel_material.reshape(-1)[idx[keep]] = mat[keep]
-        scene.voxel_color.reshape(-1, 3)[idx[keep]] = rgb[keep]
+        vm, vc = scene.voxel_material.reshape(-1), scene.voxel_color.reshape(-1, 3)
+        if UNDO is not None:  # inside a kernel call: what the launch overwrites, for the rollback of a failed vectorised run
+            UNDO.append((scene, idx[keep], vm[idx[keep]], vc[idx[keep]]))
+        vm[idx[keep]] = mat[keep]
+        vc[idx[keep]] = rgb[keep]
 
 
 # ------------------------------------------------------------------------------------------ masks and selects
@@ -932,16 +935,22 @@ def vectorise(fn):
 
 
 def _snapshot():
-    return [(s, s.voxel_material.copy(), s.voxel_color.copy()) for s in (r() for r in SCENES) if s is not None], (RNG.launch, RNG.ctr, RNG.base, RNG.depth)
+    """Start of a top-level kernel call: the applied launches are recorded from here on (an undo log, not a copy of the grid)."""
+    global UNDO
+    UNDO = []
+    return (RNG.launch, RNG.ctr, RNG.base, RNG.depth)
 
 
 def _restore(snap):
-    global LANES
+    """Undo every launch the failed vectorised run has applied (newest first) and put the random stream back. Writes the
+    kernel issued directly from plain code are not undone: the sequential re-run issues them again, in the same order."""
+    global LANES, UNDO
     LANES = None
-    for s, mat, col in snap[0]:
-        s.voxel_material[...] = mat
-        s.voxel_color[...] = col
-    RNG.launch, RNG.ctr, RNG.base, RNG.depth = snap[1]
+    for scene, idx, mat, rgb in reversed(UNDO or []):
+        scene.voxel_material.reshape(-1)[idx] = mat
+        scene.voxel_color.reshape(-1, 3)[idx] = rgb
+    UNDO = None
+    RNG.launch, RNG.ctr, RNG.base, RNG.depth = snap
 
 
 _DEPTH = [0]
@@ -962,10 +971,13 @@ def decorate(fn, is_kernel):
     def entry(*a, **k):
         if LANES is not None or _DEPTH[0] > 0:
             return simd(True if LANES is None else LANES.all, *a, **k)  # (a direct call from plain code inside a lane context cannot happen: calls are rewritten)
+        global UNDO
         snap = _snapshot()
         _DEPTH[0] += 1
         try:
-            return simd(True, *a, **k)
+            r = simd(True, *a, **k)
+            UNDO = None
+            return r
         except Exception as e:  # noqa: BLE001 - anything the masked form cannot do: the plain function can
             _restore(snap)
             if fn.__name__ not in _WARNED:

@@ -154,10 +154,6 @@ class Scene:
         self._clouds = False
         self.last_image = None
         self.last_stats = None
-        if _vz is not None:
-            import weakref
-
-            _vz.SCENES[:] = [r for r in _vz.SCENES if r() is not None] + [weakref.ref(self)]
 
     # ------------------------------------------------------------------ voxel authoring
     @staticmethod
